@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Benchmark of the ReLU-QP solve path on B200 (the contract the driver depends on).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload mpc_single|large_qp|mpc_batched]
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+  mpc_single  (default; BASELINE.json configs[1]) one cold solve of a random linear-MPC QP
+              (nx=12 nu=4 horizon 20 -> 320 variables, 320 constraints, D=960, fp64); the QP
+              instance (initial state x0 -> l, u) changes every step.  N>1: N independent
+              replicas, one per GPU ("replicas only": a single QP does not shard).
+  large_qp    (configs[2]) one cold solve of rand_qp(2000, 500, 500) (D=4000) in fp32.
+  mpc_batched (configs[3]) 4096 MPC QPs sharing W per GPU in one batched solve; N>1 shards
+              columns across GPUs (weak scaling), no data-path collective.
+
+Printed JSON (one line, rank 0): metric qp_solves_per_sec, value = whole-job solves/s with all
+inputs resident in HBM when the timed region starts (CUDA events around each launch, L2 flushed
+between steps), e2e = the same through the public Python API with HOST inputs (numpy l, u in,
+x out; wall clock incl. H2D/D2H), roofline for the dominant kernel, cpu_baseline = the CPU
+oracle (torch-CPU restatement of the reference, de-aliased) on this box's host cores.
+
+--impl reference times that CPU oracle alone on the same workload (the reference itself is
+Python + torch on CPU; /root/reference does not exist on the GPU box, so its restatement in
+oracle/ is what runs; kind "port").
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(REPO, "reluqp-py_b200"), REPO):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+L2_FLUSH_BYTES = 512 << 20
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]),
+                    bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(object):
+    """Samples SM clock and throttle reasons during the timed region (nvidia-smi -lms)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(power) if power else None, samples=len(sm), reasons=sorted(reasons))
+
+
+# ------------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------------
+def make_workload(name, n_instances=64):
+    """Returns dict(problem=(H,g,A,l0,u0), L, U, dtype, label, setup kwargs)."""
+    from reluqp import utils
+    from reluqp.mpc import RandomLinMPC
+    if name in ("mpc_single", "mpc_batched"):
+        plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+        nb = n_instances if name == "mpc_single" else 4096
+        X0 = plant.sample_x0(nb)
+        L, U = plant.bounds(X0)
+        return dict(problem=(plant.H, plant.g, plant.A, L[0], U[0]), L=L, U=U, dtype=torch.float64,
+                    label="random linear MPC nx=12 nu=4 horizon=20 (nvar=320, nc=320, D=960), "
+                          "x0~N(0,I), u_max=0.05, eps_abs=1e-3, cold start" +
+                          ("" if name == "mpc_single" else ", 4096 QPs sharing W per GPU"),
+                    kw=dict())
+    if name == "large_qp":
+        H, g, A, l, u, _ = utils.rand_qp(2000, 500, 500, seed=0, compute_sol=False)
+        return dict(problem=(H, g, A, l, u), L=l[None, :], U=u[None, :], dtype=torch.float32,
+                    label="rand_qp(nx=2000, n_eq=500, n_ineq=500, seed=0) D=4000, fp32 iterate on "
+                          "fp64-formed matrices, eps_abs=1e-3, cold start", kw=dict())
+    raise SystemExit("unknown workload " + name)
+
+
+def algorithmic_bytes(nx, nc, elem, iters, checks):
+    """per ADMM iteration s*(D^2 + 3D + 2nc); per check s*(nx^2 + 2 nc nx)."""
+    D = nx + 2 * nc
+    return elem * (iters * (D * D + 3 * D + 2 * nc) + checks * (nx * nx + 2 * nc * nx))
+
+
+def cpu_oracle_run(wl, n_solves, n_warm, threads=None):
+    """Time the CPU oracle on the same QP instances; returns (solves/s, seconds/solve list, iters)."""
+    from oracle import reluqp_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    H, g, A, l, u = wl["problem"]
+    kw = dict(wl["kw"])
+    if wl["dtype"] == torch.float32:
+        kw.update(precision=torch.float32, setup_precision=torch.float64)
+    t0 = time.perf_counter()
+    s = O.OracleSolver(H, g, A, l, u, warm_starting=False, **kw)
+    setup_s = time.perf_counter() - t0
+    L, U = wl["L"], wl["U"]
+    times, iters = [], []
+    for i in range(n_warm + n_solves):
+        j = i % L.shape[0]
+        s.update(l=L[j], u=U[j])
+        t0 = time.perf_counter()
+        r = s.solve()
+        dt = time.perf_counter() - t0
+        if i >= n_warm:
+            times.append(dt)
+            iters.append(r.iter)
+    return len(times) / sum(times), times, iters, setup_s
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port) on this box's host cores."""
+    if rank != 0:
+        return
+    wl = make_workload(args.workload if args.workload != "mpc_batched" else "mpc_batched")
+    per_step = 1 if args.workload != "mpc_batched" else 8     # bounded sample of the 4096-QP batch
+    n = max(1, args.steps) * per_step
+    nw = max(1, args.warmup) * per_step
+    if args.workload == "large_qp":
+        n, nw = min(n, 5), min(nw, 2)
+    sps, times, iters, setup_s = cpu_oracle_run(wl, n, nw)
+    cores = torch.get_num_threads()
+    sample = "{} cold solves ({} warm-up) of: {}".format(len(times), nw, wl["label"])
+    line = dict(metric="qp_solves_per_sec", value=sps, unit="solves/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * per_step / sps if args.workload != "mpc_batched" else
+                1e3 * 4096 / sps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64" if wl["dtype"] == torch.float64 else "f32", data="synthetic", impl="reference",
+                config=dict(workload=args.workload, description=wl["label"]),
+                cpu_baseline=dict(value=sps, unit="solves/s", cores=cores, kind="port", sample=sample,
+                                  us_per_admm_iter=1e6 * sum(times) / max(1, sum(iters)),
+                                  setup_s=setup_s, host_cpus=os.cpu_count()),
+                e2e=dict(value=sps, unit="solves/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mpc_single", choices=["mpc_single", "large_qp", "mpc_batched"])
+    ap.add_argument("--grid", type=int, default=0)
+    ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--w-residency", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from reluqp import _cabi, reluqpth
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the solve path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    if args.workload == "mpc_batched":
+        from bench_batched import run_batched            # separate module: batched path
+        run_batched(args, rank, world, dev)
+        return
+
+    wl = make_workload(args.workload)
+    elem = 8 if wl["dtype"] == torch.float64 else 4
+    tuning = {k: v for k, v in dict(grid=args.grid, block=args.block, w_residency=args.w_residency).items() if v}
+    m = reluqpth.ReLU_QP()
+    m.setup(*wl["problem"], device=dev, precision=wl["dtype"], warm_starting=False, **wl["kw"], **tuning)
+    nx, nc = m.QP.nx, m.QP.nc
+    eng = m._engine
+    Ld = torch.as_tensor(wl["L"], dtype=wl["dtype"], device=dev)
+    Ud = torch.as_tensor(wl["U"], dtype=wl["dtype"], device=dev)
+    ninst = Ld.shape[0]
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    v = torch.zeros(nx + 2 * nc, dtype=wl["dtype"], device=dev)
+    rho0 = m.rho_ind
+
+    def resident_step(j, ev0, ev1):
+        """inputs already in HBM: select instance j (device copy), flush L2, time the solve launch"""
+        m.QP.l.copy_(Ld[j])
+        m.QP.u.copy_(Ud[j])
+        v.zero_()
+        flush.fill_(j & 0xff)
+        ev0.record()
+        eng.launch(v, rho0)
+        ev1.record()
+        r = eng.finish()
+        return int(r.iter), int(r.n_checks), int(r.status), (int(r.t_end_ns) - int(r.t_begin_ns)) * 1e-3
+
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for w in range(args.warmup):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        resident_step(w % ninst, e0, e1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    iters, checks, statuses, loop_us = [], [], [], []
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        it, ck, stt, lus = resident_step((args.warmup + s) % ninst, *evs[s])
+        iters.append(it); checks.append(ck); statuses.append(stt); loop_us.append(lus)
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    if world > 1:
+        dist.barrier()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = sum(step_ms)
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.item())
+
+    # ---- e2e through the public API with host buffers (numpy l,u in; x out on the host)
+    Lh, Uh = wl["L"], wl["U"]
+    h2d = 2 * nc * elem
+    d2h = nx * elem + 88
+    for w in range(args.warmup):
+        m.update(l=Lh[w % ninst], u=Uh[w % ninst]); m.solve().x.cpu()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        j = (args.warmup + s) % ninst
+        m.update(l=Lh[j], u=Uh[j])
+        res = m.solve()
+        xh = res.x.cpu()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s_max = float(te.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    # measured L2 / HBM read bandwidth with the library's own probe (for context in the roofline)
+    probe = {}
+    try:
+        lib = _cabi.load()
+        import ctypes as C
+        for tag, nbytes in (("l2_read_gbs", 48 << 20), ("hbm_read_gbs", 2 << 30)):
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            buf.zero_()
+            ms = C.c_float(0)
+            best = 0.0
+            for _ in range(3):
+                _cabi.check(lib.rqp_probe_bandwidth(buf.data_ptr(), nbytes, 10, C.byref(ms),
+                                                    torch.cuda.current_stream().cuda_stream), "probe")
+                best = max(best, nbytes / (ms.value * 1e-3) / 1e9)
+            probe[tag] = best
+            del buf
+    except Exception as exc:  # measurement helper only
+        probe["error"] = str(exc)
+
+    alg_bytes = [algorithmic_bytes(nx, nc, elem, it, ck) for it, ck in zip(iters, checks)]
+    achieved = sum(alg_bytes) / (total_ms * 1e-3) / 1e9
+    launch = m.last_launch
+    solves = args.steps * world
+    value = solves / (total_ms_max * 1e-3)
+    line = dict(
+        metric="qp_solves_per_sec", value=value, unit="solves/s", n_gpus=world, steps=args.steps,
+        warmup=args.warmup, ms_per_step=total_ms_max / args.steps, higher_is_better=True, scaling="weak",
+        vs_baseline=None, dtype="f64" if elem == 8 else "f32", data="synthetic",
+        config=dict(workload=args.workload, description=wl["label"], instances=ninst,
+                    multi_gpu="replicas only" if world > 1 else "single GPU",
+                    l2="flushed between steps (512 MiB fill)", timing="CUDA events around each solve launch, summed",
+                    launch=dict(grid=launch["grid"], block=launch["block"], rows_per_cta=launch["rows_per_cta"],
+                                rows_in_smem=launch["rows_in_smem"])),
+        us_per_admm_iter=1e3 * total_ms / sum(iters),
+        us_per_admm_iter_in_kernel=sum(loop_us) / sum(iters),
+        iters_per_solve=sum(iters) / len(iters),
+        all_solved=all(s == 0 for s in statuses),
+        wall_s_timed_region=t_wall,
+        roofline=dict(bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s",
+                      frac=achieved / peaks["hbm_gbs"], traffic=None, peak_source=peaks["source"],
+                      note="HBM-equivalent: W_rho stays in shared memory / L2 across iterations, so achieved "
+                           "can exceed the DRAM copy peak; algorithmic bytes = s*(D^2+3D+2nc) per iteration "
+                           "+ s*(nx^2+2*nc*nx) per check", **probe),
+        e2e=dict(value=solves / e2e_s_max, unit="solves/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                 ms_per_step=1e3 * e2e_s_max / args.steps,
+                 api="ReLU_QP.update(l=numpy, u=numpy); ReLU_QP.solve(); results.x.cpu()"),
+        gpu_launches=args.steps,
+        clocks=clocks,
+    )
+    if not args.no_cpu_baseline:
+        n_cpu = 40 if args.workload == "mpc_single" else 3
+        sps, times, cit, setup_s = cpu_oracle_run(wl, n_cpu, 10 if args.workload == "mpc_single" else 1)
+        line["cpu_baseline"] = dict(
+            value=sps, unit="solves/s", cores=torch.get_num_threads(), kind="port",
+            sample="{} cold solves of the same workload through oracle/reluqp_oracle.py (torch CPU, "
+                   "de-aliased reference loop)".format(len(times)),
+            us_per_admm_iter=1e6 * sum(times) / sum(cit), iters_per_solve=sum(cit) / len(cit),
+            setup_s=setup_s, host_cpus=os.cpu_count())
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

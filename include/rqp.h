@@ -1,0 +1,196 @@
+/*
+ * rqp.h — C ABI of the B200-native ReLU-QP solve path (librqp.so).
+ *
+ * The reference (gstoica27/ReLUQP-py) has NO native boundary: its hot path is a Python loop
+ * over torch ops.  This header is the seam a maintainer would bind instead of that loop; each
+ * entry point cites the reference lines it replaces (paths relative to
+ * ReLU-QP-py/reluqp/).  All pointers are plain DEVICE pointers unless a name ends in _host;
+ * no torch types cross the ABI.  Every function returns 0 (RQP_OK) or a negative rqp_status;
+ * nothing throws or aborts.  Non-convergence is not an error: it is result.status ==
+ * RQP_STATUS_MAX_ITER ("max_iters_reached", reluqpth.py:245).
+ *
+ * Ownership: the caller (PyTorch) allocates and owns every buffer, including the workspace.
+ * The library keeps no pointer past the call that received it.  A workspace must be zero
+ * filled once before its first use and belongs to one in-flight solve at a time.
+ * Streams: work is enqueued on the cudaStream_t passed as `void* stream`; no call
+ * synchronises the host except rqp_query and rqp_probe_bandwidth.
+ */
+#ifndef RQP_H_
+#define RQP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RQP_ABI_VERSION 1
+
+typedef enum rqp_dtype { RQP_F32 = 0, RQP_F64 = 1 } rqp_dtype;
+
+typedef enum rqp_status {
+    RQP_OK = 0,
+    RQP_ERR_BAD_ARG = -1,       /* null pointer, negative size, misaligned leading dimension */
+    RQP_ERR_UNSUPPORTED = -2,   /* shape / dtype / device this build cannot run            */
+    RQP_ERR_CUDA = -3,          /* a CUDA runtime call failed (see rqp_last_cuda_error)     */
+    RQP_ERR_WORKSPACE = -4,     /* workspace too small                                      */
+    RQP_ERR_LAUNCH_TOO_LARGE = -5, /* cooperative grid does not fit on the device          */
+    RQP_ERR_WATCHDOG = -6       /* in-kernel wait exceeded the watchdog (reported in result.error) */
+} rqp_status;
+
+/* result.status values; the Python layer maps them to the reference's strings
+ * (reluqpth.py:236 "solved", :245 "max_iters_reached"). */
+#define RQP_STATUS_SOLVED 0
+#define RQP_STATUS_MAX_ITER 1
+#define RQP_STATUS_RUNNING 2    /* batched: column still active (never returned to users) */
+
+typedef struct rqp_caps {
+    int32_t abi_version;
+    int32_t cc_major, cc_minor;
+    int32_t sm_count;
+    int32_t max_smem_per_block;     /* opt-in bytes */
+    int32_t cooperative_launch;
+    int64_t l2_bytes;
+    int64_t global_mem_bytes;
+} rqp_caps;
+
+/*
+ * Problem data: what ReLU_Layer.setup_matrices builds (reluqpth.py:40-78) plus the QP itself
+ * (classes.py:23-30).  Layout in HBM, all row-major, element type = dtype:
+ *   W    [n_rho][D][ldw]   D = nx + 2 nc; ldw >= D, ldw % 4 == 0; columns D..ldw-1 are ZERO
+ *   b    [n_rho][D]        b_rho = B_rho g (reluqpth.py:77)
+ *   H    [nx][nx]   A [nc][nx]   AT [nx][nc] (= A transposed, so A'lam reads rows)
+ *   g    [nx]       l,u [nc] (+-inf allowed)       rhos [n_rho] ascending
+ */
+typedef struct rqp_problem {
+    int32_t dtype;              /* rqp_dtype */
+    int32_t nx, nc, n_rho;
+    int64_t ldw;
+    const void* W;
+    const void* b;
+    const void* H;
+    const void* A;
+    const void* AT;
+    const void* g;
+    const void* l;
+    const void* u;
+    const void* rhos;
+} rqp_problem;
+
+/* Settings the loop reads (classes.py:32-65; eps_rel is additive, 0 = reference behaviour). */
+typedef struct rqp_settings {
+    int32_t max_iter;
+    int32_t check_interval;
+    int32_t adaptive_rho;       /* 0: never check, run max_iter iterations (reluqpth.py:218) */
+    int32_t reserved0;
+    double eps_abs;
+    double eps_rel;
+    double rho_min, rho_max;
+    double adaptive_rho_tolerance;
+    /* launch tuning; 0 = choose automatically */
+    int32_t grid;               /* number of CTAs (<= SM count)                         */
+    int32_t block;              /* threads per CTA: 256 or 512                          */
+    int32_t w_residency;        /* 0 auto, 1 force shared-memory resident, 2 force streamed */
+    int32_t watchdog_ms;        /* 0 = 4000 ms per in-kernel wait                       */
+} rqp_settings;
+
+/* Solver state carried across solves (reluqpth.py:148-153: `output` and `rho_ind`). */
+typedef struct rqp_state {
+    void* v;                    /* [D] in/out: stacked [x; z; lambda], updated in place  */
+    int32_t rho_ind;            /* in: start index into rhos                             */
+    uint32_t epoch;             /* in/out: exchange-flag epoch of this workspace; start at 1
+                                   after zero-filling the workspace and pass the returned
+                                   value to the next call; re-zero the workspace and restart
+                                   at 1 once it exceeds 0x70000000 */
+} rqp_state;
+
+/* Written to DEVICE memory by the kernel (copy it back after the stream is synchronised).
+ * Field meaning = Info in classes.py:67-88. */
+typedef struct rqp_result {
+    int32_t iter;
+    int32_t status;             /* RQP_STATUS_*                                          */
+    int32_t rho_ind;            /* index after the solve (already moved)   */
+    int32_t error;              /* 0 or RQP_ERR_WATCHDOG                                 */
+    double pri_res, dua_res, rho_estimate, obj_val;
+    int32_t n_checks;
+    int32_t n_rho_switches;
+    uint64_t t_begin_ns, t_end_ns; /* %globaltimer at loop entry / exit (CTA 0)          */
+    int32_t grid, block, rows_per_cta, rows_in_smem; /* what actually ran                */
+} rqp_result;
+
+/* One record per residual check: {k, rho_ind_after, pri, dua, rho_estimate} as 5 doubles. */
+#define RQP_TRACE_STRIDE 5
+
+int rqp_query(int device, rqp_caps* caps);
+
+/* Bytes of workspace rqp_solve needs for this problem (exchange cells + reduction slots). */
+int rqp_workspace_size(const rqp_problem* prob, const rqp_settings* stng, size_t* bytes);
+
+/*
+ * The whole body of ReLU_QP.solve's loop (reluqpth.py:214-241) and its fall-through
+ * (:243-248) as ONE persistent cooperative kernel: per iteration
+ * v <- clamp_[nx,nx+nc)(W_rho v + b_rho; l, u) (ReLU_Layer.jit_forward, reluqpth.py:84-89,
+ * de-aliased), every check_interval iterations the residuals / rho estimate
+ * (compute_residuals, :307-318), the +-1 rho-index move (:223-227) and the termination test
+ * (:233), and at the end the objective (compute_J, :320-322).
+ * result_dev, trace_dev (may be NULL; trace_cap records) are device pointers.
+ */
+int rqp_solve(const rqp_problem* prob, const rqp_settings* stng, rqp_state* state,
+              rqp_result* result_dev, double* trace_dev, int32_t trace_cap,
+              void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * ReLU_QP.update's bias refresh (reluqpth.py:166-169): b[k] = Bmat[k] g for every rho in one
+ * launch.  Bmat [n_rho][D][nx] row-major, g [nx], b_out [n_rho][D].
+ */
+int rqp_update_bias(int32_t dtype, int32_t n_rho, int32_t D, int32_t nx, const void* Bmat,
+                    const void* g, void* b_out, void* stream);
+
+/*
+ * Batched solve: B independent QPs that share H, A (hence every W_rho) and differ in l, u
+ * (and optionally g).  Column j is DEFINED as the reference's single cold solve of QP j
+ * (update(l_j,u_j[,g_j]) then solve(), reluqpth.py:159-183, 201-249).  State is column
+ * contiguous: V [B][ldv], L/U [B][nc], G [B][nx] or NULL (then prob->g / prob->b are used).
+ * Per-column outputs are device arrays of length B.
+ */
+typedef struct rqp_batch {
+    int32_t B;                  /* number of QPs on this device                          */
+    int32_t ldv;                /* leading dimension of V rows (>= D, % 4 == 0)          */
+    void* V;                    /* [B][ldv] in/out                                       */
+    const void* L;              /* [B][nc]                                               */
+    const void* U;              /* [B][nc]                                               */
+    const void* G;              /* [B][nx] or NULL                                       */
+    const void* Bmat;           /* [n_rho][D][nx], needed only when G != NULL            */
+    int32_t* rho_ind;           /* [B] in/out                                            */
+    int32_t* iter;              /* [B] out                                               */
+    int32_t* status;            /* [B] out RQP_STATUS_*                                  */
+    void* pri_res;              /* [B] out (dtype)                                       */
+    void* dua_res;              /* [B] out                                               */
+    void* rho_estimate;         /* [B] out                                               */
+} rqp_batch;
+
+int rqp_batch_workspace_size(const rqp_problem* prob, const rqp_settings* stng, int32_t B,
+                             size_t* bytes);
+
+/* sweeps_host (may be NULL) receives the number of check windows that were run. */
+int rqp_solve_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_batch* batch,
+                      void* workspace, size_t workspace_bytes, int32_t* sweeps_host,
+                      void* stream);
+
+/*
+ * Measurement helper for bench.py's roofline denominators: reads `bytes` of `buf` `reps`
+ * times with 128-bit loads from every SM and reports the average milliseconds per pass
+ * (synchronises).  A buffer smaller than L2 measures L2 bandwidth, a larger one HBM.
+ */
+int rqp_probe_bandwidth(const void* buf, size_t bytes, int32_t reps, float* ms_per_pass,
+                        void* stream);
+
+const char* rqp_strerror(int code);
+/* cudaGetErrorString of the last CUDA failure seen by this library on this thread. */
+const char* rqp_last_cuda_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RQP_H_ */

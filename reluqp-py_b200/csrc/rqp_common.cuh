@@ -1,0 +1,269 @@
+// Device-side helpers shared by the ReLU-QP kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rqp.h"
+
+namespace rqp {
+
+// ---------------------------------------------------------------------------------------------
+// Error plumbing for the host side of the ABI.
+// ---------------------------------------------------------------------------------------------
+void set_last_cuda_error(cudaError_t e);
+#define RQP_CUDA_TRY(expr)                         \
+    do {                                           \
+        cudaError_t e__ = (expr);                  \
+        if (e__ != cudaSuccess) {                  \
+            ::rqp::set_last_cuda_error(e__);       \
+            return RQP_ERR_CUDA;                   \
+        }                                          \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Small device utilities.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// torch.max / vector_norm(inf) propagate NaN; fmax() would drop it.
+template <typename T>
+__device__ __forceinline__ T nanmax(T a, T b) {
+    return (a != a) ? a : ((b != b) ? b : (a > b ? a : b));
+}
+// torch.clamp(x, lo, hi): NaN stays NaN, lo > hi gives hi.
+template <typename T>
+__device__ __forceinline__ T clamp_keep_nan(T x, T lo, T hi) {
+    x = (x < lo) ? lo : x;
+    x = (x > hi) ? hi : x;
+    return x;
+}
+template <typename T>
+__device__ __forceinline__ T absval(T x) { return x < T(0) ? -x : ((x == T(0)) ? T(0) : x); }
+template <>
+__device__ __forceinline__ float absval<float>(float x) { return fabsf(x); }
+template <>
+__device__ __forceinline__ double absval<double>(double x) { return fabs(x); }
+
+__device__ __forceinline__ float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += shfl_xor(v, m);
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_nanmax(T v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v = nanmax(v, shfl_xor(v, m));
+    return v;
+}
+
+// Reduce R (= 8) per-lane values across the 32 lanes of a warp with 4+2+1+1+1 shuffles instead
+// of 8*5: at each of the first three steps a lane hands half of its values to its partner and
+// keeps the other half.  On return lanes with (lane & 3) == 0 hold in a[0] the full sum of
+// value index (lane >> 2).  The summation tree is fixed, so results are run-to-run identical.
+template <typename T>
+__device__ __forceinline__ void warp_multi_reduce8(T (&a)[8], int lane) {
+    {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            T send = hi ? a[j] : a[j + 4];
+            T keep = hi ? a[j + 4] : a[j];
+            a[j] = keep + shfl_xor(send, 16);
+        }
+    }
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            T send = hi ? a[j] : a[j + 2];
+            T keep = hi ? a[j + 2] : a[j];
+            a[j] = keep + shfl_xor(send, 8);
+        }
+    }
+    {
+        const bool hi = lane & 4;
+        T send = hi ? a[0] : a[1];
+        T keep = hi ? a[1] : a[0];
+        a[0] = keep + shfl_xor(send, 4);
+    }
+    a[0] += shfl_xor(a[0], 2);
+    a[0] += shfl_xor(a[0], 1);
+    // value index held: bit0 <- lane bit2, bit1 <- lane bit3, bit2 <- lane bit4  == (lane >> 2)
+}
+
+// ---------------------------------------------------------------------------------------------
+// Flagged exchange cells ("LL" style: payload and flag travel in the same 8-byte word, so a
+// reader that sees the flag has the payload; no separate barrier or fence is needed).
+// One cell per state element.  float: one u64 {flag:32 | bits:32}.  double: two u64
+// {flag | lo32}, {flag | hi32}; each 8-byte word is written/read by a single scalar-atomic
+// access inside a 16-byte vector op.
+// A "vector column" is 16 bytes of state (4 floats / 2 doubles) = 4 words = 32 bytes of cells.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t a) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(a) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_u64x2(uint64_t* p, uint64_t a, uint64_t b) {
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ld_relaxed_u64x2(const uint64_t* p, uint64_t& a, uint64_t& b) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <typename T>
+struct Cell;
+
+template <>
+struct Cell<float> {
+    static constexpr int kVec = 4;            // elements per 16-byte vector column
+    static constexpr int kWordsPerElem = 1;
+    static __device__ __forceinline__ void publish(uint64_t* cells, int elem, float v, uint32_t flag) {
+        st_relaxed_u64(cells + elem, (uint64_t(flag) << 32) | uint64_t(__float_as_uint(v)));
+    }
+    // words w[0..3] of one vector column -> 4 floats; returns a bit mask of elements whose flag matched
+    static __device__ __forceinline__ uint32_t unpack(const uint64_t (&w)[4], uint32_t flag, float (&out)[4]) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            out[e] = __uint_as_float(uint32_t(w[e]));
+            m |= (uint32_t(w[e] >> 32) == flag) ? (1u << e) : 0u;
+        }
+        return m;
+    }
+};
+
+template <>
+struct Cell<double> {
+    static constexpr int kVec = 2;
+    static constexpr int kWordsPerElem = 2;
+    static __device__ __forceinline__ void publish(uint64_t* cells, int elem, double v, uint32_t flag) {
+        const uint64_t bits = uint64_t(__double_as_longlong(v));
+        const uint64_t f = uint64_t(flag) << 32;
+        st_relaxed_u64x2(cells + 2 * size_t(elem), f | (bits & 0xffffffffull), f | (bits >> 32));
+    }
+    static __device__ __forceinline__ uint32_t unpack(const uint64_t (&w)[4], uint32_t flag, double (&out)[2]) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const uint64_t bits = (w[2 * e] & 0xffffffffull) | (w[2 * e + 1] << 32);
+            out[e] = __longlong_as_double((long long)bits);
+            const bool ok = (uint32_t(w[2 * e] >> 32) == flag) && (uint32_t(w[2 * e + 1] >> 32) == flag);
+            m |= ok ? (1u << e) : 0u;
+        }
+        return m;
+    }
+};
+
+// Bounded spin: returns false when the watchdog expires or another CTA raised the abort flag.
+struct Watchdog {
+    uint64_t limit_ns;
+    uint32_t* abort_flag;
+    uint64_t t0;
+    uint32_t spins;
+    __device__ __forceinline__ void arm() { spins = 0; t0 = 0; }
+    __device__ __forceinline__ bool expired() {
+        if ((++spins & 0xffu) != 0u) return false;
+        if (ld_relaxed_u32(abort_flag) != 0u) return true;
+        const uint64_t now = globaltimer_ns();
+        if (t0 == 0) { t0 = now; return false; }
+        if (now - t0 > limit_ns) { atomicExch(abort_flag, 1u); return true; }
+        return false;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// 128-bit register vectors.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<float> {
+    float4 q;
+    __device__ __forceinline__ float dot(const float (&v)[4], float acc) const {
+        acc = fmaf(q.x, v[0], acc);
+        acc = fmaf(q.y, v[1], acc);
+        acc = fmaf(q.z, v[2], acc);
+        acc = fmaf(q.w, v[3], acc);
+        return acc;
+    }
+    static __device__ __forceinline__ Vec16 ldg(const float* p) {
+        Vec16 r;
+        r.q = __ldg(reinterpret_cast<const float4*>(p));
+        return r;
+    }
+    static __device__ __forceinline__ Vec16 lds(const float* p) {
+        Vec16 r;
+        r.q = *reinterpret_cast<const float4*>(p);
+        return r;
+    }
+};
+template <>
+struct Vec16<double> {
+    double2 q;
+    __device__ __forceinline__ double dot(const double (&v)[2], double acc) const {
+        acc = fma(q.x, v[0], acc);
+        acc = fma(q.y, v[1], acc);
+        return acc;
+    }
+    static __device__ __forceinline__ Vec16 ldg(const double* p) {
+        Vec16 r;
+        r.q = __ldg(reinterpret_cast<const double2*>(p));
+        return r;
+    }
+    static __device__ __forceinline__ Vec16 lds(const double* p) {
+        Vec16 r;
+        r.q = *reinterpret_cast<const double2*>(p);
+        return r;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) for staging a W row slab into
+// shared memory.  Single-CTA use: the shared::cluster destination is this CTA's own window.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+}  // namespace rqp

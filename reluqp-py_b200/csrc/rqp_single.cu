@@ -1,0 +1,633 @@
+// Single-QP ReLU-QP solve as ONE persistent cooperative kernel (sm_100a).
+//
+// Replaces the whole Python loop of ReLU_QP.solve (reference reluqpth.py:201-249): per iteration
+//   v <- clamp_[nx,nx+nc)(W_rho v + b_rho; l, u)          (jit_forward, :84-89, de-aliased)
+// every check_interval iterations the residuals and rho estimate (compute_residuals, :307-318),
+// the +-1 rho-index move (:223-227) and the termination test (:233); at the end the objective
+// (compute_J, :320-322) and, on max_iter, the fall-through residual evaluation (:243).
+//
+// Design (DESIGN.md has the full story):
+//  * Row-slab ownership: CTA c owns rows [c*rpc, (c+1)*rpc) of W_rho.  The slab is staged once
+//    per rho into shared memory with 1-D bulk async copies (TMA engine) and reused every
+//    iteration; rows that do not fit stay in global memory and are streamed from L2/HBM with
+//    128-bit loads ("hybrid" residency).  A rho switch re-stages the slab without leaving the
+//    kernel.
+//  * Column-owner GEMV: thread t owns 16-byte vector columns t, t+NT, ... of v.  It keeps those v
+//    entries in registers and multiplies them into all rows of the slab, 8 rows at a time, so v
+//    is read once per iteration and W exactly once.  Per-row partial sums are reduced with a
+//    9-shuffle transposing tree, then across warps through shared memory in a fixed order
+//    (bit-reproducible).
+//  * Flagged-cell exchange instead of a grid barrier: every state element travels with the
+//    iteration number in the same 8-byte word (rqp_common.cuh).  A CTA publishes its rows of
+//    v_k and every thread polls exactly the cells of the columns it owns; one L2 round trip
+//    orders iteration k+1 after iteration k, with two buffers alternating.
+//  * Residual checks are distributed over all warps of the grid (one matrix row per warp-task),
+//    reduced per CTA, all-gathered through flagged cells, and every CTA then takes the SAME
+//    decision from bitwise identical numbers (rho estimate, index move, termination).
+//  * Every wait is bounded by a watchdog; on expiry the kernel exits with result.error set.
+#include <math_constants.h>
+
+#include "rqp_common.cuh"
+#include "rqp_host.h"
+
+namespace rqp {
+
+constexpr int RM = 8;  // rows per register chunk
+
+struct SingleParams {
+    const void* W;
+    const void* b;
+    const void* H;
+    const void* A;
+    const void* AT;
+    const void* g;
+    const void* l;
+    const void* u;
+    const void* rhos;
+    void* v;
+    uint64_t* vcells;   // [2][nvec*4] words
+    uint64_t* pcells;   // [2][G*8*2] words (double cells)
+    uint32_t* abort_flag;
+    rqp_result* result;
+    double* trace;
+    long long ldw;
+    double thr_p, thr_d, eps_rel, rho_min, rho_max, tol;
+    unsigned long long watchdog_ns;
+    int nx, nc, D, n_rho;
+    int rho_ind0;
+    int max_iter, check_interval, adaptive;
+    uint32_t epoch;
+    int rpc;        // rows per CTA
+    int rows_smem;  // rows of each slab resident in shared memory
+    int trace_cap;
+};
+
+template <typename T>
+__device__ __forceinline__ T t_sqrt(T x);
+template <>
+__device__ __forceinline__ float t_sqrt<float>(float x) { return sqrtf(x); }
+template <>
+__device__ __forceinline__ double t_sqrt<double>(double x) { return sqrt(x); }
+
+// 8 rows x CPT vector columns of the slab against the thread's v registers.
+template <typename T, int CPT, bool SMEM, bool FULL>
+__device__ __forceinline__ void chunk_dot(const T* __restrict__ wrow0, long long ldw, int nrows,
+                                          const int (&coff)[CPT], const T (&vv)[CPT][Cell<T>::kVec],
+                                          T (&acc)[RM]) {
+#pragma unroll
+    for (int r = 0; r < RM; ++r) acc[r] = T(0);
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+        Vec16<T> w[RM];
+#pragma unroll
+        for (int r = 0; r < RM; ++r) {
+            if (FULL || r < nrows) {
+                const T* ptr = wrow0 + (long long)r * ldw + coff[i];
+                w[r] = SMEM ? Vec16<T>::lds(ptr) : Vec16<T>::ldg(ptr);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RM; ++r) {
+            if (FULL || r < nrows) acc[r] = w[r].dot(vv[i], acc[r]);
+        }
+    }
+}
+
+struct Decision {
+    int rho_ind;
+    int done;
+    double rho, pri, dua, obj;
+};
+
+template <typename T, int CPT, int NT>
+__global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p) {
+    using C = Cell<T>;
+    constexpr int VEC = C::kVec;
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int D = p.D, nx = p.nx, nc = p.nc;
+    const long long ldw = p.ldw;
+    const int nvec = int(ldw / VEC);
+    const int G = gridDim.x;
+    const int r0 = blockIdx.x * p.rpc;
+    const int rows = min(p.rpc, D - r0);
+    const int rpc_pad = (p.rpc + RM - 1) / RM * RM;
+    const int rows_s = min(rows, p.rows_smem);  // rows of THIS slab in shared memory
+    const int nchunks = (rows + RM - 1) / RM;
+
+    const T* __restrict__ Wall = static_cast<const T*>(p.W);
+    const T* __restrict__ ball = static_cast<const T*>(p.b);
+    const T* __restrict__ rhos = static_cast<const T*>(p.rhos);
+
+    // ---- shared memory carve-up
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* Ws = reinterpret_cast<T*>(smem_raw);                    // [rows_smem][ldw]
+    T* vs = Ws + size_t(p.rows_smem) * ldw;                    // [ldw]   (check phase only)
+    T* red = vs + ldw;                                         // [2][NW][rpc_pad]
+    size_t off = (reinterpret_cast<unsigned char*>(red + 2 * NW * rpc_pad) - smem_raw + 15) & ~size_t(15);
+    double* part = reinterpret_cast<double*>(smem_raw + off);  // [NW][8]
+    double* tot = part + NW * 8;                               // [NW][8]
+    Decision* dec = reinterpret_cast<Decision*>(tot + NW * 8);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(dec + 1);
+
+    Watchdog wd{p.watchdog_ns, p.abort_flag, 0, 0};
+    const uint32_t epoch = p.epoch;
+
+    // ---- per-thread column ownership (iteration invariant)
+    int coff[CPT];        // element offset of the owned vector column inside a W row (clamped)
+    uint32_t need[CPT];   // which elements of the column are real state (not ldw padding)
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+        const int c = tid + i * NT;
+        const int nval = (c < nvec) ? max(0, min(VEC, D - c * VEC)) : 0;
+        need[i] = (1u << nval) - 1u;
+        coff[i] = min(c, nvec - 1) * VEC;
+    }
+
+    // ---- finalize-thread registers: thread t < rows owns state element r0 + t
+    const bool is_fin = tid < rows;
+    const int my_row = r0 + tid;
+    int rho_ind = p.rho_ind0;
+    T rho = rhos[rho_ind];
+    T my_b = T(0), my_lo = -CUDART_INF, my_hi = CUDART_INF, my_v = T(0);
+    if (is_fin) {
+        my_v = static_cast<const T*>(p.v)[my_row];
+        if (my_row >= nx && my_row < nx + nc) {
+            my_lo = static_cast<const T*>(p.l)[my_row - nx];
+            my_hi = static_cast<const T*>(p.u)[my_row - nx];
+        }
+        my_b = ball[size_t(rho_ind) * D + my_row];
+        C::publish(p.vcells, my_row, my_v, epoch);  // v_0 into buffer 0
+    }
+
+    // ---- stage the W slab of the current rho
+    uint32_t mbar_parity = 0;
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto stage_slab = [&](int ri) {
+        // caller guarantees every thread is past its last read of Ws (a __syncthreads)
+        if (rows_s > 0) {
+            if (tid == 0) {
+                const size_t bytes = size_t(rows_s) * ldw * sizeof(T);
+                const unsigned char* src =
+                    reinterpret_cast<const unsigned char*>(Wall + (size_t(ri) * D + r0) * ldw);
+                mbar_expect_tx(mbar, uint32_t(bytes));
+                for (size_t o = 0; o < bytes; o += 32768) {
+                    const uint32_t n = uint32_t(min(size_t(32768), bytes - o));
+                    bulk_g2s(reinterpret_cast<unsigned char*>(Ws) + o, src + o, n, mbar);
+                }
+            }
+            wd.arm();
+            bool ok = true;
+            while (!mbar_try_wait(mbar, mbar_parity)) {
+                if (wd.expired()) { ok = false; break; }
+            }
+            mbar_parity ^= 1u;
+            return ok;
+        }
+        return true;
+    };
+    bool ok = stage_slab(rho_ind);
+
+    int k = 0;
+    int n_checks = 0, n_switch = 0;
+    bool solved = false, aborted = false;
+    T pri = CUDART_NAN, dua = CUDART_NAN, obj = CUDART_NAN;
+    uint64_t t_begin = 0;
+    if (blockIdx.x == 0 && tid == 0) t_begin = globaltimer_ns();
+
+    // Residual evaluation on v_k (flag fk in vcells buffer k&1).  final_pass: no index move, no
+    // termination test (reluqpth.py:243).  Returns false on watchdog abort (uniform over the CTA).
+    auto residual_pass = [&](int kk, uint32_t pflag, bool final_pass) -> bool {
+        const uint64_t* vslot = p.vcells + size_t(kk & 1) * nvec * 4;
+        const uint32_t fk = epoch + uint32_t(kk);
+        bool good = true;
+        // 1. stage v_k into shared memory
+        wd.arm();
+        for (int c = tid; c < nvec; c += NT) {
+            const int nval = max(0, min(VEC, D - c * VEC));
+            const uint32_t nd = (1u << nval) - 1u;
+            T out[VEC];
+            uint32_t m = 0;
+            while (good) {
+                uint64_t w[4];
+                ld_relaxed_u64x2(vslot + size_t(c) * 4, w[0], w[1]);
+                ld_relaxed_u64x2(vslot + size_t(c) * 4 + 2, w[2], w[3]);
+                m = C::unpack(w, fk, out);
+                if ((m & nd) == nd) break;
+                if (wd.expired()) good = false;
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) vs[c * VEC + e] = ((nd >> e) & 1u) ? out[e] : T(0);
+        }
+        if (__syncthreads_or(!good)) return false;
+
+        // 2. one matrix row per warp-task, grid-strided
+        const T* __restrict__ Hm = static_cast<const T*>(p.H);
+        const T* __restrict__ Am = static_cast<const T*>(p.A);
+        const T* __restrict__ ATm = static_cast<const T*>(p.AT);
+        const T* __restrict__ gv = static_cast<const T*>(p.g);
+        const T* xs = vs;
+        const T* zs = vs + nx;
+        const T* ls = vs + nx + nc;
+        T m0 = T(0), m1 = T(0), m2 = T(0), m3 = T(0), m4 = T(0), m5 = T(0), m6 = T(0), osum = T(0);
+        const int GW = G * NW;
+        for (int i = blockIdx.x * NW + warp; i < nc + nx; i += GW) {
+            if (i < nc) {
+                const T* __restrict__ Ar = Am + size_t(i) * nx;
+                T s0 = T(0), s1 = T(0);
+                int j = lane;
+                for (; j + 32 < nx; j += 64) {
+                    s0 = fma(__ldg(Ar + j), xs[j], s0);
+                    s1 = fma(__ldg(Ar + j + 32), xs[j + 32], s1);
+                }
+                if (j < nx) s0 = fma(__ldg(Ar + j), xs[j], s0);
+                const T t1 = warp_sum(s0 + s1);
+                const T zi = zs[i];
+                m0 = nanmax(m0, absval(t1 - zi));
+                m1 = nanmax(m1, absval(t1));
+                m2 = nanmax(m2, absval(zi));
+            } else {
+                const int ii = i - nc;
+                const T* __restrict__ Hr = Hm + size_t(ii) * nx;
+                const T* __restrict__ Tr = ATm + size_t(ii) * nc;
+                T s0 = T(0), s1 = T(0), q0 = T(0), q1 = T(0);
+                int j = lane;
+                for (; j + 32 < nx; j += 64) {
+                    s0 = fma(__ldg(Hr + j), xs[j], s0);
+                    s1 = fma(__ldg(Hr + j + 32), xs[j + 32], s1);
+                }
+                if (j < nx) s0 = fma(__ldg(Hr + j), xs[j], s0);
+                j = lane;
+                for (; j + 32 < nc; j += 64) {
+                    q0 = fma(__ldg(Tr + j), ls[j], q0);
+                    q1 = fma(__ldg(Tr + j + 32), ls[j + 32], q1);
+                }
+                if (j < nc) q0 = fma(__ldg(Tr + j), ls[j], q0);
+                const T t2 = warp_sum(s0 + s1);
+                const T t3 = warp_sum(q0 + q1);
+                const T gi = __ldg(gv + ii);
+                m3 = nanmax(m3, absval((t2 + t3) + gi));
+                m4 = nanmax(m4, absval(t2));
+                m5 = nanmax(m5, absval(t3));
+                m6 = nanmax(m6, absval(gi));
+                osum += xs[ii] * (T(0.5) * t2 + gi);
+            }
+        }
+        // 3. CTA reduction, publish 8 partials as double cells
+        if (lane == 0) {
+            double* pw = part + warp * 8;
+            pw[0] = double(m0); pw[1] = double(m1); pw[2] = double(m2); pw[3] = double(m3);
+            pw[4] = double(m4); pw[5] = double(m5); pw[6] = double(m6); pw[7] = double(osum);
+        }
+        __syncthreads();
+        uint64_t* pslot = p.pcells + size_t(n_checks & 1) * size_t(G) * 16;
+        if (tid < 8) {
+            double a = part[tid];
+            for (int w = 1; w < NW; ++w) {
+                const double bq = part[w * 8 + tid];
+                a = (tid == 7) ? (a + bq) : nanmax(a, bq);
+            }
+            Cell<double>::publish(pslot, blockIdx.x * 8 + tid, a, pflag);
+        }
+        // 4. all-gather: thread t folds quantity q = t & 7 over CTAs (t >> 3) + m * NT/8
+        {
+            const int q = tid & 7;
+            double a = 0.0;
+            wd.arm();
+            for (int c = tid >> 3; c < G; c += NT / 8) {
+                double val = 0.0;
+                while (good) {
+                    uint64_t w0, w1;
+                    ld_relaxed_u64x2(pslot + (size_t(c) * 8 + q) * 2, w0, w1);
+                    if (uint32_t(w0 >> 32) == pflag && uint32_t(w1 >> 32) == pflag) {
+                        val = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+                        break;
+                    }
+                    if (wd.expired()) good = false;
+                }
+                a = (q == 7) ? (a + val) : nanmax(a, val);
+            }
+            // lanes with equal (lane & 7) hold the same quantity
+            double o8 = __shfl_xor_sync(0xffffffffu, a, 8);
+            a = (q == 7) ? (a + o8) : nanmax(a, o8);
+            double o16 = __shfl_xor_sync(0xffffffffu, a, 16);
+            a = (q == 7) ? (a + o16) : nanmax(a, o16);
+            if (lane < 8) tot[warp * 8 + lane] = a;
+        }
+        if (__syncthreads_or(!good)) return false;
+        // 5. scalar logic, identical in every CTA
+        if (tid == 0) {
+            double t[8];
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) {
+                double a = tot[qq];
+                for (int w = 1; w < NW; ++w) a = (qq == 7) ? (a + tot[w * 8 + qq]) : nanmax(a, tot[w * 8 + qq]);
+                t[qq] = a;
+            }
+            const T pr = T(t[0]), du = T(t[3]);
+            const T nprim = nanmax(T(t[1]), T(t[2]));
+            const T ndual = nanmax(nanmax(T(t[4]), T(t[5])), T(t[6]));
+            const T num = pr / nprim;
+            const T den = du / ndual;
+            const T rho_new = clamp_keep_nan(T(rho * t_sqrt(num / den)), T(p.rho_min), T(p.rho_max));
+            int ri = rho_ind;
+            int dn = 0;
+            if (!final_pass) {
+                const T cur = rhos[ri];
+                if (rho_new > cur * T(p.tol) && ri < p.n_rho - 1) ri += 1;
+                else if (rho_new < cur / T(p.tol) && ri > 0) ri -= 1;
+                T tp = T(p.thr_p), td = T(p.thr_d);
+                if (p.eps_rel != 0.0) {
+                    tp = tp + T(p.eps_rel) * nprim;
+                    td = td + T(p.eps_rel) * ndual;
+                }
+                dn = (pr < tp && du < td) ? 1 : 0;
+            }
+            dec->rho_ind = ri;
+            dec->done = dn;
+            dec->rho = double(rho_new);
+            dec->pri = double(pr);
+            dec->dua = double(du);
+            dec->obj = t[7];
+            if (blockIdx.x == 0 && p.trace != nullptr && n_checks < p.trace_cap) {
+                double* tr = p.trace + size_t(n_checks) * RQP_TRACE_STRIDE;
+                tr[0] = double(kk); tr[1] = double(ri); tr[2] = double(pr); tr[3] = double(du);
+                tr[4] = double(rho_new);
+            }
+        }
+        __syncthreads();
+        rho = T(dec->rho);
+        pri = T(dec->pri);
+        dua = T(dec->dua);
+        obj = T(dec->obj);
+        const int new_ri = dec->rho_ind;
+        solved = dec->done != 0;
+        n_checks += 1;
+        __syncthreads();  // dec / part / tot may be rewritten by the next pass
+        if (new_ri != rho_ind && !solved) {
+            rho_ind = new_ri;
+            n_switch += 1;
+            if (is_fin) my_b = ball[size_t(rho_ind) * D + my_row];
+            if (!stage_slab(rho_ind)) good = false;
+            if (__syncthreads_or(!good)) return false;
+        } else {
+            rho_ind = new_ri;
+        }
+        return true;
+    };
+
+    if (__syncthreads_or(!ok)) aborted = true;
+
+    if (!aborted) {
+        for (k = 1; k <= p.max_iter; ++k) {
+            // ---- gather the owned columns of v_{k-1}
+            const uint64_t* vslot = p.vcells + size_t((k - 1) & 1) * nvec * 4;
+            const uint32_t fprev = epoch + uint32_t(k - 1);
+            T vv[CPT][VEC];
+            {
+                uint64_t w[CPT][4];
+                uint32_t pending = 0;
+#pragma unroll
+                for (int i = 0; i < CPT; ++i) {
+                    const uint64_t* cp = vslot + size_t(coff[i] / VEC) * 4;
+                    ld_relaxed_u64x2(cp, w[i][0], w[i][1]);
+                    ld_relaxed_u64x2(cp + 2, w[i][2], w[i][3]);
+                }
+#pragma unroll
+                for (int i = 0; i < CPT; ++i) {
+                    T out[VEC];
+                    const uint32_t m = C::unpack(w[i], fprev, out);
+                    if ((m & need[i]) != need[i]) pending |= 1u << i;
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) vv[i][e] = ((need[i] >> e) & 1u) ? out[e] : T(0);
+                }
+                wd.arm();
+                while (pending != 0u && ok) {
+#pragma unroll
+                    for (int i = 0; i < CPT; ++i) {
+                        if (pending & (1u << i)) {
+                            const uint64_t* cp = vslot + size_t(coff[i] / VEC) * 4;
+                            uint64_t ww[4];
+                            ld_relaxed_u64x2(cp, ww[0], ww[1]);
+                            ld_relaxed_u64x2(cp + 2, ww[2], ww[3]);
+                            T out[VEC];
+                            const uint32_t m = C::unpack(ww, fprev, out);
+                            if ((m & need[i]) == need[i]) {
+                                pending &= ~(1u << i);
+#pragma unroll
+                                for (int e = 0; e < VEC; ++e) vv[i][e] = ((need[i] >> e) & 1u) ? out[e] : T(0);
+                            }
+                        }
+                    }
+                    if (pending != 0u && wd.expired()) ok = false;
+                }
+            }
+
+            // ---- slab GEMV, 8 rows per chunk
+            T* redk = red + size_t(k & 1) * NW * rpc_pad + size_t(warp) * rpc_pad;
+            const T* Wg = Wall + (size_t(rho_ind) * D + r0) * ldw;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const int rbase = ch * RM;
+                const int nr = min(RM, rows - rbase);
+                T acc[RM];
+                if (rbase < rows_s) {  // rows_s is a multiple of RM unless it equals rows
+                    const T* w0 = Ws + size_t(rbase) * ldw;
+                    if (nr == RM) chunk_dot<T, CPT, true, true>(w0, ldw, nr, coff, vv, acc);
+                    else chunk_dot<T, CPT, true, false>(w0, ldw, nr, coff, vv, acc);
+                } else {
+                    const T* w0 = Wg + size_t(rbase) * ldw;
+                    if (nr == RM) chunk_dot<T, CPT, false, true>(w0, ldw, nr, coff, vv, acc);
+                    else chunk_dot<T, CPT, false, false>(w0, ldw, nr, coff, vv, acc);
+                }
+                warp_multi_reduce8(acc, lane);
+                if ((lane & 3) == 0) redk[rbase + (lane >> 2)] = acc[0];
+            }
+            if (__syncthreads_or(!ok)) { aborted = true; break; }
+
+            // ---- finalize own rows: cross-warp sum (fixed order), bias, clamp, publish v_k
+            if (is_fin) {
+                const T* rk = red + size_t(k & 1) * NW * rpc_pad + tid;
+                T y = rk[0];
+#pragma unroll
+                for (int w = 1; w < NW; ++w) y += rk[size_t(w) * rpc_pad];
+                y += my_b;
+                my_v = clamp_keep_nan(y, my_lo, my_hi);
+                C::publish(p.vcells + size_t(k & 1) * nvec * 4, my_row, my_v, epoch + uint32_t(k));
+            }
+
+            // ---- residual check (reluqpth.py:218)
+            if (p.adaptive && (k % p.check_interval) == 0) {
+                if (!residual_pass(k, epoch + uint32_t(k), false)) { aborted = true; break; }
+                if (solved) break;
+            }
+        }
+    }
+    if (k > p.max_iter) k = p.max_iter;
+
+    // ---- max_iter fall-through: residuals of the last iterate, no index move (reluqpth.py:243)
+    if (!solved && !aborted) {
+        if (!residual_pass(k, epoch + uint32_t(p.max_iter) + 1u, true)) aborted = true;
+    }
+
+    if (is_fin) static_cast<T*>(p.v)[my_row] = my_v;
+    if (blockIdx.x == 0 && tid == 0) {
+        rqp_result r;
+        r.iter = k;
+        r.status = solved ? RQP_STATUS_SOLVED : RQP_STATUS_MAX_ITER;
+        r.rho_ind = rho_ind;
+        r.error = aborted ? RQP_ERR_WATCHDOG : 0;
+        r.pri_res = double(pri);
+        r.dua_res = double(dua);
+        r.rho_estimate = double(rho);
+        r.obj_val = double(obj);
+        r.n_checks = n_checks;
+        r.n_rho_switches = n_switch;
+        r.t_begin_ns = t_begin;
+        r.t_end_ns = globaltimer_ns();
+        r.grid = G;
+        r.block = NT;
+        r.rows_per_cta = p.rpc;
+        r.rows_in_smem = p.rows_smem;
+        *p.result = r;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// Host side: launch geometry + dispatch.
+// -------------------------------------------------------------------------------------------
+static size_t smem_fixed_bytes(int elem, long long ldw, int rpc, int block) {
+    const int NW = block / 32;
+    const int rpc_pad = (rpc + RM - 1) / RM * RM;
+    size_t o = size_t(ldw) * elem;                 // vs
+    o += size_t(2) * NW * rpc_pad * elem;          // red
+    o = (o + 15) & ~size_t(15);
+    o += size_t(2) * NW * 8 * sizeof(double);      // part, tot
+    o += sizeof(Decision) + 16;                    // dec, mbar
+    return o;
+}
+
+int plan_single(const rqp_problem* prob, const rqp_settings* stng, const rqp_caps& caps, SinglePlan* plan) {
+    if (!prob || !stng || !plan) return RQP_ERR_BAD_ARG;
+    if (prob->nx < 1 || prob->nc < 1 || prob->n_rho < 1) return RQP_ERR_BAD_ARG;
+    if (prob->dtype != RQP_F32 && prob->dtype != RQP_F64) return RQP_ERR_UNSUPPORTED;
+    const int D = prob->nx + 2 * prob->nc;
+    if (prob->ldw < D || (prob->ldw % 4) != 0) return RQP_ERR_BAD_ARG;
+    const int elem = prob->dtype == RQP_F64 ? 8 : 4;
+    const int vec = 16 / elem;
+    const int nvec = int(prob->ldw / vec);
+    int block = stng->block;
+    if (block == 0) block = (nvec > 16 * 256) ? 512 : 256;
+    if (block != 256 && block != 512) return RQP_ERR_UNSUPPORTED;
+    int cpt_rt = (nvec + block - 1) / block;
+    int cpt = 1;
+    while (cpt < cpt_rt) cpt *= 2;
+    if (cpt > 16) return RQP_ERR_UNSUPPORTED;
+    if (block == 512 && cpt > 8) return RQP_ERR_UNSUPPORTED;
+    int grid = stng->grid > 0 ? stng->grid : caps.sm_count;
+    if (grid > caps.sm_count) return RQP_ERR_LAUNCH_TOO_LARGE;
+    int rpc = (D + grid - 1) / grid;
+    if (stng->grid <= 0 && rpc < RM) rpc = RM;     // at least one full register chunk per CTA
+    grid = (D + rpc - 1) / rpc;
+    if (rpc > block) return RQP_ERR_UNSUPPORTED;
+    const size_t fixed = smem_fixed_bytes(elem, prob->ldw, rpc, block);
+    const size_t row_bytes = size_t(prob->ldw) * elem;
+    const size_t cap = size_t(caps.max_smem_per_block);
+    if (fixed + 1024 > cap) return RQP_ERR_UNSUPPORTED;
+    long long fit = (long long)((cap - fixed - 256) / row_bytes);
+    int rows_smem = int(fit < rpc ? fit : rpc);
+    if (stng->w_residency == 2) rows_smem = 0;
+    if (rows_smem < rpc) rows_smem = rows_smem / RM * RM;
+    if (stng->w_residency == 1 && rows_smem < rpc) return RQP_ERR_UNSUPPORTED;
+    plan->grid = grid;
+    plan->block = block;
+    plan->cpt = cpt;
+    plan->rpc = rpc;
+    plan->rows_smem = rows_smem;
+    plan->smem_bytes = fixed + size_t(rows_smem) * row_bytes + 128;
+    plan->vcells_bytes = size_t(2) * nvec * 4 * sizeof(uint64_t);
+    plan->pcells_bytes = size_t(2) * caps.sm_count * 16 * sizeof(uint64_t);
+    plan->ws_bytes = 256 + plan->vcells_bytes + plan->pcells_bytes;
+    return RQP_OK;
+}
+
+template <typename T, int CPT, int NT>
+static int launch_one(const SingleParams& prm, const SinglePlan& plan, cudaStream_t stream) {
+    auto kern = rqp_single_kernel<T, CPT, NT>;
+    RQP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes)));
+    int occ = 0;
+    RQP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, plan.smem_bytes));
+    if (occ < 1) return RQP_ERR_LAUNCH_TOO_LARGE;
+    void* args[] = {const_cast<SingleParams*>(&prm)};
+    RQP_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(plan.grid), dim3(NT), args,
+                                             plan.smem_bytes, stream));
+    return RQP_OK;
+}
+
+template <typename T, int NT>
+static int launch_cpt(const SingleParams& prm, const SinglePlan& plan, cudaStream_t stream) {
+    switch (plan.cpt) {
+        case 1: return launch_one<T, 1, NT>(prm, plan, stream);
+        case 2: return launch_one<T, 2, NT>(prm, plan, stream);
+        case 4: return launch_one<T, 4, NT>(prm, plan, stream);
+        case 8: return launch_one<T, 8, NT>(prm, plan, stream);
+        case 16:
+            if (NT == 256) return launch_one<T, 16, 256>(prm, plan, stream);
+            return RQP_ERR_UNSUPPORTED;
+    }
+    return RQP_ERR_UNSUPPORTED;
+}
+
+int launch_single(const rqp_problem* prob, const rqp_settings* stng, rqp_state* state, rqp_result* result_dev,
+                  double* trace_dev, int32_t trace_cap, void* ws, size_t ws_bytes, const rqp_caps& caps,
+                  cudaStream_t stream) {
+    SinglePlan plan;
+    int rc = plan_single(prob, stng, caps, &plan);
+    if (rc != RQP_OK) return rc;
+    if (!state || !state->v || !result_dev || !ws) return RQP_ERR_BAD_ARG;
+    if (ws_bytes < plan.ws_bytes) return RQP_ERR_WORKSPACE;
+    if (stng->max_iter < 0 || stng->check_interval < 1) return RQP_ERR_BAD_ARG;
+    if (state->rho_ind < 0 || state->rho_ind >= prob->n_rho) return RQP_ERR_BAD_ARG;
+    if (state->epoch == 0 || state->epoch > 0x70000000u) return RQP_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(prob->W) & 15) || (reinterpret_cast<uintptr_t>(ws) & 255)) return RQP_ERR_BAD_ARG;
+
+    SingleParams prm;
+    prm.W = prob->W; prm.b = prob->b; prm.H = prob->H; prm.A = prob->A; prm.AT = prob->AT;
+    prm.g = prob->g; prm.l = prob->l; prm.u = prob->u; prm.rhos = prob->rhos;
+    prm.v = state->v;
+    unsigned char* w8 = static_cast<unsigned char*>(ws);
+    prm.abort_flag = reinterpret_cast<uint32_t*>(w8);
+    prm.vcells = reinterpret_cast<uint64_t*>(w8 + 256);
+    prm.pcells = reinterpret_cast<uint64_t*>(w8 + 256 + plan.vcells_bytes);
+    prm.result = result_dev;
+    prm.trace = trace_dev;
+    prm.trace_cap = trace_dev ? trace_cap : 0;
+    prm.ldw = prob->ldw;
+    prm.nx = prob->nx; prm.nc = prob->nc; prm.D = prob->nx + 2 * prob->nc; prm.n_rho = prob->n_rho;
+    prm.rho_ind0 = state->rho_ind;
+    prm.max_iter = stng->max_iter;
+    prm.check_interval = stng->check_interval;
+    prm.adaptive = stng->adaptive_rho;
+    // thresholds of reluqpth.py:233, formed in double on the host exactly like eps_abs*np.sqrt(n)
+    prm.thr_p = stng->eps_abs * sqrt(double(prob->nc));
+    prm.thr_d = stng->eps_abs * sqrt(double(prob->nx));
+    prm.eps_rel = stng->eps_rel;
+    prm.rho_min = stng->rho_min; prm.rho_max = stng->rho_max; prm.tol = stng->adaptive_rho_tolerance;
+    prm.watchdog_ns = (unsigned long long)(stng->watchdog_ms > 0 ? stng->watchdog_ms : 4000) * 1000000ull;
+    prm.epoch = state->epoch;
+    prm.rpc = plan.rpc;
+    prm.rows_smem = plan.rows_smem;
+
+    if (prob->dtype == RQP_F64) {
+        rc = plan.block == 256 ? launch_cpt<double, 256>(prm, plan, stream) : launch_cpt<double, 512>(prm, plan, stream);
+    } else {
+        rc = plan.block == 256 ? launch_cpt<float, 256>(prm, plan, stream) : launch_cpt<float, 512>(prm, plan, stream);
+    }
+    if (rc == RQP_OK) state->epoch += uint32_t(stng->max_iter) + 2u;
+    return rc;
+}
+
+}  // namespace rqp

@@ -1,0 +1,473 @@
+"""ReLU-QP solver, B200-native: the Python surface of the reference
+(``ReLU-QP-py/reluqp/reluqpth.py``: ``ReLU_QP.setup / update / update_settings / solve /
+warm_start / clear_primal_dual`` and ``ReLU_Layer``) over hand-written sm_100a CUDA reached
+through the C ABI of ``include/rqp.h``.
+
+What runs where:
+  * setup (``reluqpth.py:20-78``): the rho grid and the layer matrices W_rho, B_rho, b_rho for
+    all rho are formed once with torch ops on the solver's device (GPU: cuSOLVER/cuBLAS) and
+    stored as ONE contiguous ``[n_rho, D, ldw]`` tensor, so the kernel switches rho by pointer
+    arithmetic.  Off the hot path.
+  * solve (``reluqpth.py:201-249``): ONE persistent cooperative kernel launch
+    (``rqp_solve``) runs every ADMM iteration, every residual check, the rho-index state
+    machine, termination and the objective.  The host does one stream synchronise and reads a
+    88-byte result record.  There is NO PyTorch or CPU fallback for this path: without
+    ``librqp.so`` or a CUDA device ``solve`` raises.
+  * update (``reluqpth.py:159-183``): new g/l/u are copied into the existing device buffers and
+    b_rho = B_rho g is refreshed for all rho by one kernel (``rqp_update_bias``).
+
+Deliberate differences from the reference, all listed in DESIGN.md: the layer product is
+de-aliased; ``device``/``precision`` are honoured (F2); for float32 the matrices
+are formed in float64 and rounded (F3; ``setup_precision=torch.float32`` restores the
+reference's all-fp32 setup); ``results.x`` is the true iterate even when no check ran
+(A.2-1); ``warm_start(x, z, lam)`` really seeds the state (A.2-9); ``update_settings`` accepts
+``eps_abs``; ``setup`` does not change torch's global default dtype (A.2-12).
+"""
+import ctypes as C
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .classes import QP, BatchResults, Info, Results, Settings, default_device, to_tensor
+
+STATUS_NAMES = {_cabi.RQP_STATUS_SOLVED: "solved", _cabi.RQP_STATUS_MAX_ITER: "max_iters_reached"}
+
+
+def _round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+class _Timer(object):
+    """CUDA events on a CUDA device (what the reference uses, ``reluqpth.py:99-100``); host
+    clock otherwise.  Seconds."""
+
+    def __init__(self, device):
+        self.cuda = device.type == "cuda"
+        if self.cuda:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.end = torch.cuda.Event(enable_timing=True)
+        self.t0 = 0.0
+
+    def tic(self):
+        if self.cuda:
+            self.start.record()
+        else:
+            self.t0 = time.perf_counter()
+
+    def toc(self):
+        if self.cuda:
+            self.end.record()
+            self.end.synchronize()
+            return self.start.elapsed_time(self.end) / 1000.0
+        return time.perf_counter() - self.t0
+
+
+class ReLU_Layer(object):
+    """The rho grid and the per-rho layer matrices (reference ``reluqpth.py:8-89``).
+
+    ``W_ks[i]``, ``B_ks[i]``, ``b_ks[i]`` are views into the contiguous ``W_all``
+    ``[n_rho, D, ldw]`` (columns D..ldw-1 are zero padding so that every row starts 16-byte
+    aligned), ``B_all`` ``[n_rho, D, nx]`` and ``b_all`` ``[n_rho, D]``."""
+
+    def __init__(self, QP=None, settings=None, setup_QP=None):
+        self.QP = QP
+        self.settings = settings if settings is not None else Settings()
+        self._setup_QP = setup_QP if setup_QP is not None else QP
+        self.rho_list = self._rho_grid()
+        self.rhos = self.setup_rhos()
+        self.W_all, self.B_all, self.b_all = self.setup_matrices()
+        D = QP.nx + 2 * QP.nc
+        n = len(self.rho_list)
+        self.W_ks = {i: self.W_all[i, :, :D] for i in range(n)}
+        self.B_ks = {i: self.B_all[i] for i in range(n)}
+        self.b_ks = {i: self.b_all[i] for i in range(n)}
+        self.clamp_inds = (QP.nx, QP.nx + QP.nc)
+        self._setup_QP = None
+
+    def _rho_grid(self):
+        """``reluqpth.py:24-35``: geometric grid around ``rho`` inside [rho_min, rho_max],
+        built in Python doubles by repeated division / multiplication, then sorted."""
+        st = self.settings
+        grid = [st.rho]
+        if st.adaptive_rho:
+            t = st.adaptive_rho_tolerance
+            r = st.rho / t
+            while r >= st.rho_min:
+                grid.append(r)
+                r = r / t
+            r = st.rho * t
+            while r <= st.rho_max:
+                grid.append(r)
+                r = r * t
+            grid.sort()
+        return grid
+
+    def setup_rhos(self):
+        st = self.settings
+        return torch.tensor(self.rho_list, device=st.device, dtype=st.precision).contiguous()
+
+    def setup_matrices(self):
+        """W_rho (3x3 blocks over [x; z; lambda]), B_rho = [-K; -AK; 0], b_rho = B_rho g with
+        K = (H + sigma I + A' R A)^-1 (``reluqpth.py:52-77``).  Blocks are written
+        straight into the strided destination; the diagonal factors R, R^-1 are applied as row
+        / column scalings (bit-identical to the reference's products with diag matrices)."""
+        st = self.settings
+        q = self._setup_QP
+        sdt = q.H.dtype
+        dev = q.H.device
+        H, g, A, l, u = q.H, q.g, q.A, q.l, q.u
+        nx, nc = q.nx, q.nc
+        D = nx + 2 * nc
+        ldw = _round_up(D, 4)
+        n = len(self.rho_list)
+        W_all = torch.zeros((n, D, ldw), device=dev, dtype=st.precision)
+        B_all = torch.zeros((n, D, nx), device=dev, dtype=st.precision)
+        eq = (u - l) <= st.eq_tol
+        Ix = torch.eye(nx, device=dev, dtype=sdt)
+        Ic = torch.eye(nc, device=dev, dtype=sdt)
+        At = A.T
+        for i, rs in enumerate(self.rho_list):
+            rvec = torch.full((nc,), rs, device=dev, dtype=sdt)
+            rvec[eq] = rs * 1e3
+            RA = rvec[:, None] * A                       # R A
+            AtRA = At @ RA
+            K = torch.linalg.inv(H + st.sigma * Ix + AtRA)
+            S = st.sigma * Ix - AtRA
+            KAt = K @ At
+            AK = A @ K
+            AKAt = AK @ At
+            W = W_all[i]
+            W[:nx, :nx] = K @ S
+            W[:nx, nx:nx + nc] = (2 * KAt) * rvec
+            W[:nx, nx + nc:D] = -KAt
+            W[nx:nx + nc, :nx] = AK @ S + A
+            W[nx:nx + nc, nx:nx + nc] = (2 * AKAt) * rvec - Ic
+            W[nx:nx + nc, nx + nc:D] = -AKAt + torch.diag(1.0 / rvec)
+            W[nx + nc:, :nx] = RA
+            W[nx + nc:, nx:nx + nc] = -torch.diag(rvec)
+            W[nx + nc:, nx + nc:D] = Ic
+            B_all[i, :nx] = -K
+            B_all[i, nx:nx + nc] = -AK
+        b_all = torch.matmul(B_all, self.QP.g).contiguous()
+        return W_all, B_all, b_all
+
+    def forward(self, input, idx):
+        """One ADMM iteration ``v <- clamp(W_idx v + b_idx)`` (``reluqpth.py:80-89``) on the
+        CUDA path; ``input`` is updated in place and returned."""
+        if getattr(self, "_engine", None) is None:
+            raise RuntimeError("ReLU_Layer.forward needs the layer to belong to a set-up ReLU_QP")
+        self._engine.run(input, int(idx), max_iter=1, adaptive=False)
+        return input
+
+    __call__ = forward
+
+
+class _Engine(object):
+    """Owns the ctypes structs, the exchange workspace and the result record of one solver and
+    calls ``rqp_solve``.  All pointers refer to tensors held by the ReLU_QP / ReLU_Layer."""
+
+    def __init__(self, qp, layers, settings, tuning):
+        if settings.device.type != "cuda":
+            raise RuntimeError(
+                "ReLU_QP.solve runs only on a CUDA device (sm_100a): device is '{}' and there is no "
+                "CPU or PyTorch fallback for the solve path".format(settings.device))
+        self.lib = _cabi.load()
+        self.device = settings.device
+        self.qp, self.layers, self.settings = qp, layers, settings
+        self.dtype = settings.precision
+        self.AT = qp.A.T.contiguous()
+        D = qp.nx + 2 * qp.nc
+        self.D = D
+        self.prob = _cabi.rqp_problem(
+            dtype=_cabi.dtype_code(self.dtype), nx=qp.nx, nc=qp.nc, n_rho=len(layers.rho_list),
+            ldw=layers.W_all.shape[2],
+            W=layers.W_all.data_ptr(), b=layers.b_all.data_ptr(), H=qp.H.data_ptr(), A=qp.A.data_ptr(),
+            AT=self.AT.data_ptr(), g=qp.g.data_ptr(), l=qp.l.data_ptr(), u=qp.u.data_ptr(),
+            rhos=layers.rhos.data_ptr())
+        self.stng = _cabi.rqp_settings()
+        self.tuning = dict(grid=0, block=0, w_residency=0, watchdog_ms=0)
+        self.tuning.update({k: int(v) for k, v in tuning.items()})
+        self._fill_settings()
+        with torch.cuda.device(self.device):
+            sz = C.c_size_t(0)
+            _cabi.check(self.lib.rqp_workspace_size(C.byref(self.prob), C.byref(self.stng), C.byref(sz)),
+                        "rqp_workspace_size")
+        self.ws = torch.zeros(sz.value, dtype=torch.uint8, device=self.device)
+        self.epoch = 1
+        # result record: pinned host memory the kernel writes directly (zero-copy over PCIe),
+        # or a device buffer + explicit copy when RQP_RESULT_MAPPED=0
+        self.mapped = os.environ.get("RQP_RESULT_MAPPED", "1") != "0"
+        nbytes = C.sizeof(_cabi.rqp_result)
+        self.res_host = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+        self.res_dev = None if self.mapped else torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        self.res_view = _cabi.rqp_result.from_address(self.res_host.data_ptr())
+        self.trace_cap = 0
+        self.trace = None
+        self.state = _cabi.rqp_state()
+
+    def _fill_settings(self, max_iter=None, adaptive=None):
+        st, s = self.settings, self.stng
+        s.max_iter = int(st.max_iter if max_iter is None else max_iter)
+        s.check_interval = int(st.check_interval)
+        s.adaptive_rho = int(bool(st.adaptive_rho if adaptive is None else adaptive))
+        s.eps_abs = float(st.eps_abs)
+        s.eps_rel = float(st.eps_rel)
+        s.rho_min = float(st.rho_min)
+        s.rho_max = float(st.rho_max)
+        s.adaptive_rho_tolerance = float(st.adaptive_rho_tolerance)
+        s.grid, s.block = self.tuning["grid"], self.tuning["block"]
+        s.w_residency, s.watchdog_ms = self.tuning["w_residency"], self.tuning["watchdog_ms"]
+
+    def enable_trace(self, cap):
+        if cap > self.trace_cap:
+            self.trace = torch.zeros(cap * _cabi.RQP_TRACE_STRIDE, dtype=torch.float64, device=self.device)
+            self.trace_cap = cap
+
+    def launch(self, v, rho_ind, max_iter=None, adaptive=None):
+        """Enqueue one solve on the current stream; no host synchronisation."""
+        self._fill_settings(max_iter, adaptive)
+        if self.epoch + self.stng.max_iter + 2 > _cabi.EPOCH_LIMIT:
+            self.ws.zero_()
+            self.epoch = 1
+        self.state.v = v.data_ptr()
+        self.state.rho_ind = int(rho_ind)
+        self.state.epoch = self.epoch
+        res_ptr = self.res_host.data_ptr() if self.mapped else self.res_dev.data_ptr()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.rqp_solve(C.byref(self.prob), C.byref(self.stng), C.byref(self.state), res_ptr,
+                                self.trace.data_ptr() if self.trace is not None else None,
+                                self.trace_cap, self.ws.data_ptr(), self.ws.numel(), stream)
+        _cabi.check(rc, "rqp_solve")
+        self.epoch = int(self.state.epoch)
+        if not self.mapped:
+            self.res_host.copy_(self.res_dev, non_blocking=True)
+
+    def finish(self):
+        """Wait for the stream and return the result record (a live ctypes view)."""
+        torch.cuda.current_stream(self.device).synchronize()
+        r = self.res_view
+        if r.error != 0:
+            self.ws.zero_()       # exchange cells may hold flags of an aborted epoch
+            self.epoch = 1
+            raise RuntimeError("rqp_solve: {} (iter {})".format(
+                self.lib.rqp_strerror(r.error).decode(), r.iter))
+        return r
+
+    def run(self, v, rho_ind, max_iter=None, adaptive=None):
+        if v.device != self.device or v.dtype != self.dtype or not v.is_contiguous() or v.numel() != self.D:
+            raise ValueError("state vector must be a contiguous {} tensor of length {} on {}".format(
+                self.dtype, self.D, self.device))
+        with torch.cuda.device(self.device):
+            self.launch(v, rho_ind, max_iter, adaptive)
+            return self.finish()
+
+
+class ReLU_QP(object):
+    def __init__(self):
+        super().__init__()
+        self.info = Info()
+        self.results = Results(info=self.info)
+        self._engine = None
+        self._batch = None
+
+    def setup(self, H, g, A, l, u,
+              verbose=False,
+              warm_starting=True,
+              scaling=False,
+              rho=0.1,
+              rho_min=1e-6,
+              rho_max=1e6,
+              sigma=1e-6,
+              adaptive_rho=True,
+              adaptive_rho_interval=1,
+              adaptive_rho_tolerance=5,
+              max_iter=4000,
+              eps_abs=1e-3,
+              check_interval=25,
+              device=None,
+              precision=torch.float64,
+              eps_rel=0.0,
+              setup_precision=None,
+              **launch_tuning):
+        """
+        Setup ReLU-QP solver problem of the form
+
+        minimize     1/2 x' * H * x + g' * x
+        subject to   l <= A * x <= u
+
+        solver settings can be specified as additional keyword arguments (same names and
+        defaults as the reference, ``reluqpth.py:102-117``).  Extra, all optional: ``eps_rel``,
+        ``setup_precision`` and kernel launch tuning (``grid``, ``block``, ``w_residency``,
+        ``watchdog_ms``; see include/rqp.h).
+        """
+        bad = set(launch_tuning) - {"grid", "block", "w_residency", "watchdog_ms"}
+        if bad:
+            raise TypeError("setup() got unexpected keyword arguments {}".format(sorted(bad)))
+        device = default_device() if device is None else torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        timer = _Timer(device)
+        timer.tic()
+
+        self.settings = Settings(verbose=verbose, warm_starting=warm_starting, scaling=scaling, rho=rho,
+                                 rho_min=rho_min, rho_max=rho_max, sigma=sigma, adaptive_rho=adaptive_rho,
+                                 adaptive_rho_interval=adaptive_rho_interval,
+                                 adaptive_rho_tolerance=adaptive_rho_tolerance, max_iter=max_iter,
+                                 eps_abs=eps_abs, check_interval=check_interval, device=device,
+                                 precision=precision, eps_rel=eps_rel, setup_precision=setup_precision)
+        st = self.settings
+        sdt = st.setup_precision
+        if precision == torch.float64:
+            sdt = torch.float64
+        setup_qp = QP(H, g, A, l, u, device=device, precision=sdt)
+        if sdt == precision:
+            self.QP = setup_qp
+        else:
+            self.QP = QP(setup_qp.H, setup_qp.g, setup_qp.A, setup_qp.l, setup_qp.u, device=device,
+                         precision=precision)
+        self.layers = ReLU_Layer(QP=self.QP, settings=st, setup_QP=setup_qp)
+        self._tuning = launch_tuning
+        self._engine = None
+        self._batch = None
+        self.layers._engine = None
+        self._timer = timer
+        self.clear_primal_dual()
+        if device.type == "cuda":
+            self._engine = _Engine(self.QP, self.layers, st, launch_tuning)
+            self.layers._engine = self._engine
+        self.results.info.setup_time = timer.toc()
+
+    # ------------------------------------------------------------------ updates
+    def update(self, g=None, l=None, u=None, Hx=None, Ax=None):
+        """Update ReLU-QP problem vectors (``reluqpth.py:159-183``).  numpy arrays or torch
+        tensors.  The device buffers are overwritten in place."""
+        # assert that matrices cannot be changed for now
+        assert Hx is None and Ax is None, "updating Hx and Ax is not supported yet"
+        st = self.settings
+        self._timer.tic()
+        if g is not None:
+            self.QP.g.copy_(to_tensor(g, st.device, st.precision), non_blocking=True)
+            L = self.layers
+            if self._engine is not None:
+                with torch.cuda.device(st.device):
+                    rc = self._engine.lib.rqp_update_bias(
+                        _cabi.dtype_code(st.precision), len(L.rho_list), L.B_all.shape[1], self.QP.nx,
+                        L.B_all.data_ptr(), self.QP.g.data_ptr(), L.b_all.data_ptr(),
+                        torch.cuda.current_stream(st.device).cuda_stream)
+                _cabi.check(rc, "rqp_update_bias")
+            else:
+                torch.matmul(L.B_all, self.QP.g, out=L.b_all)
+        if l is not None:
+            self.QP.l.copy_(to_tensor(l, st.device, st.precision), non_blocking=True)
+        if u is not None:
+            self.QP.u.copy_(to_tensor(u, st.device, st.precision), non_blocking=True)
+        self.results.info.update_time = self._timer.toc()
+        return None
+
+    def update_settings(self, **kwargs):
+        """
+        Update ReLU-QP solver settings
+
+        It is possible to change: 'max_iter', 'eps_abs', 'eps_rel', 'verbose', 'check_interval'
+        (the reference's whitelist spells eps_abs "eps_ab", ``reluqpth.py:194``; both work here)
+        """
+        for key, value in kwargs.items():
+            if key == "eps_ab":
+                key = "eps_abs"
+            if key in ["max_iter", "eps_abs", "eps_rel", "verbose", "check_interval"]:
+                setattr(self.settings, key, value)
+            elif key in ["rho", "rho_min", "rho_max", "sigma", "adaptive_rho", "adaptive_rho_interval",
+                         "adaptive_rho_tolerance"]:
+                raise ValueError("Cannot change {} after setup".format(key))
+            else:
+                raise ValueError("Invalid setting: {}".format(key))
+
+    # ------------------------------------------------------------------ solve
+    def solve(self):
+        """Solve QP Problem: one persistent-kernel launch (see module docstring)."""
+        if self._engine is None:
+            raise RuntimeError(
+                "ReLU_QP.solve needs a CUDA device: this solver was set up on '{}'. The solve path is "
+                "hand-written sm_100a CUDA behind librqp.so; there is no CPU fallback.".format(
+                    self.settings.device))
+        st = self.settings
+        nx, nc = self.QP.nx, self.QP.nc
+        eng = self._engine
+        self._timer.tic()
+        if st.verbose and st.adaptive_rho:
+            eng.enable_trace(st.max_iter // max(1, st.check_interval) + 2)
+        r = eng.run(self.output, self.rho_ind)
+        if st.verbose and eng.trace is not None:
+            tr = eng.trace[:min(r.n_checks, eng.trace_cap) * _cabi.RQP_TRACE_STRIDE].cpu().view(-1, 5)
+            for k, _, pri, dua, rho in tr.tolist():
+                print('Iter: {}, rho: {:.2e}, res_p: {:.2e}, res_d: {:.2e}'.format(int(k), rho, pri, dua))
+        self.rho_ind = int(r.rho_ind)
+        self.x, self.z, self.lam = self.output[:nx], self.output[nx:nx + nc], self.output[nx + nc:nx + 2 * nc]
+        self.update_results(iter=int(r.iter), status=STATUS_NAMES[int(r.status)], pri_res=r.pri_res,
+                            dua_res=r.dua_res, rho_estimate=r.rho_estimate, obj_val=r.obj_val)
+        self.last_launch = dict(grid=int(r.grid), block=int(r.block), rows_per_cta=int(r.rows_per_cta),
+                                rows_in_smem=int(r.rows_in_smem), n_checks=int(r.n_checks),
+                                n_rho_switches=int(r.n_rho_switches),
+                                kernel_loop_us=(int(r.t_end_ns) - int(r.t_begin_ns)) / 1e3)
+        return self.results
+
+    def warm_start(self, x=None, z=None, lam=None, rho=None):
+        """Warm start primal / dual variables and rho.  Unlike the reference (where x, z, lam are
+        stored but never reach the state vector) the state IS seeded here."""
+        st = self.settings
+        nx, nc = self.QP.nx, self.QP.nc
+        if x is not None:
+            self.output[:nx].copy_(to_tensor(x, st.device, st.precision))
+        if z is not None:
+            self.output[nx:nx + nc].copy_(to_tensor(z, st.device, st.precision))
+        if lam is not None:
+            self.output[nx + nc:].copy_(to_tensor(lam, st.device, st.precision))
+        if rho is not None:
+            self.rho_ind = int(np.argmin(np.abs(np.asarray(self.layers.rho_list) - rho)))
+        return None
+
+    def update_results(self, iter=None, status=None, pri_res=None, dua_res=None, rho_estimate=None,
+                       obj_val=None):
+        """Update results and info (``reluqpth.py:278-305``).  x and z are views of the state
+        vector, as in the reference; scalar infos are 0-dim CPU tensors of the solver dtype."""
+        dt = self.settings.precision
+        info = self.results.info
+        self.results.x = self.x
+        self.results.z = self.z
+        info.iter = iter
+        info.status = status
+        info.obj_val = torch.tensor(obj_val, dtype=dt)
+        info.pri_res = torch.tensor(pri_res, dtype=dt)
+        info.dua_res = torch.tensor(dua_res, dtype=dt)
+        info.rho_estimate = torch.tensor(rho_estimate, dtype=dt)
+        run_time = self._timer.toc()
+        info.run_time = run_time
+        info.solve_time = info.update_time + run_time
+        if not self.settings.warm_starting:
+            self.clear_primal_dual()
+
+    def clear_primal_dual(self):
+        """Clear primal and dual variables and reset rho index (``reluqpth.py:324-333``).  A
+        fresh state vector is allocated, so earlier ``results.x`` keep their values."""
+        st = self.settings
+        nx, nc = self.QP.nx, self.QP.nc
+        self.output = torch.zeros(nx + 2 * nc, device=st.device, dtype=st.precision)
+        self.x, self.z, self.lam = self.output[:nx], self.output[nx:nx + nc], self.output[nx + nc:]
+        self.rho_ind = int(np.argmin(np.abs(np.asarray(self.layers.rho_list) - st.rho)))
+        return None
+
+    # ------------------------------------------------------------------ batched (additive API)
+    def solve_batch(self, l, u, g=None, max_sweeps=None):
+        """Solve B QPs that share this solver's H, A (hence every W_rho) and differ in l, u
+        (``[B, nc]``) and optionally g (``[B, nx]``).  Column j is defined as what the reference
+        would return for ``update(l=l[j], u=u[j][, g=g[j]])`` followed by a cold ``solve()``.
+        Returns a ``BatchResults``; nothing of the single-QP state is touched."""
+        from ._batch import BatchEngine
+        if self._engine is None:
+            raise RuntimeError("ReLU_QP.solve_batch needs a CUDA device; there is no CPU fallback")
+        if self._batch is None:
+            self._batch = BatchEngine(self)
+        return self._batch.solve(l, u, g)

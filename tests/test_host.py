@@ -1,0 +1,182 @@
+"""CPU tests of the host side: generators are bit-exact restatements, the setup stage forms
+the reference's matrices, the API keeps the reference's names and error behaviour, the solve
+path refuses to run without CUDA, and librqp.so exports everything include/rqp.h declares."""
+import ctypes
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import REPO, known_answer_problem
+from oracle import reluqp_oracle as O
+from reluqp import _cabi, reluqpth, utils
+from reluqp.classes import QP, Info, Results, Settings
+from reluqp.mpc import RandomLinMPC, ihlqr
+
+
+def _sha(*arrs):
+    h = hashlib.sha256()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def test_rand_qp_bit_exact(golden):
+    H, g, A, l, u, _ = utils.rand_qp(10, 5, 5, seed=1, compute_sol=False)
+    assert _sha(H, g, A, l, u) == golden.meta["c1_sha256"]
+    assert _sha(H, g, A, l, u).startswith("853fe27d9c67293d")
+    np.testing.assert_array_equal(H[0], golden.arrays("small")["c1/H_row0"])
+    for name, meta in golden.meta["sweep"].items():
+        if meta["seed"] != 0 or meta["nx"] > 100:
+            continue
+        p = utils.rand_qp(meta["nx"], meta["n_eq"], meta["n_ineq"], seed=meta["seed"], compute_sol=False)
+        assert _sha(*p[:5])[:16] == meta["sha256"]
+
+
+def test_rand_qp_without_cvxpy_warns():
+    with pytest.warns(UserWarning):
+        out = utils.rand_qp(4, 2, 2, seed=0, compute_sol=True)
+    assert out[5] is None and out[0].shape == (4, 4)
+
+
+def test_mpc_generator(golden):
+    plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+    assert (plant.nvar, plant.nc) == (320, 320)
+    assert _sha(plant.H, plant.g, plant.A) == golden.meta["mpc"]["sha256"]
+    assert abs(np.max(np.abs(np.linalg.eigvals(plant.Ad))) - 1.0) < 1e-12
+    K, P = ihlqr(plant.Ad, plant.Bd, plant.Q, plant.R, plant.Q)
+    # P solves the discrete Riccati equation
+    Acl = plant.Ad - plant.Bd @ K
+    np.testing.assert_allclose(P, plant.Q + plant.Ad.T @ P @ Acl, atol=1e-6)
+    # dynamics rows reproduce a rollout
+    x0 = plant.sample_x0()
+    l, u = plant.bounds(x0)
+    w = np.zeros(plant.nvar)
+    x = x0
+    for k in range(plant.horizon):
+        uk = 0.01 * np.ones(plant.nu)
+        x = plant.Ad @ x + plant.Bd @ uk
+        w[k * 16:k * 16 + 4] = uk
+        w[k * 16 + 4:(k + 1) * 16] = x
+    r = plant.A @ w
+    np.testing.assert_allclose(r[:240], l[:240], atol=1e-12)
+    assert np.all(r[240:] <= u[240:]) and np.all(r[240:] >= l[240:])
+    L, U = plant.bounds(np.stack([x0, 2 * x0]))
+    np.testing.assert_allclose(L[0], l, rtol=1e-13, atol=1e-15)   # gemm vs gemv rounding
+    np.testing.assert_allclose(L[1, :12], 2 * l[:12])
+
+
+def test_setup_matches_oracle_cpu():
+    """The GPU setup stage is plain torch, so it can be checked on CPU against the oracle's
+    matrices (which are pinned to the reference's)."""
+    H, g, A, l, u = known_answer_problem()
+    m = reluqpth.ReLU_QP()
+    m.setup(H, g, A, l, u, device="cpu")
+    s = O.OracleSolver(H, g, A, l, u)
+    assert m.layers.rho_list == s.rho_list and len(m.layers.rhos) == 18
+    assert m.rho_ind == 7 and m.layers.clamp_inds == (3, 8)
+    assert m.layers.W_all.shape == (18, 13, 16) and m.layers.W_all.is_contiguous()
+    assert float(m.layers.W_all[:, :, 13:].abs().max()) == 0.0
+    for i in range(18):
+        np.testing.assert_allclose(m.layers.W_ks[i].numpy(), s.W[i].numpy(), rtol=1e-10, atol=1e-11)
+        np.testing.assert_allclose(m.layers.B_ks[i].numpy(), s.B[i].numpy(), rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(m.layers.b_ks[i].numpy(), s.b[i].numpy(), rtol=1e-10, atol=1e-12)
+    H, g, A, l, u, _ = utils.rand_qp(30, 7, 7, seed=5, compute_sol=False)
+    m.setup(H, g, A, l, u, device="cpu", rho=1.0, adaptive_rho_tolerance=3)
+    s = O.OracleSolver(H, g, A, l, u, rho=1.0, adaptive_rho_tolerance=3)
+    assert m.layers.rho_list == s.rho_list
+    for i in range(len(s.rho_list)):
+        scale = float(s.W[i].abs().max())
+        assert float((m.layers.W_ks[i] - s.W[i]).abs().max()) < 1e-9 * scale
+
+
+def test_fp32_setup_modes():
+    H, g, A, l, u, _ = utils.rand_qp(20, 5, 5, seed=2, compute_sol=False)
+    m = reluqpth.ReLU_QP()
+    m.setup(H, g, A, l, u, device="cpu", precision=torch.float32)           # fp64 setup, rounded
+    s = O.OracleSolver(H, g, A, l, u, precision=torch.float32, setup_precision=torch.float64)
+    assert m.layers.W_all.dtype == torch.float32 and m.QP.H.dtype == torch.float32
+    assert float((m.layers.W_ks[7] - s.W[7]).abs().max()) <= 2e-6 * float(s.W[7].abs().max())
+    m.setup(H, g, A, l, u, device="cpu", precision=torch.float32, setup_precision=torch.float32)
+    assert m.layers.W_all.dtype == torch.float32
+
+
+def test_update_and_settings_cpu():
+    H, g, A, l, u, _ = utils.rand_qp(10, 5, 5, seed=1, compute_sol=False)
+    m = reluqpth.ReLU_QP()
+    m.setup(H, g, A, l, u, device="cpu")
+    _, g2, _, l2, u2, _ = utils.update_qp(H, A, 5, 5, seed=7, compute_sol=False)
+    m.update(g=g2, l=torch.from_numpy(l2), u=u2)
+    s = O.OracleSolver(H, g, A, l, u)
+    s.update(g=g2, l=l2, u=u2)
+    for i in range(18):
+        np.testing.assert_allclose(m.layers.b_ks[i].numpy(), s.b[i].numpy(), rtol=1e-9, atol=1e-12)
+    np.testing.assert_array_equal(m.QP.l.numpy(), l2)
+    with pytest.raises(AssertionError, match="updating Hx and Ax is not supported yet"):
+        m.update(Hx=H)
+    m.update_settings(max_iter=10, eps_abs=1e-5, check_interval=5, verbose=False, eps_ab=1e-4)
+    assert m.settings.max_iter == 10 and m.settings.eps_abs == 1e-4 and m.settings.check_interval == 5
+    with pytest.raises(ValueError, match="Cannot change rho after setup"):
+        m.update_settings(rho=1.0)
+    with pytest.raises(ValueError, match="Invalid setting: bogus"):
+        m.update_settings(bogus=1)
+    m.warm_start(x=np.ones(10), rho=12.0)
+    assert float(m.output[:10].sum()) == 10.0 and m.rho_ind == 10
+    m.clear_primal_dual()
+    assert float(m.output.abs().max()) == 0.0 and m.rho_ind == 7
+
+
+def test_solve_refuses_without_cuda():
+    H, g, A, l, u = known_answer_problem()
+    m = reluqpth.ReLU_QP()
+    m.setup(H, g, A, l, u, device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.solve()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.solve_batch(np.stack([l, l]), np.stack([u, u]))
+
+
+def test_api_surface():
+    """Names users of the reference rely on."""
+    for name in ("setup", "update", "update_settings", "solve", "warm_start", "clear_primal_dual",
+                 "update_results"):
+        assert callable(getattr(reluqpth.ReLU_QP, name))
+    st = Settings()
+    for k, v in dict(verbose=False, warm_starting=True, scaling=False, rho=0.1, rho_min=1e-6, rho_max=1e6,
+                     sigma=1e-6, adaptive_rho=True, adaptive_rho_interval=1, adaptive_rho_tolerance=5,
+                     max_iter=4000, eps_abs=1e-3, eq_tol=1e-6, check_interval=25,
+                     precision=torch.float64, eps_rel=0.0).items():
+        assert getattr(st, k) == v
+    info = Info()
+    for k in ("iter", "status", "obj_val", "pri_res", "dua_res", "setup_time", "solve_time", "update_time",
+              "run_time", "rho_estimate"):
+        assert hasattr(info, k)
+    assert Results(info=info).info is info
+    q = QP(np.eye(2), np.zeros(2), np.ones((3, 2)), np.zeros(3), np.ones(3), device="cpu")
+    assert (q.nx, q.nc) == (2, 3) and q.H.dtype == torch.float64
+    with pytest.raises(ValueError):
+        QP(np.eye(2), np.zeros(3), np.ones((3, 2)), np.zeros(3), np.ones(3), device="cpu")
+
+
+def test_cabi_exports_match_header():
+    """Every function include/rqp.h declares is exported by librqp.so, and the ctypes struct
+    sizes agree with the C layout rules."""
+    assert os.path.exists(_cabi.LIB_PATH), "build librqp.so first: make -C reluqp-py_b200"
+    hdr = open(os.path.join(REPO, "include", "rqp.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(rqp_\w+)\s*\(", hdr, flags=re.M))
+    assert declared == set(_cabi.EXPORTS)
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    lib.rqp_strerror.restype = ctypes.c_char_p
+    assert lib.rqp_strerror(0) == b"ok" and b"watchdog" in lib.rqp_strerror(-6)
+    assert ctypes.sizeof(_cabi.rqp_result) == 88
+    assert ctypes.sizeof(_cabi.rqp_settings) == 72
+    assert ctypes.sizeof(_cabi.rqp_problem) == 96
+    assert ctypes.sizeof(_cabi.rqp_state) == 16
+    # bad arguments are reported, not crashed on (no GPU needed: checks come first)
+    assert lib.rqp_update_bias(1, 0, 0, 0, None, None, None, None) == -1
+    assert lib.rqp_query(0, None) == -1

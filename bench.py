@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--grid", type=int, default=0)
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--w-residency", type=int, default=0)
+    ap.add_argument("--backoff", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -228,7 +229,8 @@ def main():
 
     wl = make_workload(args.workload)
     elem = 8 if wl["dtype"] == torch.float64 else 4
-    tuning = {k: v for k, v in dict(grid=args.grid, block=args.block, w_residency=args.w_residency).items() if v}
+    tuning = {k: v for k, v in dict(grid=args.grid, block=args.block, w_residency=args.w_residency,
+                                           poll_backoff_ns=args.backoff).items() if v}
     m = reluqpth.ReLU_QP()
     m.setup(*wl["problem"], device=dev, precision=wl["dtype"], warm_starting=False, **wl["kw"], **tuning)
     nx, nc = m.QP.nx, m.QP.nc
@@ -240,6 +242,8 @@ def main():
     v = torch.zeros(nx + 2 * nc, dtype=wl["dtype"], device=dev)
     rho0 = m.rho_ind
 
+    phases = []
+
     def resident_step(j, ev0, ev1):
         """inputs already in HBM: select instance j (device copy), flush L2, time the solve launch"""
         m.QP.l.copy_(Ld[j])
@@ -250,6 +254,7 @@ def main():
         eng.launch(v, rho0)
         ev1.record()
         r = eng.finish()
+        phases.append([int(c) for c in r.phase_cycles])
         return int(r.iter), int(r.n_checks), int(r.status), (int(r.t_end_ns) - int(r.t_begin_ns)) * 1e-3
 
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -264,6 +269,7 @@ def main():
         sampler.start()
     torch.cuda.synchronize()
     iters, checks, statuses, loop_us = [], [], [], []
+    phases.clear()
     t_wall0 = time.perf_counter()
     for s in range(args.steps):
         it, ck, stt, lus = resident_step((args.warmup + s) % ninst, *evs[s])
@@ -282,7 +288,7 @@ def main():
     # ---- e2e through the public API with host buffers (numpy l,u in; x out on the host)
     Lh, Uh = wl["L"], wl["U"]
     h2d = 2 * nc * elem
-    d2h = nx * elem + 88
+    d2h = nx * elem + 152
     for w in range(args.warmup):
         m.update(l=Lh[w % ninst], u=Uh[w % ninst]); m.solve().x.cpu()
     torch.cuda.synchronize()
@@ -346,6 +352,10 @@ def main():
         us_per_admm_iter_in_kernel=sum(loop_us) / sum(iters),
         iters_per_solve=sum(iters) / len(iters),
         all_solved=all(s == 0 for s in statuses),
+        phase_cycles_per_iter=dict(zip(
+            ["wait_v", "gemv_reduce", "cta_barrier", "finalize_publish", "checks", "failed_poll_rounds", "slab_loads"],
+            [round(sum(ph[i] for ph in phases) / sum(iters), 1) for i in range(7)])),
+        w_in_registers=bool(phases[0][7]),
         wall_s_timed_region=t_wall,
         roofline=dict(bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s",
                       frac=achieved / peaks["hbm_gbs"], traffic=None, peak_source=peaks["source"],

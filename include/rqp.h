@@ -83,7 +83,7 @@ typedef struct rqp_settings {
     int32_t max_iter;
     int32_t check_interval;
     int32_t adaptive_rho;       /* 0: never check, run max_iter iterations (reluqpth.py:218) */
-    int32_t reserved0;
+    int32_t poll_backoff_ns;    /* tuning: sleep between failed exchange polls (0 = none)  */
     double eps_abs;
     double eps_rel;
     double rho_min, rho_max;
@@ -91,7 +91,8 @@ typedef struct rqp_settings {
     /* launch tuning; 0 = choose automatically */
     int32_t grid;               /* number of CTAs (<= SM count)                         */
     int32_t block;              /* threads per CTA: 256 or 512                          */
-    int32_t w_residency;        /* 0 auto, 1 force shared-memory resident, 2 force streamed */
+    int32_t w_residency;        /* 0 auto, 1 force shared-memory resident, 2 force streamed,
+                                   3 force register resident                             */
     int32_t watchdog_ms;        /* 0 = 4000 ms per in-kernel wait                       */
 } rqp_settings;
 
@@ -117,6 +118,11 @@ typedef struct rqp_result {
     int32_t n_rho_switches;
     uint64_t t_begin_ns, t_end_ns; /* %globaltimer at loop entry / exit (CTA 0)          */
     int32_t grid, block, rows_per_cta, rows_in_smem; /* what actually ran                */
+    /* diagnostics, thread 0 of CTA 0, SM clock cycles summed over the iterations:
+     * [0] waiting for v_{k-1}, [1] slab GEMV + warp reduction, [2] CTA barrier,
+     * [3] cross-warp sum + publish, [4] residual checks, [5] number of failed poll rounds,
+     * [6] W slab (re)loads, [7] 1 if the slab lives in registers */
+    uint64_t phase_cycles[8];
 } rqp_result;
 
 /* One record per residual check: {k, rho_ind_after, pri, dua, rho_estimate} as 5 doubles. */

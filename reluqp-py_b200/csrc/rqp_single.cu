@@ -60,6 +60,7 @@ struct SingleParams {
     int rpc;        // rows per CTA
     int rows_smem;  // rows of each slab resident in shared memory
     int trace_cap;
+    int backoff_ns; // sleep between failed exchange polls
 };
 
 template <typename T>
@@ -99,7 +100,10 @@ struct Decision {
     double rho, pri, dua, obj;
 };
 
-template <typename T, int CPT, int NT>
+// RMODE: the CTA's slab has at most RM rows and is held in REGISTERS (thread t keeps the
+// 16-byte pieces of its own columns for all rows), loaded once per rho straight from global
+// memory; shared memory then only carries the reductions.
+template <typename T, int CPT, int NT, bool RMODE>
 __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p) {
     using C = Cell<T>;
     constexpr int VEC = C::kVec;
@@ -167,8 +171,25 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
         fence_mbar_init();
     }
     __syncthreads();
+    Vec16<T> wreg[RMODE ? RM : 1][RMODE ? CPT : 1];
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, RMODE ? 1 : 0};
     auto stage_slab = [&](int ri) {
         // caller guarantees every thread is past its last read of Ws (a __syncthreads)
+        const long long ts = clock64();
+        if (RMODE) {
+            const T* Wg = Wall + (size_t(ri) * D + r0) * ldw;
+#pragma unroll
+            for (int r = 0; r < RM; ++r) {
+#pragma unroll
+                for (int i = 0; i < CPT; ++i) {
+                    // rows beyond the slab repeat the last row (never written out)
+                    wreg[RMODE ? r : 0][RMODE ? i : 0] =
+                        Vec16<T>::ldg(Wg + (long long)min(r, rows - 1) * ldw + coff[i]);
+                }
+            }
+            ph[6] += clock64() - ts;
+            return true;
+        }
         if (rows_s > 0) {
             if (tid == 0) {
                 const size_t bytes = size_t(rows_s) * ldw * sizeof(T);
@@ -186,6 +207,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 if (wd.expired()) { ok = false; break; }
             }
             mbar_parity ^= 1u;
+            ph[6] += clock64() - ts;
             return ok;
         }
         return true;
@@ -384,6 +406,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
 
     if (!aborted) {
         for (k = 1; k <= p.max_iter; ++k) {
+            const long long tp0 = clock64();
             // ---- gather the owned columns of v_{k-1}
             const uint64_t* vslot = p.vcells + size_t((k - 1) & 1) * nvec * 4;
             const uint32_t fprev = epoch + uint32_t(k - 1);
@@ -407,6 +430,8 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 }
                 wd.arm();
                 while (pending != 0u && ok) {
+                    ph[5] += 1;
+                    if (p.backoff_ns > 0) __nanosleep(p.backoff_ns);
 #pragma unroll
                     for (int i = 0; i < CPT; ++i) {
                         if (pending & (1u << i)) {
@@ -427,9 +452,23 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 }
             }
 
+            const long long tp1 = clock64();
             // ---- slab GEMV, 8 rows per chunk
             T* redk = red + size_t(k & 1) * NW * rpc_pad + size_t(warp) * rpc_pad;
             const T* Wg = Wall + (size_t(rho_ind) * D + r0) * ldw;
+            if (RMODE) {
+                T acc[RM];
+#pragma unroll
+                for (int r = 0; r < RM; ++r) acc[r] = T(0);
+#pragma unroll
+                for (int i = 0; i < CPT; ++i) {
+#pragma unroll
+                    for (int r = 0; r < RM; ++r)
+                        acc[r] = wreg[RMODE ? r : 0][RMODE ? i : 0].dot(vv[i], acc[r]);
+                }
+                warp_multi_reduce8(acc, lane);
+                if ((lane & 3) == 0) redk[lane >> 2] = acc[0];
+            } else
             for (int ch = 0; ch < nchunks; ++ch) {
                 const int rbase = ch * RM;
                 const int nr = min(RM, rows - rbase);
@@ -446,7 +485,9 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 warp_multi_reduce8(acc, lane);
                 if ((lane & 3) == 0) redk[rbase + (lane >> 2)] = acc[0];
             }
+            const long long tp2 = clock64();
             if (__syncthreads_or(!ok)) { aborted = true; break; }
+            const long long tp3 = clock64();
 
             // ---- finalize own rows: cross-warp sum (fixed order), bias, clamp, publish v_k
             if (is_fin) {
@@ -459,9 +500,14 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 C::publish(p.vcells + size_t(k & 1) * nvec * 4, my_row, my_v, epoch + uint32_t(k));
             }
 
+            const long long tp4 = clock64();
+            ph[0] += tp1 - tp0; ph[1] += tp2 - tp1; ph[2] += tp3 - tp2; ph[3] += tp4 - tp3;
+
             // ---- residual check (reluqpth.py:218)
             if (p.adaptive && (k % p.check_interval) == 0) {
-                if (!residual_pass(k, epoch + uint32_t(k), false)) { aborted = true; break; }
+                const bool good = residual_pass(k, epoch + uint32_t(k), false);
+                ph[4] += clock64() - tp4;
+                if (!good) { aborted = true; break; }
                 if (solved) break;
             }
         }
@@ -492,6 +538,8 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
         r.block = NT;
         r.rows_per_cta = p.rpc;
         r.rows_in_smem = p.rows_smem;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.phase_cycles[i] = (unsigned long long)ph[i];
         *p.result = r;
     }
 }
@@ -542,6 +590,11 @@ int plan_single(const rqp_problem* prob, const rqp_settings* stng, const rqp_cap
     if (stng->w_residency == 2) rows_smem = 0;
     if (rows_smem < rpc) rows_smem = rows_smem / RM * RM;
     if (stng->w_residency == 1 && rows_smem < rpc) return RQP_ERR_UNSUPPORTED;
+    // register residency: one chunk of rows, at most 4 vector columns per thread (128 registers)
+    const bool can_reg = (rpc <= RM) && (cpt <= 4) && (block == 256);
+    if (stng->w_residency == 3 && !can_reg) return RQP_ERR_UNSUPPORTED;
+    plan->rmode = (stng->w_residency == 3 || (stng->w_residency == 0 && can_reg)) ? 1 : 0;
+    if (plan->rmode) rows_smem = 0;
     plan->grid = grid;
     plan->block = block;
     plan->cpt = cpt;
@@ -554,9 +607,9 @@ int plan_single(const rqp_problem* prob, const rqp_settings* stng, const rqp_cap
     return RQP_OK;
 }
 
-template <typename T, int CPT, int NT>
+template <typename T, int CPT, int NT, bool RMODE = false>
 static int launch_one(const SingleParams& prm, const SinglePlan& plan, cudaStream_t stream) {
-    auto kern = rqp_single_kernel<T, CPT, NT>;
+    auto kern = rqp_single_kernel<T, CPT, NT, RMODE>;
     RQP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes)));
     int occ = 0;
     RQP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, plan.smem_bytes));
@@ -569,6 +622,15 @@ static int launch_one(const SingleParams& prm, const SinglePlan& plan, cudaStrea
 
 template <typename T, int NT>
 static int launch_cpt(const SingleParams& prm, const SinglePlan& plan, cudaStream_t stream) {
+    if (plan.rmode) {
+        if (NT != 256) return RQP_ERR_UNSUPPORTED;
+        switch (plan.cpt) {
+            case 1: return launch_one<T, 1, 256, true>(prm, plan, stream);
+            case 2: return launch_one<T, 2, 256, true>(prm, plan, stream);
+            case 4: return launch_one<T, 4, 256, true>(prm, plan, stream);
+        }
+        return RQP_ERR_UNSUPPORTED;
+    }
     switch (plan.cpt) {
         case 1: return launch_one<T, 1, NT>(prm, plan, stream);
         case 2: return launch_one<T, 2, NT>(prm, plan, stream);
@@ -620,6 +682,7 @@ int launch_single(const rqp_problem* prob, const rqp_settings* stng, rqp_state* 
     prm.epoch = state->epoch;
     prm.rpc = plan.rpc;
     prm.rows_smem = plan.rows_smem;
+    prm.backoff_ns = stng->poll_backoff_ns;
 
     if (prob->dtype == RQP_F64) {
         rc = plan.block == 256 ? launch_cpt<double, 256>(prm, plan, stream) : launch_cpt<double, 512>(prm, plan, stream);

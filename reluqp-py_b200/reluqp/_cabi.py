@@ -39,7 +39,7 @@ class rqp_problem(C.Structure):
 
 class rqp_settings(C.Structure):
     _fields_ = [("max_iter", C.c_int32), ("check_interval", C.c_int32), ("adaptive_rho", C.c_int32),
-                ("reserved0", C.c_int32),
+                ("poll_backoff_ns", C.c_int32),
                 ("eps_abs", C.c_double), ("eps_rel", C.c_double), ("rho_min", C.c_double),
                 ("rho_max", C.c_double), ("adaptive_rho_tolerance", C.c_double),
                 ("grid", C.c_int32), ("block", C.c_int32), ("w_residency", C.c_int32),
@@ -57,7 +57,7 @@ class rqp_result(C.Structure):
                 ("n_checks", C.c_int32), ("n_rho_switches", C.c_int32),
                 ("t_begin_ns", C.c_uint64), ("t_end_ns", C.c_uint64),
                 ("grid", C.c_int32), ("block", C.c_int32), ("rows_per_cta", C.c_int32),
-                ("rows_in_smem", C.c_int32)]
+                ("rows_in_smem", C.c_int32), ("phase_cycles", C.c_uint64 * 8)]
 
 
 class rqp_batch(C.Structure):

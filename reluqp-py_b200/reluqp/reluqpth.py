@@ -11,7 +11,7 @@ What runs where:
   * solve (``reluqpth.py:201-249``): ONE persistent cooperative kernel launch
     (``rqp_solve``) runs every ADMM iteration, every residual check, the rho-index state
     machine, termination and the objective.  The host does one stream synchronise and reads a
-    88-byte result record.  There is NO PyTorch or CPU fallback for this path: without
+    152-byte result record.  There is NO PyTorch or CPU fallback for this path: without
     ``librqp.so`` or a CUDA device ``solve`` raises.
   * update (``reluqpth.py:159-183``): new g/l/u are copied into the existing device buffers and
     b_rho = B_rho g is refreshed for all rho by one kernel (``rqp_update_bias``).
@@ -188,7 +188,7 @@ class _Engine(object):
             AT=self.AT.data_ptr(), g=qp.g.data_ptr(), l=qp.l.data_ptr(), u=qp.u.data_ptr(),
             rhos=layers.rhos.data_ptr())
         self.stng = _cabi.rqp_settings()
-        self.tuning = dict(grid=0, block=0, w_residency=0, watchdog_ms=0)
+        self.tuning = dict(grid=0, block=0, w_residency=0, watchdog_ms=0, poll_backoff_ns=0)
         self.tuning.update({k: int(v) for k, v in tuning.items()})
         self._fill_settings()
         with torch.cuda.device(self.device):
@@ -220,6 +220,7 @@ class _Engine(object):
         s.adaptive_rho_tolerance = float(st.adaptive_rho_tolerance)
         s.grid, s.block = self.tuning["grid"], self.tuning["block"]
         s.w_residency, s.watchdog_ms = self.tuning["w_residency"], self.tuning["watchdog_ms"]
+        s.poll_backoff_ns = self.tuning["poll_backoff_ns"]
 
     def enable_trace(self, cap):
         if cap > self.trace_cap:
@@ -303,7 +304,7 @@ class ReLU_QP(object):
         ``setup_precision`` and kernel launch tuning (``grid``, ``block``, ``w_residency``,
         ``watchdog_ms``; see include/rqp.h).
         """
-        bad = set(launch_tuning) - {"grid", "block", "w_residency", "watchdog_ms"}
+        bad = set(launch_tuning) - {"grid", "block", "w_residency", "watchdog_ms", "poll_backoff_ns"}
         if bad:
             raise TypeError("setup() got unexpected keyword arguments {}".format(sorted(bad)))
         device = default_device() if device is None else torch.device(device)
@@ -411,7 +412,8 @@ class ReLU_QP(object):
         self.last_launch = dict(grid=int(r.grid), block=int(r.block), rows_per_cta=int(r.rows_per_cta),
                                 rows_in_smem=int(r.rows_in_smem), n_checks=int(r.n_checks),
                                 n_rho_switches=int(r.n_rho_switches),
-                                kernel_loop_us=(int(r.t_end_ns) - int(r.t_begin_ns)) / 1e3)
+                                kernel_loop_us=(int(r.t_end_ns) - int(r.t_begin_ns)) / 1e3,
+                                phase_cycles=[int(c) for c in r.phase_cycles])
         return self.results
 
     def warm_start(self, x=None, z=None, lam=None, rho=None):

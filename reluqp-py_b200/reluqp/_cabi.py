@@ -65,7 +65,8 @@ class rqp_batch(C.Structure):
                 ("V", C.c_void_p), ("L", C.c_void_p), ("U", C.c_void_p), ("G", C.c_void_p),
                 ("Bmat", C.c_void_p),
                 ("rho_ind", C.c_void_p), ("iter", C.c_void_p), ("status", C.c_void_p),
-                ("pri_res", C.c_void_p), ("dua_res", C.c_void_p), ("rho_estimate", C.c_void_p)]
+                ("pri_res", C.c_void_p), ("dua_res", C.c_void_p), ("rho_estimate", C.c_void_p),
+                ("engine", C.c_int32), ("reserved", C.c_int32), ("W_hi", C.c_void_p), ("W_lo", C.c_void_p)]
 
 
 _lib = None

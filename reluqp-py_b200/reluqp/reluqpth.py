@@ -52,17 +52,21 @@ class _Timer(object):
         self.t0 = 0.0
 
     def tic(self):
+        self.t0 = time.perf_counter()
         if self.cuda:
             self.start.record()
-        else:
-            self.t0 = time.perf_counter()
 
-    def toc(self):
-        if self.cuda:
+    def toc(self, sync=True):
+        """Seconds since tic().  sync=False (update): do not block the host; the time is the host
+        time spent enqueueing, the device part is absorbed by the following solve's run_time."""
+        if self.cuda and sync:
             self.end.record()
             self.end.synchronize()
             return self.start.elapsed_time(self.end) / 1000.0
         return time.perf_counter() - self.t0
+
+    def tic_host(self):
+        self.t0 = time.perf_counter()
 
 
 class ReLU_Layer(object):
@@ -329,6 +333,7 @@ class ReLU_QP(object):
         else:
             self.QP = QP(setup_qp.H, setup_qp.g, setup_qp.A, setup_qp.l, setup_qp.u, device=device,
                          precision=precision)
+        self._pack_vectors()
         self.layers = ReLU_Layer(QP=self.QP, settings=st, setup_QP=setup_qp)
         self._tuning = launch_tuning
         self._engine = None
@@ -342,15 +347,62 @@ class ReLU_QP(object):
         self.results.info.setup_time = timer.toc()
 
     # ------------------------------------------------------------------ updates
+    def _pack_vectors(self):
+        """g, l, u become views of ONE device buffer [g | l | u] mirrored by one pinned host buffer,
+        so ``update`` is a host memcpy plus a single async H2D copy and the pointers held by the C
+        structs never change."""
+        q, st = self.QP, self.settings
+        nx, nc = q.nx, q.nc
+        buf = torch.empty(nx + 2 * nc, device=st.device, dtype=st.precision)
+        buf[:nx].copy_(q.g)
+        buf[nx:nx + nc].copy_(q.l)
+        buf[nx + nc:].copy_(q.u)
+        q.g, q.l, q.u = buf[:nx], buf[nx:nx + nc], buf[nx + nc:]
+        self._glu = buf
+        self._glu_host = torch.empty(nx + 2 * nc, dtype=st.precision)
+        if st.device.type == "cuda":
+            self._glu_host = self._glu_host.pin_memory()
+        self._glu_np = self._glu_host.numpy()
+        self._glu_event = torch.cuda.Event() if st.device.type == "cuda" else None
+        self._glu_pending = False
+
+    def _stage(self, lo, hi, value):
+        """value (numpy / torch / sequence) -> staging buffer [lo, hi); device tensors go direct."""
+        if torch.is_tensor(value) and value.device.type != "cpu":
+            self._glu[lo:hi].copy_(value.to(self.settings.precision), non_blocking=True)
+            return None
+        if self._glu_pending:                     # the previous async copy may still read the staging buffer
+            self._glu_event.synchronize()
+            self._glu_pending = False
+        if torch.is_tensor(value):
+            self._glu_host[lo:hi].copy_(value)
+        else:
+            np.copyto(self._glu_np[lo:hi], np.asarray(value), casting="unsafe")
+        return (lo, hi)
+
     def update(self, g=None, l=None, u=None, Hx=None, Ax=None):
         """Update ReLU-QP problem vectors (``reluqpth.py:159-183``).  numpy arrays or torch
-        tensors.  The device buffers are overwritten in place."""
+        tensors.  The device buffers are overwritten in place (one async H2D copy); nothing here
+        synchronises the host, the following ``solve`` does."""
         # assert that matrices cannot be changed for now
         assert Hx is None and Ax is None, "updating Hx and Ax is not supported yet"
         st = self.settings
+        nx, nc = self.QP.nx, self.QP.nc
         self._timer.tic()
+        spans = [sp for sp in (self._stage(0, nx, g) if g is not None else None,
+                               self._stage(nx, nx + nc, l) if l is not None else None,
+                               self._stage(nx + nc, nx + 2 * nc, u) if u is not None else None) if sp]
+        if spans:
+            lo, hi = min(a for a, _ in spans), max(b for _, b in spans)
+            if len(spans) == 2 and spans[0][1] != spans[1][0]:     # g and u only: two copies
+                for a, b in spans:
+                    self._glu[a:b].copy_(self._glu_host[a:b], non_blocking=True)
+            else:
+                self._glu[lo:hi].copy_(self._glu_host[lo:hi], non_blocking=True)
+            if self._glu_event is not None:
+                self._glu_event.record()
+                self._glu_pending = True
         if g is not None:
-            self.QP.g.copy_(to_tensor(g, st.device, st.precision), non_blocking=True)
             L = self.layers
             if self._engine is not None:
                 with torch.cuda.device(st.device):
@@ -361,11 +413,7 @@ class ReLU_QP(object):
                 _cabi.check(rc, "rqp_update_bias")
             else:
                 torch.matmul(L.B_all, self.QP.g, out=L.b_all)
-        if l is not None:
-            self.QP.l.copy_(to_tensor(l, st.device, st.precision), non_blocking=True)
-        if u is not None:
-            self.QP.u.copy_(to_tensor(u, st.device, st.precision), non_blocking=True)
-        self.results.info.update_time = self._timer.toc()
+        self.results.info.update_time = self._timer.toc(sync=False)
         return None
 
     def update_settings(self, **kwargs):
@@ -462,7 +510,7 @@ class ReLU_QP(object):
         return None
 
     # ------------------------------------------------------------------ batched (additive API)
-    def solve_batch(self, l, u, g=None, max_sweeps=None):
+    def solve_batch(self, l, u, g=None, engine=0):
         """Solve B QPs that share this solver's H, A (hence every W_rho) and differ in l, u
         (``[B, nc]``) and optionally g (``[B, nx]``).  Column j is defined as what the reference
         would return for ``update(l=l[j], u=u[j][, g=g[j]])`` followed by a cold ``solve()``.
@@ -472,4 +520,4 @@ class ReLU_QP(object):
             raise RuntimeError("ReLU_QP.solve_batch needs a CUDA device; there is no CPU fallback")
         if self._batch is None:
             self._batch = BatchEngine(self)
-        return self._batch.solve(l, u, g)
+        return self._batch.solve(l, u, g, engine=engine)

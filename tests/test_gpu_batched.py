@@ -1,0 +1,175 @@
+"""GPU parity tests of the batched solve (rqp_solve_batched): column j must equal the reference's
+single cold solve of QP j (golden vectors from the real reference + live CPU oracle), in fp64 with
+identical iteration counts; fp32 within 1e-4 with iteration counts reported."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import reluqp_oracle as O
+from reluqp import reluqpth, utils
+from reluqp.mpc import RandomLinMPC
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_model(prob, **kw):
+    m = reluqpth.ReLU_QP()
+    m.setup(*prob, device="cuda", warm_starting=False, **kw)
+    return m
+
+
+def test_small_mpc_columns_match_reference(golden):
+    plant = RandomLinMPC(nx=4, nu=2, horizon=5, seed=3, u_max=0.1)
+    X0 = plant.sample_x0(8)
+    L, U = plant.bounds(X0)
+    m = gpu_model((plant.H, plant.g, plant.A, L[0], U[0]))
+    res = m.solve_batch(L, U)
+    assert res.status == ["solved"] * 8
+    for j in range(8):
+        gold = golden.case("mpc", "mpcs_col{}".format(j))
+        assert int(res.iter[j]) == gold["iter"], j
+        assert rel_err(res.x[j].cpu().numpy(), gold["x"]) < 1e-6
+        assert rel_err(res.z[j].cpu().numpy(), gold["z"]) < 1e-6
+        assert float(res.pri_res[j]) == pytest.approx(gold["pri"], rel=1e-2, abs=1e-7)
+
+
+def test_c2_columns_match_reference_and_single_path(golden):
+    """BASELINE config 4 semantics on 32 columns of the C2 plant: golden iteration counts (75..125,
+    several rho buckets alive at once) and agreement with this repo's single-QP kernel."""
+    plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+    X0 = plant.sample_x0(32)
+    L, U = plant.bounds(X0)
+    m = gpu_model((plant.H, plant.g, plant.A, L[0], U[0]))
+    res = m.solve_batch(L, U)
+    iters = res.iter.cpu().numpy()
+    gold_iters = np.array([golden.case("mpc", "mpc_col{}".format(j))["iter"] for j in range(32)])
+    np.testing.assert_array_equal(iters, gold_iters)
+    assert len(set(gold_iters.tolist())) >= 3                    # columns finish in different windows
+    for j in range(32):
+        gold = golden.case("mpc", "mpc_col{}".format(j))
+        assert rel_err(res.x[j].cpu().numpy(), gold["x"]) < 1e-6, j
+        assert rel_err(res.z[j].cpu().numpy(), gold["z"]) < 1e-6, j
+    for j in (0, 3, 9):
+        m.update(l=L[j], u=U[j])
+        r1 = m.solve()
+        assert r1.info.iter == int(res.iter[j])
+        assert rel_err(res.x[j].cpu().numpy(), r1.x.cpu().numpy()) < 1e-9
+
+
+def test_batched_with_per_column_g():
+    """update(g, l, u) per column: b_j = B_rho g_j must follow the column's rho bucket."""
+    H, g, A, l, u, _ = utils.rand_qp(30, 7, 7, seed=4, compute_sol=False)
+    Gs, Ls, Us = [], [], []
+    for sd in range(6):
+        _, g2, _, l2, u2, _ = utils.update_qp(H, A, 7, 7, seed=20 + sd, compute_sol=False)
+        Gs.append(g2); Ls.append(l2); Us.append(u2)
+    G, L, U = np.stack(Gs), np.stack(Ls), np.stack(Us)
+    m = gpu_model((H, g, A, l, u), eps_abs=1e-6)
+    res = m.solve_batch(L, U, g=G)
+    ref = O.solve_batch(H, g, A, L, U, G=G, eps_abs=1e-6)
+    for j, r in enumerate(ref):
+        assert int(res.iter[j]) == r.iter and res.status[j] == r.status, j
+        assert rel_err(res.x[j].cpu().numpy(), r.x.numpy()) < 1e-6
+        assert int(res.rho_ind[j]) == r.rho_ind
+
+
+def test_batched_max_iter_and_adaptive_off():
+    plant = RandomLinMPC(nx=4, nu=2, horizon=5, seed=3, u_max=0.1)
+    L, U = plant.bounds(plant.sample_x0(5))
+    prob = (plant.H, plant.g, plant.A, L[0], U[0])
+    for kw in (dict(max_iter=60, eps_abs=1e-12), dict(adaptive_rho=False, max_iter=40), dict(max_iter=30)):
+        m = gpu_model(prob, **kw)
+        res = m.solve_batch(L, U)
+        ref = O.solve_batch(plant.H, plant.g, plant.A, L, U, **kw)
+        for j, r in enumerate(ref):
+            assert int(res.iter[j]) == r.iter and res.status[j] == r.status, (kw, j)
+            assert rel_err(res.x[j].cpu().numpy(), r.x.numpy()) < 1e-6, (kw, j)
+            assert float(res.pri_res[j]) == pytest.approx(r.pri_res, rel=1e-3, abs=1e-9)
+
+
+def _fp32_setup():
+    plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+    X0 = plant.sample_x0(256)
+    L, U = plant.bounds(X0)
+    return plant, L, U
+
+
+def test_tc_engine_matches_simt_for_fixed_iterations():
+    """The tcgen05 3xTF32 GEMM against the SIMT fp32 and fp64 engines after a FIXED number of
+    iterations (no checks): same map applied the same number of times, so differences are pure
+    arithmetic.  1 iteration must be exact (v0 = 0 -> v1 = clamp(b)); later ones fp32-grade."""
+    plant, L, U = _fp32_setup()
+    prob = (plant.H, plant.g, plant.A, L[0], U[0])
+    for it, tol in ((1, 0.0), (2, 1e-6), (5, 1e-3), (30, 1e-3)):
+        kw = dict(adaptive_rho=False, max_iter=it)
+        r64 = gpu_model(prob, **kw).solve_batch(L, U)
+        m32 = gpu_model(prob, precision=torch.float32, **kw)
+        rs = m32.solve_batch(L, U, engine=1)
+        rt = m32.solve_batch(L, U, engine=2)
+        v64 = torch.cat([r64.x, r64.z, r64.lam], 1).double()
+        vs = torch.cat([rs.x, rs.z, rs.lam], 1).double()
+        vt = torch.cat([rt.x, rt.z, rt.lam], 1).double()
+        scale = float(v64.abs().max())
+        assert not torch.isnan(vt).any()
+        assert float((vt - vs).abs().max()) <= tol * scale, it
+        # the tensor-core engine is as close to fp64 as plain fp32 FMA is (within 4x)
+        assert float((vt - v64).abs().max()) <= 4 * float((vs - v64).abs().max()) + 1e-6 * scale, it
+        assert rt.status == ["max_iters_reached"] * 256 and int(rt.iter[0]) == it
+
+
+def test_batched_fp32_solution_quality(capsys):
+    """fp32 contract on the MPC family (fp32 iteration counts are rounding-chaotic, so they
+    are REPORTED).  Asserted: every column reaches 'solved' like fp64; the fp32 solution satisfies the
+    termination thresholds when its residuals are re-evaluated in fp64; and its distance to the
+    high-accuracy optimum x* is of the same order as the fp64 solve's own distance at the same
+    eps_abs (the tolerance, not the arithmetic, limits x here: |x_fp64(1e-3) - x*| is itself ~1e-2)."""
+    plant, L, U = _fp32_setup()
+    prob = (plant.H, plant.g, plant.A, L[0], U[0])
+    xstar = gpu_model(prob, eps_abs=1e-9, max_iter=20000).solve_batch(L, U).x
+    r64 = gpu_model(prob).solve_batch(L, U)
+    m32 = gpu_model(prob, precision=torch.float32)
+    scale = xstar.abs().amax(1)
+    e64 = ((r64.x - xstar).abs().amax(1) / scale).cpu().numpy()
+    H, g, A = (torch.as_tensor(t, dtype=torch.float64, device="cuda") for t in (plant.H, plant.g, plant.A))
+    # the fp32 solver clamps against the fp32-rounded bounds
+    Ld, Ud = (torch.as_tensor(t, dtype=torch.float32, device="cuda").double() for t in (L, U))
+    for eng, name in ((1, "simt fp32"), (2, "tcgen05 3xTF32")):
+        r = m32.solve_batch(L, U, engine=eng)
+        e32 = ((r.x.double() - xstar).abs().amax(1) / scale).cpu().numpy()
+        x, z, lam = r.x.double(), r.z.double(), r.lam.double()
+        pri = (x @ A.T - z).abs().amax(1)
+        dua = (x @ H.T + lam @ A + g).abs().amax(1)
+        feas = (z - torch.minimum(torch.maximum(z, Ld), Ud)).abs().amax(1)
+        with capsys.disabled():
+            print("\n[{}] solved {}/256, iters mean {:.1f} max {} (fp64 mean {:.1f} max {}); |x-x*|/|x*| median "
+                  "{:.2e} max {:.2e} (fp64 solve: median {:.2e} max {:.2e}); fp64-evaluated pri max {:.2e} dua max "
+                  "{:.2e}".format(name, int(r.status_code.eq(0).sum()), r.iter.float().mean().item(),
+                                  int(r.iter.max()), r64.iter.float().mean().item(), int(r64.iter.max()),
+                                  np.median(e32), e32.max(), np.median(e64), e64.max(), float(pri.max()),
+                                  float(dua.max())))
+        assert r.status == ["solved"] * 256
+        assert float(feas.max()) == 0.0                              # z respects the bounds exactly
+        assert float(pri.max()) < 1e-3 * np.sqrt(320) * 1.05        # thresholds of reluqpth.py:233
+        assert float(dua.max()) < 1e-3 * np.sqrt(320) * 1.05
+        assert np.median(e32) < 3 * np.median(e64) + 1e-4 and e32.max() < 3 * e64.max() + 1e-4
+
+
+def test_large_batch_properties():
+    """4096 columns (BASELINE config 4 size): every column solved, iteration counts multiples of the
+    check interval, KKT residuals small, and a re-solve of a permuted batch gives permuted results."""
+    plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+    X0 = plant.sample_x0(4096)
+    L, U = plant.bounds(X0)
+    m = gpu_model((plant.H, plant.g, plant.A, L[0], U[0]))
+    res = m.solve_batch(L, U)
+    it = res.iter.cpu().numpy()
+    assert res.status_code.eq(0).all() and (it % 25 == 0).all() and it.min() >= 25 and it.max() <= 400
+    x = res.x.cpu().numpy(); z = res.z.cpu().numpy(); lam = res.lam.cpu().numpy()
+    for j in range(0, 4096, 512):
+        kp, kd = O.kkt_residuals(plant.H, plant.g, plant.A, L[j], U[j], x[j], z[j], lam[j])
+        assert kd < 1e-3 * np.sqrt(320) * 1.01 and kp < 2e-3 * np.sqrt(320)
+    perm = np.random.RandomState(0).permutation(4096)
+    res2 = m.solve_batch(L[perm], U[perm])
+    np.testing.assert_array_equal(res2.iter.cpu().numpy(), it[perm])
+    assert np.max(np.abs(res2.x.cpu().numpy() - x[perm])) < 1e-9

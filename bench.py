@@ -226,6 +226,8 @@ def main():
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--w-residency", type=int, default=0)
     ap.add_argument("--backoff", type=int, default=0)
+    ap.add_argument("--prepoll", type=int, default=0)
+    ap.add_argument("--exch-flags", type=int, default=0)
     ap.add_argument("--batch", type=int, default=4096, help="QPs per GPU for --workload mpc_batched")
     ap.add_argument("--batch-dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--batch-engine", type=int, default=0, help="0 auto, 1 SIMT, 2 tcgen05")
@@ -267,7 +269,7 @@ def main():
                 a2 = copy.copy(args)
                 a2.workload, a2.no_cpu_baseline = wname, True
                 a2.steps, a2.warmup = (3, 3) if wname != "mpc_single" else (20, 3)
-                a2.grid = a2.block = a2.w_residency = a2.backoff = 0
+                a2.grid = a2.block = a2.w_residency = a2.backoff = a2.prepoll = a2.exch_flags = 0
                 try:
                     d = run_batched(a2, 0, 1, dev) if wname == "mpc_batched" else run_single(a2, 0, 1, dev)
                     others[wname] = {k: d[k] for k in ("value", "unit", "ms_per_step", "dtype", "iters_per_solve",
@@ -292,7 +294,8 @@ def run_single(args, rank, world, dev):
     wl = make_workload(args.workload)
     elem = 8 if wl["dtype"] == torch.float64 else 4
     tuning = {k: v for k, v in dict(grid=args.grid, block=args.block, w_residency=args.w_residency,
-                                           poll_backoff_ns=args.backoff).items() if v}
+                                           poll_backoff_ns=args.backoff, prepoll_cycles=args.prepoll,
+                                           exchange_flags=args.exch_flags).items() if v}
     m = reluqpth.ReLU_QP()
     m.setup(*wl["problem"], device=dev, precision=wl["dtype"], warm_starting=False, **wl["kw"], **tuning)
     nx, nc = m.QP.nx, m.QP.nc

@@ -94,6 +94,9 @@ typedef struct rqp_settings {
     int32_t w_residency;        /* 0 auto, 1 force shared-memory resident, 2 force streamed,
                                    3 force register resident                             */
     int32_t watchdog_ms;        /* 0 = 4000 ms per in-kernel wait                       */
+    int32_t prepoll_cycles;     /* tuning: SM cycles to spin after the CTA barrier before the
+                                   first exchange poll (0 = default 600, < 0 = none)      */
+    int32_t exchange_flags;     /* tuning: bit 0 = CTA barrier after the publish store    */
 } rqp_settings;
 
 /* Solver state carried across solves (reluqpth.py:148-153: `output` and `rho_ind`). */

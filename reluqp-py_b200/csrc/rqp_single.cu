@@ -61,6 +61,8 @@ struct SingleParams {
     int rows_smem;  // rows of each slab resident in shared memory
     int trace_cap;
     int backoff_ns; // sleep between failed exchange polls
+    int prepoll_cycles;   // spin this many SM cycles after the CTA barrier before the first poll
+    int exch_flags;       // bit 0: CTA barrier after the publish store (polls queue behind it)
 };
 
 template <typename T>
@@ -92,6 +94,57 @@ __device__ __forceinline__ void chunk_dot(const T* __restrict__ wrow0, long long
             if (FULL || r < nrows) acc[r] = w[r].dot(vv[i], acc[r]);
         }
     }
+}
+
+// Warp dot product of a global-memory row with a shared-memory vector: up to 8 independent loads per
+// lane are issued before the first use (the rows are read once per check, from L2 or HBM, so the
+// loop is latency bound unless the loads overlap).  Every lane returns the full sum.
+template <typename T>
+__device__ __forceinline__ T warp_row_dot(const T* __restrict__ row, const T* xs, int n, int lane) {
+    T s0 = T(0), s1 = T(0);
+    for (int j0 = 0; j0 < n; j0 += 256) {
+        T a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u * 32 + lane;
+            a[u] = (j < n) ? __ldg(row + j) : T(0);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+            const int j = j0 + u * 32 + lane;
+            s0 = fma(a[u], (j < n) ? xs[j] : T(0), s0);
+            s1 = fma(a[u + 1], (j + 32 < n) ? xs[j + 32] : T(0), s1);
+        }
+    }
+    return warp_sum(s0 + s1);
+}
+
+// Two rows at once (H x and A' lambda of the same index): all loads of both rows are in flight
+// together.  Returns the two sums through references.
+template <typename T>
+__device__ __forceinline__ void warp_row_dot2(const T* __restrict__ r1, const T* x1, int n1,
+                                              const T* __restrict__ r2, const T* x2, int n2, int lane, T& o1, T& o2) {
+    T s0 = T(0), s1 = T(0), q0 = T(0), q1 = T(0);
+    const int nmax = n1 > n2 ? n1 : n2;
+    for (int j0 = 0; j0 < nmax; j0 += 128) {
+        T a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * 32 + lane;
+            a[u] = (j < n1) ? __ldg(r1 + j) : T(0);
+            b[u] = (j < n2) ? __ldg(r2 + j) : T(0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u += 2) {
+            const int j = j0 + u * 32 + lane;
+            s0 = fma(a[u], (j < n1) ? x1[j] : T(0), s0);
+            s1 = fma(a[u + 1], (j + 32 < n1) ? x1[j + 32] : T(0), s1);
+            q0 = fma(b[u], (j < n2) ? x2[j] : T(0), q0);
+            q1 = fma(b[u + 1], (j + 32 < n2) ? x2[j + 32] : T(0), q1);
+        }
+    }
+    o1 = warp_sum(s0 + s1);
+    o2 = warp_sum(q0 + q1);
 }
 
 struct Decision {
@@ -259,38 +312,15 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
         const int GW = G * NW;
         for (int i = blockIdx.x * NW + warp; i < nc + nx; i += GW) {
             if (i < nc) {
-                const T* __restrict__ Ar = Am + size_t(i) * nx;
-                T s0 = T(0), s1 = T(0);
-                int j = lane;
-                for (; j + 32 < nx; j += 64) {
-                    s0 = fma(__ldg(Ar + j), xs[j], s0);
-                    s1 = fma(__ldg(Ar + j + 32), xs[j + 32], s1);
-                }
-                if (j < nx) s0 = fma(__ldg(Ar + j), xs[j], s0);
-                const T t1 = warp_sum(s0 + s1);
+                const T t1 = warp_row_dot(Am + size_t(i) * nx, xs, nx, lane);
                 const T zi = zs[i];
                 m0 = nanmax(m0, absval(t1 - zi));
                 m1 = nanmax(m1, absval(t1));
                 m2 = nanmax(m2, absval(zi));
             } else {
                 const int ii = i - nc;
-                const T* __restrict__ Hr = Hm + size_t(ii) * nx;
-                const T* __restrict__ Tr = ATm + size_t(ii) * nc;
-                T s0 = T(0), s1 = T(0), q0 = T(0), q1 = T(0);
-                int j = lane;
-                for (; j + 32 < nx; j += 64) {
-                    s0 = fma(__ldg(Hr + j), xs[j], s0);
-                    s1 = fma(__ldg(Hr + j + 32), xs[j + 32], s1);
-                }
-                if (j < nx) s0 = fma(__ldg(Hr + j), xs[j], s0);
-                j = lane;
-                for (; j + 32 < nc; j += 64) {
-                    q0 = fma(__ldg(Tr + j), ls[j], q0);
-                    q1 = fma(__ldg(Tr + j + 32), ls[j + 32], q1);
-                }
-                if (j < nc) q0 = fma(__ldg(Tr + j), ls[j], q0);
-                const T t2 = warp_sum(s0 + s1);
-                const T t3 = warp_sum(q0 + q1);
+                T t2, t3;
+                warp_row_dot2(Hm + size_t(ii) * nx, xs, nx, ATm + size_t(ii) * nc, ls, nc, lane, t2, t3);
                 const T gi = __ldg(gv + ii);
                 m3 = nanmax(m3, absval((t2 + t3) + gi));
                 m4 = nanmax(m4, absval(t2));
@@ -499,6 +529,12 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 my_v = clamp_keep_nan(y, my_lo, my_hi);
                 C::publish(p.vcells + size_t(k & 1) * nvec * 4, my_row, my_v, epoch + uint32_t(k));
             }
+            if (p.exch_flags & 1) __syncthreads();
+            if (p.prepoll_cycles > 0) {
+                const long long t_until = tp3 + p.prepoll_cycles;
+                while (clock64() < t_until) {
+                }
+            }
 
             const long long tp4 = clock64();
             ph[0] += tp1 - tp0; ph[1] += tp2 - tp1; ph[2] += tp3 - tp2; ph[3] += tp4 - tp3;
@@ -689,6 +725,10 @@ int launch_single(const rqp_problem* prob, const rqp_settings* stng, rqp_state* 
     prm.rpc = plan.rpc;
     prm.rows_smem = plan.rows_smem;
     prm.backoff_ns = stng->poll_backoff_ns;
+    // 0 = default: 600 SM cycles (measured optimum on B200 for register/shared-resident slabs: the
+    // publish store is not queued behind ~900 early poll requests of the same SM); < 0 = none
+    prm.prepoll_cycles = stng->prepoll_cycles == 0 ? 600 : (stng->prepoll_cycles < 0 ? 0 : stng->prepoll_cycles);
+    prm.exch_flags = stng->exchange_flags;
 
     if (prob->dtype == RQP_F64) {
         rc = plan.block == 256 ? launch_cpt<double, 256>(prm, plan, stream) : launch_cpt<double, 512>(prm, plan, stream);

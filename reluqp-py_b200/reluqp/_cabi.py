@@ -43,7 +43,7 @@ class rqp_settings(C.Structure):
                 ("eps_abs", C.c_double), ("eps_rel", C.c_double), ("rho_min", C.c_double),
                 ("rho_max", C.c_double), ("adaptive_rho_tolerance", C.c_double),
                 ("grid", C.c_int32), ("block", C.c_int32), ("w_residency", C.c_int32),
-                ("watchdog_ms", C.c_int32)]
+                ("watchdog_ms", C.c_int32), ("prepoll_cycles", C.c_int32), ("exchange_flags", C.c_int32)]
 
 
 class rqp_state(C.Structure):

@@ -192,7 +192,8 @@ class _Engine(object):
             AT=self.AT.data_ptr(), g=qp.g.data_ptr(), l=qp.l.data_ptr(), u=qp.u.data_ptr(),
             rhos=layers.rhos.data_ptr())
         self.stng = _cabi.rqp_settings()
-        self.tuning = dict(grid=0, block=0, w_residency=0, watchdog_ms=0, poll_backoff_ns=0)
+        self.tuning = dict(grid=0, block=0, w_residency=0, watchdog_ms=0, poll_backoff_ns=0, prepoll_cycles=0,
+                           exchange_flags=0)
         self.tuning.update({k: int(v) for k, v in tuning.items()})
         self._fill_settings()
         with torch.cuda.device(self.device):
@@ -225,6 +226,7 @@ class _Engine(object):
         s.grid, s.block = self.tuning["grid"], self.tuning["block"]
         s.w_residency, s.watchdog_ms = self.tuning["w_residency"], self.tuning["watchdog_ms"]
         s.poll_backoff_ns = self.tuning["poll_backoff_ns"]
+        s.prepoll_cycles, s.exchange_flags = self.tuning["prepoll_cycles"], self.tuning["exchange_flags"]
 
     def enable_trace(self, cap):
         if cap > self.trace_cap:
@@ -308,7 +310,8 @@ class ReLU_QP(object):
         ``setup_precision`` and kernel launch tuning (``grid``, ``block``, ``w_residency``,
         ``watchdog_ms``; see include/rqp.h).
         """
-        bad = set(launch_tuning) - {"grid", "block", "w_residency", "watchdog_ms", "poll_backoff_ns"}
+        bad = set(launch_tuning) - {"grid", "block", "w_residency", "watchdog_ms", "poll_backoff_ns", "prepoll_cycles",
+                                    "exchange_flags"}
         if bad:
             raise TypeError("setup() got unexpected keyword arguments {}".format(sorted(bad)))
         device = default_device() if device is None else torch.device(device)

@@ -174,7 +174,7 @@ def test_cabi_exports_match_header():
     lib.rqp_strerror.restype = ctypes.c_char_p
     assert lib.rqp_strerror(0) == b"ok" and b"watchdog" in lib.rqp_strerror(-6)
     assert ctypes.sizeof(_cabi.rqp_result) == 152
-    assert ctypes.sizeof(_cabi.rqp_settings) == 72
+    assert ctypes.sizeof(_cabi.rqp_settings) == 80
     assert ctypes.sizeof(_cabi.rqp_problem) == 96
     assert ctypes.sizeof(_cabi.rqp_state) == 16
     assert ctypes.sizeof(_cabi.rqp_batch) == 120

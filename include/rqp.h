@@ -177,11 +177,13 @@ typedef struct rqp_batch {
     void* pri_res;              /* [B] out (dtype)                                       */
     void* dua_res;              /* [B] out                                               */
     void* rho_estimate;         /* [B] out                                               */
-    /* GEMM engine: 0 auto (fp32 with W_hi/W_lo -> tcgen05 3xTF32, else tiled SIMT), 1 SIMT, 2 tcgen05 */
+    /* GEMM engine: 0 auto (fp32 with W_hi/W_lo -> tcgen05 3xTF32 cta_group::2, else tiled SIMT),
+     * 1 SIMT, 2 tcgen05 cta_group::1 (128x128 tiles), 3 tcgen05 cta_group::2 (256x256 pair tiles) */
     int32_t engine;
     int32_t reserved;
     const void* W_hi;           /* fp32 only: TF32 planes of W, same shape as W: W_hi = rna_tf32(W), */
-    const void* W_lo;           /*            W_lo = W - W_hi                                     */
+    const void* W_lo;           /*            W_lo = rna_tf32(W - W_hi)                            */
+    void* reserved_dbg;         /* NULL, or 16 x uint64 device counters (tcgen05 engine diagnostics) */
 } rqp_batch;
 
 int rqp_batch_workspace_size(const rqp_problem* prob, const rqp_settings* stng, int32_t B,

@@ -25,7 +25,7 @@
 
 namespace rqp {
 
-constexpr int BALIGN = 128;  // bucket alignment in slots = widest GEMM column tile
+constexpr int BALIGN = 256;  // bucket alignment in slots = widest GEMM column tile (cta_group::2 pair tile)
 
 template <typename T>
 struct BatchCtx {
@@ -437,8 +437,9 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     if (std::is_same<T, float>::value) {
         const bool have_planes = bt->W_hi != nullptr && bt->W_lo != nullptr;
         if (bt->engine == 2 && !have_planes) return RQP_ERR_BAD_ARG;
+        if (bt->engine == 3 && !have_planes) return RQP_ERR_BAD_ARG;
         use_tc = have_planes && bt->engine != 1;
-    } else if (bt->engine == 2) {
+    } else if (bt->engine == 2 || bt->engine == 3) {
         return RQP_ERR_UNSUPPORTED;   // tcgen05 has no fp64 kind; fp64 keeps the SIMT engine
     }
     c.tc = use_tc ? 1 : 0;
@@ -511,8 +512,18 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.Yh = reinterpret_cast<float*>(c.Vh[src ^ 1]); a.Yl = reinterpret_cast<float*>(c.Vl[src ^ 1]);
         a.Yplain = write_plain ? reinterpret_cast<float*>(c.V[src ^ 1]) : nullptr;
         a.D = D; a.nx = nx; a.nc = nc; a.ldv = ldv;
-        a.n_col_tiles = cap / BALIGN; a.n_row_tiles = (D + 127) / 128; a.k_blocks = (D + 31) / 32;
-        return tc_launch(map_wh, map_wl, map_xh[src], map_xl[src], a, sm_count, st);
+        a.k_blocks = (D + 31) / 32;
+        a.dbg = static_cast<unsigned long long*>(bt->reserved_dbg);
+        // auto: the CTA-pair kernel pays off once there are enough column tiles to fill the chip
+        // (measured crossover ~8k active columns at D = 960); below that the 1-CTA kernel has twice
+        // the parallelism per active column
+        const bool one_sm = bt->engine == 2 || (bt->engine != 3 && *nact_host < 8192);
+        if (one_sm) {                 // 1-CTA tiles: 128 rows x 128 columns
+            a.n_col_tiles = cap / 128; a.n_row_tiles = (D + 127) / 128;
+            return tc_launch(map_wh, map_wl, map_xh[src], map_xl[src], a, sm_count, st);
+        }
+        a.n_col_tiles = cap / 256; a.n_row_tiles = (D + 255) / 256;   // CTA-pair tiles: 256 x 256
+        return tc2_launch(map_wh, map_wl, map_xh[src], map_xl[src], a, sm_count, st);
     };
     auto gemm_iter = [&](int src) {
         GemmArgs<T> a;

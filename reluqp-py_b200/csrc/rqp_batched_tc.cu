@@ -7,12 +7,12 @@
 // so one k-step issues three tcgen05.mma.kind::tf32 into the same fp32 TMEM accumulator.  W planes
 // are split once at setup; the X planes of the NEXT iteration are produced by this kernel's epilogue.
 //
-// Structure (one persistent CTA per SM, 192 threads, warp specialised):
+// Structure (one persistent CTA per SM, 320 threads, warp specialised):
 //   warp 0    TMA producer: per k-block of 32 columns four 128x128B SWIZZLE_128B boxes
 //             (W_hi, W_lo rows of the tile's rho; X_hi, X_lo rows of the tile's columns) -> smem ring
 //   warp 1    MMA issuer (one elected lane): 4 k-steps x 3 MMAs (M128 N128 K8) per k-block into one of
 //             two TMEM accumulator stages; tcgen05.commit frees the smem slot / publishes the accumulator
-//   warps 2-5 epilogue: tcgen05.ld 32x32b (each warp its own 32-lane quarter), + bias, clamp rows of the
+//   warps 2-9 epilogue: tcgen05.ld 32x32b (two warps per 32-lane TMEM quarter, half the columns each), + bias, clamp rows of the
 //             z block against the column's l/u, split into TF32 hi/lo planes, coalesced stores (lanes =
 //             consecutive state rows of one column); optionally the plain fp32 state for the checks
 // Tiles: 128 state rows x 128 columns; column tiles never straddle a rho bucket (BALIGN = 128).
@@ -33,7 +33,8 @@ constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                 // 16 KB per op
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;                // W_hi, W_lo, X_hi, X_lo
 constexpr int TC_ACC_STAGES = 2;
 constexpr int TC_TMEM_COLS = TC_ACC_STAGES * TC_BN;              // 256
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int TC_EPI_WARPS = 8;
 constexpr size_t TC_SMEM_BYTES = size_t(TC_STAGES) * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 // ---------------------------------------------------------------------------------------------
@@ -131,6 +132,83 @@ __device__ __forceinline__ float tf32_rna(float x) {
     return __uint_as_float(r);
 }
 
+
+// Epilogue of one 32-column chunk of an accumulator tile for the thread owning state row m:
+// bias, clamp of z rows against the column's bounds, TF32 split, stores (lanes of a warp = consecutive
+// rows of one column -> 128-byte coalesced).  Written for a warp that runs almost alone on its SM
+// sub-partition: straight-line predicated code, pointer-increment addressing (no 64-bit multiply per
+// column), all global loads of a 16-column half issued before its first store (the compiler cannot
+// hoist loads above stores that may alias), slot->column map read once per chunk and broadcast by
+// shuffle.
+struct EpiRow {
+    const float* Lz;    // a.L + (m - nx)   (z rows only)
+    const float* Uz;
+    const float* bcol;  // a.bias_cols + m or null
+    float* ph;          // a.Yh + m
+    float* pl;
+    float* pp;          // a.Yplain + m or null
+    float bias_shared;
+    bool m_ok, is_z;
+};
+
+__device__ __forceinline__ void tc_epilogue_chunk(const TcArgs& a, const EpiRow& e, const uint32_t (&r)[32], int n0,
+                                                  int lane) {
+    const int o_lane = __ldg(a.orig + n0 + lane);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float lo[16], hi[16], bc[16];
+        int oj[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            oj[j] = __shfl_sync(0xffffffffu, o_lane, h * 16 + j);
+            const int oc = max(oj[j], 0) * a.nc;
+            lo[j] = -CUDART_INF_F;
+            hi[j] = CUDART_INF_F;
+            if (e.is_z) {
+                lo[j] = __ldg(e.Lz + oc);
+                hi[j] = __ldg(e.Uz + oc);
+            }
+            bc[j] = e.bias_shared;
+            if (e.bcol != nullptr && e.m_ok) bc[j] = __ldg(e.bcol + size_t(n0 + h * 16 + j) * a.D);
+        }
+        const size_t col0 = size_t(n0 + h * 16) * a.ldv;
+        float* ph = e.ph + col0;
+        float* pl = e.pl + col0;
+        float* pp = e.pp ? e.pp + col0 : nullptr;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float y = __uint_as_float(r[h * 16 + j]) + bc[j];
+            y = clamp_keep_nan(y, lo[j], hi[j]);
+            const float yh = tf32_rna(y);
+            const float yl = tf32_rna(y - yh);   // round (not truncate) the low plane: no one-sided bias
+            if (oj[j] >= 0 && e.m_ok) {
+                ph[0] = yh;
+                pl[0] = yl;
+                if (pp) pp[0] = y;
+            }
+            ph += a.ldv;
+            pl += a.ldv;
+            if (pp) pp += a.ldv;
+        }
+    }
+}
+
+__device__ __forceinline__ EpiRow make_epi_row(const TcArgs& a, int m, int rho) {
+    EpiRow e;
+    e.m_ok = m < a.D;
+    e.is_z = e.m_ok && m >= a.nx && m < a.nx + a.nc;
+    const int mz = e.is_z ? m - a.nx : 0;
+    e.Lz = a.L + mz;
+    e.Uz = a.U + mz;
+    const int mc = e.m_ok ? m : 0;
+    e.bcol = a.bias_cols ? a.bias_cols + mc : nullptr;
+    e.ph = a.Yh + mc;
+    e.pl = a.Yl + mc;
+    e.pp = a.Yplain ? a.Yplain + mc : nullptr;
+    e.bias_shared = (e.m_ok && a.bias_cols == nullptr) ? __ldg(a.b_all + size_t(rho) * a.D + m) : 0.f;
+    return e;
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
                       const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
@@ -152,7 +230,7 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_wh); prefetch_tmap(&map_wl); prefetch_tmap(&map_xh); prefetch_tmap(&map_xl);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < TC_ACC_STAGES; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
+        for (int s = 0; s < TC_ACC_STAGES; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, TC_EPI_WARPS); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TC_TMEM_COLS);
@@ -165,14 +243,17 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
         // ================= TMA producer =================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            long long w_empty = 0, t_all = clock64();
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const int ct = t / a.n_row_tiles, rt = t % a.n_row_tiles;
-                const int rho = a.tile_rho[ct];
+                const int rho = a.tile_rho[ct >> 1];          // tile_rho is per 256-column bucket tile
                 if (rho < 0) continue;
                 const int wrow = rho * a.D + rt * TC_BM;
                 const int xrow = ct * TC_BN;
                 for (int kb = 0; kb < a.k_blocks; ++kb) {
+                    const long long tw = clock64();
                     mbar_wait(empty + stage, phase ^ 1u);
+                    w_empty += clock64() - tw;
                     unsigned char* sp = base + size_t(stage) * TC_STAGE_BYTES;
                     mbar_expect_tx(full + stage, TC_STAGE_BYTES);
                     tma_load_2d(sp, &map_wh, kb * TC_BK, wrow, full + stage);
@@ -182,19 +263,26 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
+            if (a.dbg && blockIdx.x == 0) { a.dbg[0] = w_empty; a.dbg[1] = clock64() - t_all; }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+        long long w_full = 0, w_acc = 0, t_all = clock64(), ntile = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const int ct = t / a.n_row_tiles;
-            if (a.tile_rho[ct] < 0) continue;
+            if (a.tile_rho[ct >> 1] < 0) continue;
+            ntile++;
+            long long tw = clock64();
             mbar_wait(acc_empty + acc, acc_phase ^ 1u);   // epilogue has drained this accumulator
+            w_acc += clock64() - tw;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * TC_BN;
             for (int kb = 0; kb < a.k_blocks; ++kb) {
+                tw = clock64();
                 mbar_wait(full + stage, phase);
+                w_full += clock64() - tw;
                 tc_fence_after();
                 if (elect_one()) {
                     unsigned char* sp = base + size_t(stage) * TC_STAGE_BYTES;
@@ -217,53 +305,228 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
             }
             if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
         }
+        if (a.dbg && blockIdx.x == 0 && lane == 0) {
+            a.dbg[2] = w_full; a.dbg[3] = w_acc; a.dbg[4] = clock64() - t_all; a.dbg[5] = ntile;
+        }
     } else {
         // ================= epilogue (warps 2..5) =================
         const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter + 32)
         uint32_t acc = 0, acc_phase = 0;
+        long long w_accf = 0, t_all = clock64();
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const int ct = t / a.n_row_tiles, rt = t % a.n_row_tiles;
-            const int rho = a.tile_rho[ct];
+            const int rho = a.tile_rho[ct >> 1];
             if (rho < 0) continue;
+            const long long tw = clock64();
             mbar_wait(acc_full + acc, acc_phase);
+            w_accf += clock64() - tw;
             tc_fence_after();
             const int m = rt * TC_BM + quarter * 32 + lane;      // state row of this thread
-            const bool m_ok = m < a.D;
-            const bool is_z = m_ok && m >= a.nx && m < a.nx + a.nc;
-            const float bias_shared = (m_ok && a.bias_cols == nullptr) ? __ldg(a.b_all + size_t(rho) * a.D + m) : 0.f;
+            const EpiRow e = make_epi_row(a, m, rho);
             const uint32_t taddr = tmem_base + acc * TC_BN + (uint32_t(quarter * 32) << 16);
+            const int half = (warp - 2) >> 2;                     // which half of the tile's columns
 #pragma unroll 1
-            for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+            for (int c0 = half * (TC_BN / 2); c0 < (half + 1) * (TC_BN / 2); c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(taddr + c0, r);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = ct * TC_BN + c0 + j;
-                    const int o = __ldg(a.orig + n);          // warp-uniform
-                    if (o < 0 || !m_ok) continue;
-                    float y = __uint_as_float(r[j]);
-                    y += a.bias_cols ? a.bias_cols[size_t(n) * a.D + m] : bias_shared;
-                    if (is_z) {
-                        const float lo = __ldg(a.L + size_t(o) * a.nc + (m - a.nx));
-                        const float hi = __ldg(a.U + size_t(o) * a.nc + (m - a.nx));
-                        y = clamp_keep_nan(y, lo, hi);
-                    }
-                    const float yh = tf32_rna(y);
-                    const size_t idx = size_t(n) * a.ldv + m;
-                    a.Yh[idx] = yh;
-                    a.Yl[idx] = tf32_rna(y - yh);   // round (not truncate) the low plane: no one-sided bias
-                    if (a.Yplain) a.Yplain[idx] = y;
-                }
+                tc_epilogue_chunk(a, e, r, ct * TC_BN + c0, lane);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + acc);
             if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
         }
+        if (a.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) { a.dbg[6] = w_accf; a.dbg[7] = clock64() - t_all; }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, TC_TMEM_COLS);
+}
+
+// =============================================================================================
+// cta_group::2 variant: a CTA PAIR (cluster of 2, same TPC) computes a 256 x 256 output tile.
+// Each CTA stages its own 128 state rows of W (A operand) and its own 128 of the tile's 256 columns
+// (half of the B operand); the pair's MMA (issued by the leader, rank 0) reads A from each CTA's own
+// shared memory and B from BOTH, so every operand byte feeds twice the MMA work of the 1-CTA kernel.
+// Protocol (as in CUTLASS sm100 2-SM pipelines): only the leader arms the full barrier, with the bytes
+// of both CTAs; both CTAs' TMA loads complete on the leader's barrier (peer bit of the mbarrier
+// address cleared); tcgen05.commit multicasts to the barriers of both CTAs; both epilogues arrive
+// remotely on the leader's accumulator-empty barrier.
+// =============================================================================================
+constexpr int TC2_BN = 256;                                        // columns per pair tile
+constexpr int TC2_TMEM_COLS = TC_ACC_STAGES * TC2_BN;              // 512: all of TMEM
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;                     // cute::Sm100MmaPeerBitMask
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                                uint64_t* leader_bar_local_alias) {
+    // the barrier operand is THIS CTA's address of the barrier with the peer bit cleared = the leader's
+    const uint32_t bar = smem_u32(leader_bar_local_alias) & kPeerBitMask;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    const uint16_t mask = 3;   // both CTAs of the pair
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar_local_alias) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar_local_alias) & kPeerBitMask)
+                 : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+rqp_batched_tc2_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
+                       const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                       const TcArgs a) {
+    extern __shared__ unsigned char tc_smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) &
+                                                            ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + size_t(TC_STAGES) * TC_STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + TC_STAGES;
+    uint64_t* acc_full = bars + 2 * TC_STAGES;
+    uint64_t* acc_empty = acc_full + TC_ACC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + TC_ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();          // 0 = leader
+    const int pair = blockIdx.x >> 1;
+    const int n_pairs = gridDim.x >> 1;
+    const int n_tiles = a.n_col_tiles * a.n_row_tiles;   // pair tiles: 256 rows x 256 columns
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_wh); prefetch_tmap(&map_wl); prefetch_tmap(&map_xh); prefetch_tmap(&map_xl);
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < TC_ACC_STAGES; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 2 * TC_EPI_WARPS); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, TC2_TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();        // barriers of BOTH CTAs are initialised before any remote arrive
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs) =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int t = pair; t < n_tiles; t += n_pairs) {
+                const int ct = t / a.n_row_tiles, rt = t % a.n_row_tiles;
+                const int rho = a.tile_rho[ct];
+                if (rho < 0) continue;
+                const int wrow = rho * a.D + rt * 256 + int(rank) * TC_BM;     // own 128 state rows
+                const int xrow = ct * TC2_BN + int(rank) * 128;               // own half of the columns
+                for (int kb = 0; kb < a.k_blocks; ++kb) {
+                    mbar_wait(empty + stage, phase ^ 1u);
+                    unsigned char* sp = base + size_t(stage) * TC_STAGE_BYTES;
+                    if (rank == 0) mbar_expect_tx(full + stage, 2 * TC_STAGE_BYTES);
+                    tma_load_2d_2sm(sp, &map_wh, kb * TC_BK, wrow, full + stage);
+                    tma_load_2d_2sm(sp + TC_TILE_BYTES, &map_wl, kb * TC_BK, wrow, full + stage);
+                    tma_load_2d_2sm(sp + 2 * TC_TILE_BYTES, &map_xh, kb * TC_BK, xrow, full + stage);
+                    tma_load_2d_2sm(sp + 3 * TC_TILE_BYTES, &map_xl, kb * TC_BK, xrow, full + stage);
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (rank == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(256, TC2_BN);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int t = pair; t < n_tiles; t += n_pairs) {
+                const int ct = t / a.n_row_tiles;
+                if (a.tile_rho[ct] < 0) continue;
+                mbar_wait(acc_empty + acc, acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * TC2_BN;
+                for (int kb = 0; kb < a.k_blocks; ++kb) {
+                    mbar_wait(full + stage, phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        unsigned char* sp = base + size_t(stage) * TC_STAGE_BYTES;
+                        const uint64_t dwh = make_kmajor_sw128_desc(sp);
+                        const uint64_t dwl = make_kmajor_sw128_desc(sp + TC_TILE_BYTES);
+                        const uint64_t dxh = make_kmajor_sw128_desc(sp + 2 * TC_TILE_BYTES);
+                        const uint64_t dxl = make_kmajor_sw128_desc(sp + 3 * TC_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 8; ++k) {
+                            const uint64_t off = uint64_t((k * 8 * 4) >> 4);
+                            umma_tf32_2sm(d_tmem, dwh + off, dxh + off, idesc, (kb | k) != 0 ? 1u : 0u);
+                            umma_tf32_2sm(d_tmem, dwh + off, dxl + off, idesc, 1u);
+                            umma_tf32_2sm(d_tmem, dwl + off, dxh + off, idesc, 1u);
+                        }
+                        umma_commit_2sm(empty + stage);
+                        if (kb == a.k_blocks - 1) umma_commit_2sm(acc_full + acc);
+                    }
+                    __syncwarp();
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                }
+                if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ================= epilogue (warps 2..5 of both CTAs) =================
+        const int quarter = warp & 3;
+        uint32_t acc = 0, acc_phase = 0;
+        for (int t = pair; t < n_tiles; t += n_pairs) {
+            const int ct = t / a.n_row_tiles, rt = t % a.n_row_tiles;
+            const int rho = a.tile_rho[ct];
+            if (rho < 0) continue;
+            mbar_wait(acc_full + acc, acc_phase);
+            tc_fence_after();
+            const int m = rt * 256 + int(rank) * TC_BM + quarter * 32 + lane;
+            const EpiRow e = make_epi_row(a, m, rho);
+            const uint32_t taddr = tmem_base + acc * TC2_BN + (uint32_t(quarter * 32) << 16);
+            const int half = (warp - 2) >> 2;
+#pragma unroll 1
+            for (int c0 = half * (TC2_BN / 2); c0 < (half + 1) * (TC2_BN / 2); c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c0, r);
+                tc_epilogue_chunk(a, e, r, ct * TC2_BN + c0, lane);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(acc_empty + acc);
+            if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, TC2_TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -297,6 +560,22 @@ int tc_make_map(CUtensorMap* map, const void* ptr, long long rows, long long col
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? RQP_OK : RQP_ERR_CUDA;
+}
+
+int tc2_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,
+               const TcArgs& args, int sm_count, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        RQP_CUDA_TRY(cudaFuncSetAttribute(rqp_batched_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          int(TC_SMEM_BYTES)));
+        attr_set = true;
+    }
+    const int n_tiles = args.n_col_tiles * args.n_row_tiles;
+    int pairs = sm_count / 2;
+    if (n_tiles < pairs) pairs = n_tiles;
+    rqp_batched_tc2_kernel<<<2 * pairs, TC_THREADS, TC_SMEM_BYTES, st>>>(wh, wl, xh, xl, args);
+    RQP_CUDA_TRY(cudaGetLastError());
+    return RQP_OK;
 }
 
 int tc_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,

@@ -105,6 +105,10 @@ class BatchEngine(object):
         if dt == torch.float32 and engine != 1:
             wh, wl = self._tf32_planes()
             bt.W_hi, bt.W_lo = wh.data_ptr(), wl.data_ptr()
+        self.dbg = None
+        if getattr(self, "want_dbg", False):
+            self.dbg = torch.zeros(16, dtype=torch.int64, device=dev)
+            bt.reserved_dbg = self.dbg.data_ptr()
         sweeps = C.c_int32(0)
         start = torch.cuda.Event(enable_timing=True)
         end = torch.cuda.Event(enable_timing=True)

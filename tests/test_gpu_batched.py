@@ -106,16 +106,21 @@ def test_tc_engine_matches_simt_for_fixed_iterations():
         r64 = gpu_model(prob, **kw).solve_batch(L, U)
         m32 = gpu_model(prob, precision=torch.float32, **kw)
         rs = m32.solve_batch(L, U, engine=1)
-        rt = m32.solve_batch(L, U, engine=2)
         v64 = torch.cat([r64.x, r64.z, r64.lam], 1).double()
         vs = torch.cat([rs.x, rs.z, rs.lam], 1).double()
-        vt = torch.cat([rt.x, rt.z, rt.lam], 1).double()
         scale = float(v64.abs().max())
-        assert not torch.isnan(vt).any()
-        assert float((vt - vs).abs().max()) <= tol * scale, it
-        # the tensor-core engine is as close to fp64 as plain fp32 FMA is (within 4x)
-        assert float((vt - v64).abs().max()) <= 4 * float((vs - v64).abs().max()) + 1e-6 * scale, it
-        assert rt.status == ["max_iters_reached"] * 256 and int(rt.iter[0]) == it
+        vts = []
+        for eng in (2, 3):            # cta_group::1 (128x128 tiles) and cta_group::2 (256x256 pair tiles)
+            rt = m32.solve_batch(L, U, engine=eng)
+            vt = torch.cat([rt.x, rt.z, rt.lam], 1).double()
+            assert not torch.isnan(vt).any()
+            assert float((vt - vs).abs().max()) <= tol * scale, (it, eng)
+            # the tensor-core engine is as close to fp64 as plain fp32 FMA is (within 4x)
+            assert float((vt - v64).abs().max()) <= 4 * float((vs - v64).abs().max()) + 1e-6 * scale, (it, eng)
+            assert rt.status == ["max_iters_reached"] * 256 and int(rt.iter[0]) == it
+            vts.append(vt)
+        # both tcgen05 kernels execute the same MMAs in the same k order: bit-identical results
+        assert torch.equal(vts[0], vts[1]), it
 
 
 def test_batched_fp32_solution_quality(capsys):
@@ -134,7 +139,7 @@ def test_batched_fp32_solution_quality(capsys):
     H, g, A = (torch.as_tensor(t, dtype=torch.float64, device="cuda") for t in (plant.H, plant.g, plant.A))
     # the fp32 solver clamps against the fp32-rounded bounds
     Ld, Ud = (torch.as_tensor(t, dtype=torch.float32, device="cuda").double() for t in (L, U))
-    for eng, name in ((1, "simt fp32"), (2, "tcgen05 3xTF32")):
+    for eng, name in ((1, "simt fp32"), (2, "tcgen05 3xTF32 1-CTA"), (3, "tcgen05 3xTF32 CTA pair")):
         r = m32.solve_batch(L, U, engine=eng)
         e32 = ((r.x.double() - xstar).abs().amax(1) / scale).cpu().numpy()
         x, z, lam = r.x.double(), r.z.double(), r.lam.double()

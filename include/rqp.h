@@ -91,8 +91,9 @@ typedef struct rqp_settings {
     /* launch tuning; 0 = choose automatically */
     int32_t grid;               /* number of CTAs (<= SM count)                         */
     int32_t block;              /* threads per CTA: 256 or 512                          */
-    int32_t w_residency;        /* 0 auto, 1 force shared-memory resident, 2 force streamed,
-                                   3 force register resident                             */
+    int32_t w_residency;        /* 0 auto, 1 force shared-memory resident, 2 force streamed
+                                   with register loads, 3 force register resident, 4 force
+                                   streamed through the bulk-copy shared-memory ring     */
     int32_t watchdog_ms;        /* 0 = 4000 ms per in-kernel wait                       */
     int32_t prepoll_cycles;     /* tuning: SM cycles to spin after the CTA barrier before the
                                    first exchange poll (0 = default 600, < 0 = none)      */

@@ -8,7 +8,7 @@
 namespace rqp {
 
 struct SinglePlan {
-    int grid, block, cpt, rpc, rows_smem, rmode;
+    int grid, block, cpt, rpc, rows_smem, rmode, ring;
     size_t smem_bytes;
     size_t vcells_bytes, pcells_bytes, ws_bytes;
 };

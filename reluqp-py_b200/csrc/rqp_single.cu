@@ -33,6 +33,7 @@
 namespace rqp {
 
 constexpr int RM = 8;  // rows per register chunk
+constexpr int RING_STAGES = 4;   // streamed-slab ring: 4 stages of RM rows x (NT * 16) bytes
 
 struct SingleParams {
     const void* W;
@@ -63,6 +64,7 @@ struct SingleParams {
     int backoff_ns; // sleep between failed exchange polls
     int prepoll_cycles;   // spin this many SM cycles after the CTA barrier before the first poll
     int exch_flags;       // bit 0: CTA barrier after the publish store (polls queue behind it)
+    int ring;             // 1: stream the slab through a shared-memory ring filled by bulk async copies
 };
 
 template <typename T>
@@ -178,14 +180,16 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
 
     // ---- shared memory carve-up
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    T* Ws = reinterpret_cast<T*>(smem_raw);                    // [rows_smem][ldw]
-    T* vs = Ws + size_t(p.rows_smem) * ldw;                    // [ldw]   (check phase only)
+    T* Ws = reinterpret_cast<T*>(smem_raw);                    // [rows_smem][ldw], or the streaming ring
+    const size_t ws_elems = p.ring ? size_t(RING_STAGES) * RM * NT * VEC : size_t(p.rows_smem) * ldw;
+    T* vs = Ws + ws_elems;                                     // [ldw]   (check phase only)
     T* red = vs + ldw;                                         // [2][NW][rpc_pad]
     size_t off = (reinterpret_cast<unsigned char*>(red + 2 * NW * rpc_pad) - smem_raw + 15) & ~size_t(15);
     double* part = reinterpret_cast<double*>(smem_raw + off);  // [NW][8]
     double* tot = part + NW * 8;                               // [NW][8]
     Decision* dec = reinterpret_cast<Decision*>(tot + NW * 8);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(dec + 1);
+    uint64_t* rbar = mbar + 1;                                 // [RING_STAGES] ring "full" barriers
 
     Watchdog wd{p.watchdog_ns, p.abort_flag, 0, 0};
     const uint32_t epoch = p.epoch;
@@ -221,14 +225,58 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
     uint32_t mbar_parity = 0;
     if (tid == 0) {
         mbar_init(mbar, 1);
+        for (int s = 0; s < RING_STAGES; ++s) mbar_init(rbar + s, 1);
         fence_mbar_init();
     }
     __syncthreads();
+    // ---- streaming ring (HBM-bound sizes): tiles of RM rows x (NT*VEC) columns of the slab, in the
+    // order (row chunk, column chunk), flow through RING_STAGES shared-memory stages filled by 1-D bulk
+    // async copies (one per row); the DMA engine keeps ~96 KB in flight per SM independent of registers,
+    // and the stream runs continuously across iterations (the next iteration's first tiles land while
+    // the exchange is waiting).
+    const int cpt_rt = (nvec + NT - 1) / NT;          // column chunks actually present
+    const int ring_T = nchunks * cpt_rt;              // tiles per iteration
+    uint32_t ring_phase = 0;                          // bit s: parity to wait for on stage s
+    int ring_cstage = 0, ring_pnext = 0;
+    auto ring_issue = [&](int t, int stage, int ri) {  // thread 0 only
+        const int ch = t / cpt_rt, ic = t - ch * cpt_rt;
+        const int nr = min(RM, rows - ch * RM);
+        const int e0 = ic * NT * VEC;
+        const uint32_t cb = uint32_t(min(NT * VEC, int(ldw) - e0)) * uint32_t(sizeof(T));
+        const T* src = Wall + (size_t(ri) * D + r0 + size_t(ch) * RM) * ldw + e0;
+        unsigned char* dst = reinterpret_cast<unsigned char*>(Ws) + size_t(stage) * RM * NT * 16;
+        mbar_expect_tx(rbar + stage, uint32_t(nr) * cb);
+        for (int r = 0; r < nr; ++r) bulk_g2s(dst + size_t(r) * NT * 16, src + size_t(r) * ldw, cb, rbar + stage);
+    };
+    auto ring_wait = [&](int stage) -> bool {
+        wd.arm();
+        while (!mbar_try_wait(rbar + stage, (ring_phase >> stage) & 1u)) {
+            if (wd.expired()) return false;
+        }
+        ring_phase ^= 1u << stage;
+        return true;
+    };
+    auto ring_start = [&](int ri) {                    // all stages idle -> fill with tiles 0..S-1
+        if (tid == 0)
+            for (int s = 0; s < RING_STAGES; ++s) ring_issue(s % ring_T, s, ri);
+        ring_cstage = 0;
+        ring_pnext = RING_STAGES % ring_T;
+    };
+    auto ring_drain = [&]() -> bool {                  // wait until no bulk copy is in flight
+        bool good = true;
+        for (int s = 0; s < RING_STAGES; ++s) good = ring_wait(s) && good;
+        return good;
+    };
     Vec16<T> wreg[RMODE ? RM : 1][RMODE ? CPT : 1];
     long long ph[8] = {0, 0, 0, 0, 0, 0, 0, RMODE ? 1 : 0};
     auto stage_slab = [&](int ri) {
         // caller guarantees every thread is past its last read of Ws (a __syncthreads)
         const long long ts = clock64();
+        if (p.ring) {
+            ring_start(ri);
+            ph[6] += clock64() - ts;
+            return true;
+        }
         if (RMODE) {
             const T* Wg = Wall + (size_t(ri) * D + r0) * ldw;
 #pragma unroll
@@ -424,6 +472,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
             rho_ind = new_ri;
             n_switch += 1;
             if (is_fin) my_b = ball[size_t(rho_ind) * D + my_row];
+            if (p.ring && !ring_drain()) good = false;   // the ring holds tiles of the old rho
             if (!stage_slab(rho_ind)) good = false;
             if (__syncthreads_or(!good)) return false;
         } else {
@@ -498,6 +547,33 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 }
                 warp_multi_reduce8(acc, lane);
                 if ((lane & 3) == 0) redk[lane >> 2] = acc[0];
+            } else if (p.ring) {
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    const int rbase = ch * RM;
+                    const int nr = min(RM, rows - rbase);
+                    T acc[RM];
+#pragma unroll
+                    for (int r = 0; r < RM; ++r) acc[r] = T(0);
+#pragma unroll
+                    for (int i = 0; i < CPT; ++i) {
+                        if (i < cpt_rt) {                       // uniform
+                            const int stage = ring_cstage;
+                            if (!ring_wait(stage)) ok = false;
+                            const T* sp = Ws + size_t(stage) * RM * NT * VEC + size_t(tid) * VEC;
+                            if (tid + i * NT < nvec) {
+#pragma unroll
+                                for (int r = 0; r < RM; ++r)
+                                    if (r < nr) acc[r] = Vec16<T>::lds(sp + size_t(r) * NT * VEC).dot(vv[i], acc[r]);
+                            }
+                            __syncthreads();                    // every warp is done with this stage
+                            if (tid == 0) ring_issue(ring_pnext, stage, rho_ind);
+                            ring_pnext = (ring_pnext + 1 == ring_T) ? 0 : ring_pnext + 1;
+                            ring_cstage = (stage + 1 == RING_STAGES) ? 0 : stage + 1;
+                        }
+                    }
+                    warp_multi_reduce8(acc, lane);
+                    if ((lane & 3) == 0) redk[rbase + (lane >> 2)] = acc[0];
+                }
             } else
             for (int ch = 0; ch < nchunks; ++ch) {
                 const int rbase = ch * RM;
@@ -555,6 +631,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
         if (!residual_pass(k, epoch + uint32_t(p.max_iter) + 1u, true)) aborted = true;
     }
 
+    if (p.ring) ring_drain();   // no bulk copy may still target this CTA's shared memory at exit
     if (is_fin) static_cast<T*>(p.v)[my_row] = my_v;
     if (blockIdx.x == 0 && tid == 0) {
         rqp_result r;
@@ -590,7 +667,7 @@ static size_t smem_fixed_bytes(int elem, long long ldw, int rpc, int block) {
     o += size_t(2) * NW * rpc_pad * elem;          // red
     o = (o + 15) & ~size_t(15);
     o += size_t(2) * NW * 8 * sizeof(double);      // part, tot
-    o += sizeof(Decision) + 16;                    // dec, mbar
+    o += sizeof(Decision) + 16 + 8 * RING_STAGES;  // dec, mbar, ring barriers
     return o;
 }
 
@@ -631,12 +708,22 @@ int plan_single(const rqp_problem* prob, const rqp_settings* stng, const rqp_cap
     if (stng->w_residency == 3 && !can_reg) return RQP_ERR_UNSUPPORTED;
     plan->rmode = (stng->w_residency == 3 || (stng->w_residency == 0 && can_reg)) ? 1 : 0;
     if (plan->rmode) rows_smem = 0;
+    // streaming ring: slabs too large for L2 (W_rho > ~96 MB) are HBM bound; a bulk-copy ring gives
+    // the DMA engine the memory-level parallelism that 8 warps of register loads cannot
+    const size_t ring_bytes = size_t(RING_STAGES) * RM * 256 * 16;
+    const int tiles = ((rpc + RM - 1) / RM) * ((nvec + 255) / 256);
+    const bool can_ring = block == 256 && !plan->rmode && tiles >= RING_STAGES && fixed + ring_bytes + 512 <= cap;
+    const bool want_ring = stng->w_residency == 4 ||
+                           (stng->w_residency == 0 && size_t(D) * prob->ldw * elem > (size_t(96) << 20));
+    if (stng->w_residency == 4 && !can_ring) return RQP_ERR_UNSUPPORTED;
+    plan->ring = (want_ring && can_ring) ? 1 : 0;
+    if (plan->ring) rows_smem = 0;
     plan->grid = grid;
     plan->block = block;
     plan->cpt = cpt;
     plan->rpc = rpc;
     plan->rows_smem = rows_smem;
-    plan->smem_bytes = fixed + size_t(rows_smem) * row_bytes + 128;
+    plan->smem_bytes = fixed + (plan->ring ? ring_bytes : size_t(rows_smem) * row_bytes) + 128;
     plan->vcells_bytes = size_t(2) * nvec * 4 * sizeof(uint64_t);
     plan->pcells_bytes = size_t(2) * caps.sm_count * 16 * sizeof(uint64_t);
     plan->ws_bytes = 256 + plan->vcells_bytes + plan->pcells_bytes;
@@ -729,6 +816,7 @@ int launch_single(const rqp_problem* prob, const rqp_settings* stng, rqp_state* 
     // publish store is not queued behind ~900 early poll requests of the same SM); < 0 = none
     prm.prepoll_cycles = stng->prepoll_cycles == 0 ? 600 : (stng->prepoll_cycles < 0 ? 0 : stng->prepoll_cycles);
     prm.exch_flags = stng->exchange_flags;
+    prm.ring = plan.ring;
 
     if (prob->dtype == RQP_F64) {
         rc = plan.block == 256 ? launch_cpt<double, 256>(prm, plan, stream) : launch_cpt<double, 512>(prm, plan, stream);

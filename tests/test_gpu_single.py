@@ -235,7 +235,9 @@ def test_launch_geometries_agree(golden):
     base = None
     for tuning in (dict(), dict(grid=2), dict(grid=7), dict(grid=148), dict(block=512),
                    dict(w_residency=1), dict(w_residency=2), dict(grid=34, w_residency=3),
-                   dict(grid=33, w_residency=2, block=512), dict(poll_backoff_ns=100)):
+                   dict(grid=33, w_residency=2, block=512), dict(poll_backoff_ns=100),
+                   dict(grid=7, w_residency=4), dict(grid=5, w_residency=4), dict(prepoll_cycles=-1),
+                   dict(exchange_flags=1)):
         m = gpu_model(prob, eps_abs=1e-6, **tuning)
         res = m.solve()
         x, _ = state_of(m, res)

@@ -267,6 +267,9 @@ class _Engine(object):
         if v.device != self.device or v.dtype != self.dtype or not v.is_contiguous() or v.numel() != self.D:
             raise ValueError("state vector must be a contiguous {} tensor of length {} on {}".format(
                 self.dtype, self.D, self.device))
+        if torch.cuda.current_device() == self.device.index:
+            self.launch(v, rho_ind, max_iter, adaptive)
+            return self.finish()
         with torch.cuda.device(self.device):
             self.launch(v, rho_ind, max_iter, adaptive)
             return self.finish()
@@ -391,7 +394,7 @@ class ReLU_QP(object):
         assert Hx is None and Ax is None, "updating Hx and Ax is not supported yet"
         st = self.settings
         nx, nc = self.QP.nx, self.QP.nc
-        self._timer.tic()
+        self._timer.tic_host()
         spans = [sp for sp in (self._stage(0, nx, g) if g is not None else None,
                                self._stage(nx, nx + nc, l) if l is not None else None,
                                self._stage(nx + nc, nx + 2 * nc, u) if u is not None else None) if sp]
@@ -448,7 +451,7 @@ class ReLU_QP(object):
         st = self.settings
         nx, nc = self.QP.nx, self.QP.nc
         eng = self._engine
-        self._timer.tic()
+        self._timer.tic_host()      # solve() ends with a stream synchronise: host time == device time
         if st.verbose and st.adaptive_rho:
             eng.enable_trace(st.max_iter // max(1, st.check_interval) + 2)
         r = eng.run(self.output, self.rho_ind)
@@ -496,7 +499,7 @@ class ReLU_QP(object):
         info.pri_res = torch.tensor(pri_res, dtype=dt)
         info.dua_res = torch.tensor(dua_res, dtype=dt)
         info.rho_estimate = torch.tensor(rho_estimate, dtype=dt)
-        run_time = self._timer.toc()
+        run_time = self._timer.toc(sync=False)
         info.run_time = run_time
         info.solve_time = info.update_time + run_time
         if not self.settings.warm_starting:
@@ -509,7 +512,9 @@ class ReLU_QP(object):
         nx, nc = self.QP.nx, self.QP.nc
         self.output = torch.zeros(nx + 2 * nc, device=st.device, dtype=st.precision)
         self.x, self.z, self.lam = self.output[:nx], self.output[nx:nx + nc], self.output[nx + nc:]
-        self.rho_ind = int(np.argmin(np.abs(np.asarray(self.layers.rho_list) - st.rho)))
+        if getattr(self, "_rho_ind0", None) is None or self._rho_ind0[0] is not self.layers:
+            self._rho_ind0 = (self.layers, int(np.argmin(np.abs(np.asarray(self.layers.rho_list) - st.rho))))
+        self.rho_ind = self._rho_ind0[1]
         return None
 
     # ------------------------------------------------------------------ batched (additive API)

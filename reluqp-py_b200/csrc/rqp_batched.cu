@@ -189,9 +189,13 @@ __global__ void batch_scatter(BatchCtx<T> c, int vsrc, int src, int iter_now, in
 
 // ------------------------------------------------------------------------------------------------
 // Tiled SIMT GEMM:  Out[n][mo + m] = sum_k Mat[m][k] * V[n][ko + k]   (+ epilogue)
-// 64 x 64 output tile, K step 16, 256 threads, 4 x 4 per thread.
+// 128 x 128 output tile, K step 8, 256 threads, 8 x 8 accumulators per thread (2 bytes of shared memory
+// traffic per FMA: at the 128 B/clk limit for fp64), global loads of the next k-slab prefetched into
+// registers while the current one is multiplied, double-buffered shared memory (one barrier per slab).
+// Thread (tx = tid % 16, ty = tid / 16) owns rows m = 32 j + 2 tx + {0,1} (j < 4) -- consecutive lanes
+// read consecutive 16-byte pieces of a shared-memory row, conflict free -- and columns n = 8 ty + i.
 // ------------------------------------------------------------------------------------------------
-constexpr int GM = 64, GN = 64, GK = 16;
+constexpr int GM = 128, GN = 128, GK = 8, GPAD = 4;
 enum { EPI_ITER = 0, EPI_RAW = 1 };
 
 template <typename T>
@@ -214,14 +218,113 @@ struct GemmArgs {
 };
 
 template <typename T, int EPI>
-__global__ void __launch_bounds__(256) bgemm_simt(GemmArgs<T> a) {
+__global__ void __launch_bounds__(256, 1) bgemm_simt(GemmArgs<T> a) {
     const int n0 = blockIdx.y * GN;
     const int rho_i = a.tile_rho[n0 / BALIGN];
     if (rho_i < 0) return;
     const int m0 = blockIdx.x * GM;
     const T* __restrict__ Mat = a.mat + (EPI == EPI_ITER ? size_t(rho_i) * a.mat_stride : 0);
-    __shared__ T As[GK][GM + 4];
-    __shared__ T Bs[GK][GN + 4];
+    __shared__ __align__(16) T As[2][GK][GM + GPAD];
+    __shared__ __align__(16) T Bs[2][GK][GN + GPAD];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int lr = tid >> 1, lk = (tid & 1) * 4;          // loader: tile row lr (0..127), k offset 0 or 4
+    const T* __restrict__ arow = Mat + size_t(min(m0 + lr, a.M - 1)) * a.ldm;
+    const T* __restrict__ brow = a.X + size_t(n0 + lr) * a.ldx + a.ko;
+    const bool arow_ok = (m0 + lr) < a.M;
+    T acc[8][8];   // [column i][row slot 2 j + e]
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = T(0);
+    T ra[4], rb[4];
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = k0 + lk + e;
+            const bool kin = k < a.K;
+            ra[e] = (kin && arow_ok) ? __ldg(arow + k) : T(0);
+            rb[e] = kin ? brow[k] : T(0);
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            As[buf][lk + e][lr] = ra[e];
+            Bs[buf][lk + e][lr] = rb[e];
+        }
+    };
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = 0; k0 < a.K; k0 += GK) {
+        const bool more = (k0 + GK) < a.K;
+        if (more) gload(k0 + GK);            // in flight during the 512 FMAs below
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            T av[8], bv[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                av[2 * j] = As[buf][k][32 * j + 2 * tx];
+                av[2 * j + 1] = As[buf][k][32 * j + 2 * tx + 1];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bv[i] = Bs[buf][k][8 * ty + i];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fma(av[j], bv[i], acc[i][j]);
+        }
+        if (more) {
+            sstore(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+    // epilogue: acc[i][2 j + e] is column n0 + 8 ty + i, row m0 + 32 j + 2 tx + e
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int n = n0 + 8 * ty + i;
+        int o = 0;
+        if (EPI == EPI_ITER) {
+            o = a.orig[n];
+            if (o < 0) continue;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int m = m0 + 32 * j + 2 * tx + e;
+                if (m >= a.M) continue;
+                T y = acc[i][2 * j + e];
+                if (EPI == EPI_ITER) {
+                    y += a.bias_cols ? a.bias_cols[size_t(n) * a.D + m] : __ldg(a.b_all + size_t(rho_i) * a.D + m);
+                    if (m >= a.nx && m < a.nx + a.nc) {
+                        const T lo = __ldg(a.L + size_t(o) * a.nc + (m - a.nx));
+                        const T hi = __ldg(a.U + size_t(o) * a.nc + (m - a.nx));
+                        y = clamp_keep_nan(y, lo, hi);
+                    }
+                }
+                a.out[size_t(n) * a.ldo + a.mo + m] = y;
+            }
+        }
+    }
+}
+
+// Small-tile variant (64 x 64 x 16, 4 x 4 per thread): four times as many CTAs per active column, used
+// while few columns are active (latency matters more than shared-memory traffic there).
+constexpr int SM64 = 64, SK64 = 16;
+
+template <typename T, int EPI>
+__global__ void __launch_bounds__(256) bgemm_simt64(GemmArgs<T> a) {
+    const int n0 = blockIdx.y * SM64;
+    const int rho_i = a.tile_rho[n0 / BALIGN];
+    if (rho_i < 0) return;
+    const int m0 = blockIdx.x * SM64;
+    const T* __restrict__ Mat = a.mat + (EPI == EPI_ITER ? size_t(rho_i) * a.mat_stride : 0);
+    __shared__ T As[SK64][SM64 + 4];
+    __shared__ T Bs[SK64][SM64 + 4];
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;  // tx -> m, ty -> n
     const int lr = tid >> 2, lc = (tid & 3) * 4;  // loader: row lr (0..63), k offset lc
@@ -230,7 +333,7 @@ __global__ void __launch_bounds__(256) bgemm_simt(GemmArgs<T> a) {
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
-    for (int k0 = 0; k0 < a.K; k0 += GK) {
+    for (int k0 = 0; k0 < a.K; k0 += SK64) {
         T ra[4], rb[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -247,7 +350,7 @@ __global__ void __launch_bounds__(256) bgemm_simt(GemmArgs<T> a) {
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < GK; ++k) {
+        for (int k = 0; k < SK64; ++k) {
             T av[4], bv[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -533,8 +636,11 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.M = D; a.K = D; a.tile_rho = c.tile_rho;
         a.b_all = c.b_all; a.bias_cols = with_g ? c.Bias[lcur] : nullptr;
         a.L = c.L; a.U = c.U; a.orig = c.orig[lcur]; a.nx = nx; a.nc = nc; a.D = D;
-        dim3 grid((D + GM - 1) / GM, cap / GN);
-        bgemm_simt<T, EPI_ITER><<<grid, 256, 0, st>>>(a);
+        if (*nact_host < 2048) {
+            bgemm_simt64<T, EPI_ITER><<<dim3((D + SM64 - 1) / SM64, cap / SM64), 256, 0, st>>>(a);
+        } else {
+            bgemm_simt<T, EPI_ITER><<<dim3((D + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
+        }
     };
     auto gemm_res = [&](int src) {
         GemmArgs<T> a;
@@ -543,13 +649,17 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.orig = c.orig[lcur]; a.nx = nx; a.nc = nc; a.D = D;
         // A x
         a.mat = c.A; a.ldm = nx; a.M = nc; a.K = nx; a.ko = 0; a.mo = 0;
-        bgemm_simt<T, EPI_RAW><<<dim3((nc + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
+        const bool small = *nact_host < 2048;
+        if (small) bgemm_simt64<T, EPI_RAW><<<dim3((nc + SM64 - 1) / SM64, cap / SM64), 256, 0, st>>>(a);
+        else bgemm_simt<T, EPI_RAW><<<dim3((nc + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
         // H x
         a.mat = c.H; a.ldm = nx; a.M = nx; a.K = nx; a.ko = 0; a.mo = nc;
-        bgemm_simt<T, EPI_RAW><<<dim3((nx + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
+        if (small) bgemm_simt64<T, EPI_RAW><<<dim3((nx + SM64 - 1) / SM64, cap / SM64), 256, 0, st>>>(a);
+        else bgemm_simt<T, EPI_RAW><<<dim3((nx + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
         // A' lambda
         a.mat = c.AT; a.ldm = nc; a.M = nx; a.K = nc; a.ko = nx + nc; a.mo = nc + nx;
-        bgemm_simt<T, EPI_RAW><<<dim3((nx + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
+        if (small) bgemm_simt64<T, EPI_RAW><<<dim3((nx + SM64 - 1) / SM64, cap / SM64), 256, 0, st>>>(a);
+        else bgemm_simt<T, EPI_RAW><<<dim3((nx + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
     };
 
     // ---- start: v = 0, rho index from the caller, first grouping into buffer 0

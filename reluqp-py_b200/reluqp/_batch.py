@@ -86,10 +86,13 @@ class BatchEngine(object):
             if G.shape != (B, nx):
                 raise ValueError("g must have shape [B, {}]".format(nx))
         self._settings()
-        ws = self._workspace(B)
         ldv = (D + 3) // 4 * 4
         V = torch.zeros((B, ldv), dtype=dt, device=dev)
         rho_ind0 = int(np.argmin(np.abs(np.asarray(sv.layers.rho_list) - sv.settings.rho)))
+        small = 64 if dt == torch.float64 else 24
+        if engine == 0 and G is None and B <= small:
+            return self._solve_small(L, U, V, rho_ind0, nx, nc, D)
+        ws = self._workspace(B)
         rho_ind = torch.full((B,), rho_ind0, dtype=torch.int32, device=dev)
         it = torch.zeros(B, dtype=torch.int32, device=dev)
         status = torch.full((B,), _cabi.RQP_STATUS_RUNNING, dtype=torch.int32, device=dev)
@@ -124,6 +127,39 @@ class BatchEngine(object):
         return BatchResults(x=V[:, :nx], z=V[:, nx:nx + nc], lam=V[:, nx + nc:D], iter=it, status_code=status,
                             pri_res=pri, dua_res=dua, rho_estimate=rho, rho_ind=rho_ind,
                             run_time=start.elapsed_time(end) / 1000.0, sweeps=int(sweeps.value))
+
+
+    def _solve_small(self, L, U, V, rho_ind0, nx, nc, D):
+        """Few columns: the batched GEMM engines sit at their per-iteration latency floor (tens of
+        microseconds) while the persistent single-QP kernel iterates in ~1.5 us, so column j is
+        solved by that kernel directly (same semantics by construction: it IS the single solve)."""
+        sv = self.solver
+        eng, qp = sv._engine, sv.QP
+        dev, dt = self.device, self.dtype
+        B = L.shape[0]
+        keep_l, keep_u = qp.l.clone(), qp.u.clone()
+        it, status, rho_ind, pri, dua, rho = [], [], [], [], [], []
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        try:
+            for j in range(B):
+                qp.l.copy_(L[j])
+                qp.u.copy_(U[j])
+                r = eng.run(V[j, :D], rho_ind0)
+                it.append(int(r.iter)); status.append(int(r.status)); rho_ind.append(int(r.rho_ind))
+                pri.append(float(r.pri_res)); dua.append(float(r.dua_res)); rho.append(float(r.rho_estimate))
+        finally:
+            qp.l.copy_(keep_l)
+            qp.u.copy_(keep_u)
+        t1.record()
+        t1.synchronize()
+        i32 = dict(dtype=torch.int32, device=dev)
+        return BatchResults(x=V[:, :nx], z=V[:, nx:nx + nc], lam=V[:, nx + nc:D], iter=torch.tensor(it, **i32),
+                            status_code=torch.tensor(status, **i32), pri_res=torch.tensor(pri, dtype=dt, device=dev),
+                            dua_res=torch.tensor(dua, dtype=dt, device=dev),
+                            rho_estimate=torch.tensor(rho, dtype=dt, device=dev),
+                            rho_ind=torch.tensor(rho_ind, **i32), run_time=t0.elapsed_time(t1) / 1000.0, sweeps=0)
 
 
 # ------------------------------------------------------------------------------------------------

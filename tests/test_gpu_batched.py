@@ -24,14 +24,16 @@ def test_small_mpc_columns_match_reference(golden):
     X0 = plant.sample_x0(8)
     L, U = plant.bounds(X0)
     m = gpu_model((plant.H, plant.g, plant.A, L[0], U[0]))
-    res = m.solve_batch(L, U)
-    assert res.status == ["solved"] * 8
-    for j in range(8):
-        gold = golden.case("mpc", "mpcs_col{}".format(j))
-        assert int(res.iter[j]) == gold["iter"], j
-        assert rel_err(res.x[j].cpu().numpy(), gold["x"]) < 1e-6
-        assert rel_err(res.z[j].cpu().numpy(), gold["z"]) < 1e-6
-        assert float(res.pri_res[j]) == pytest.approx(gold["pri"], rel=1e-2, abs=1e-7)
+    for engine in (1, 0):                   # batched SIMT engine, then the small-batch dispatch
+        res = m.solve_batch(L, U, engine=engine)
+        assert res.status == ["solved"] * 8
+        assert (res.sweeps == 0) == (engine == 0)
+        for j in range(8):
+            gold = golden.case("mpc", "mpcs_col{}".format(j))
+            assert int(res.iter[j]) == gold["iter"], j
+            assert rel_err(res.x[j].cpu().numpy(), gold["x"]) < 1e-6
+            assert rel_err(res.z[j].cpu().numpy(), gold["z"]) < 1e-6
+            assert float(res.pri_res[j]) == pytest.approx(gold["pri"], rel=1e-2, abs=1e-7)
 
 
 def test_c2_columns_match_reference_and_single_path(golden):
@@ -41,7 +43,7 @@ def test_c2_columns_match_reference_and_single_path(golden):
     X0 = plant.sample_x0(32)
     L, U = plant.bounds(X0)
     m = gpu_model((plant.H, plant.g, plant.A, L[0], U[0]))
-    res = m.solve_batch(L, U)
+    res = m.solve_batch(L, U, engine=1)
     iters = res.iter.cpu().numpy()
     gold_iters = np.array([golden.case("mpc", "mpc_col{}".format(j))["iter"] for j in range(32)])
     np.testing.assert_array_equal(iters, gold_iters)
@@ -55,6 +57,23 @@ def test_c2_columns_match_reference_and_single_path(golden):
         r1 = m.solve()
         assert r1.info.iter == int(res.iter[j])
         assert rel_err(res.x[j].cpu().numpy(), r1.x.cpu().numpy()) < 1e-9
+
+
+def test_small_batch_dispatch_matches_batched_engine():
+    """B <= 64 (fp64) is routed to the persistent single-QP kernel; the result must be the same as
+    the batched engine's (forced with engine=1) column by column."""
+    plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+    L, U = plant.bounds(plant.sample_x0(6))
+    m = gpu_model((plant.H, plant.g, plant.A, L[0], U[0]))
+    l_before = m.QP.l.clone()
+    ra = m.solve_batch(L, U)                # dispatch -> single-QP kernel
+    rb = m.solve_batch(L, U, engine=1)      # batched SIMT engine
+    assert ra.sweeps == 0 and rb.sweeps > 0
+    assert torch.equal(m.QP.l, l_before)    # the solver's own problem data is restored
+    np.testing.assert_array_equal(ra.iter.cpu().numpy(), rb.iter.cpu().numpy())
+    assert ra.status == rb.status == ["solved"] * 6
+    assert float((ra.x - rb.x).abs().max()) < 1e-9 and float((ra.lam - rb.lam).abs().max()) < 1e-8
+    np.testing.assert_allclose(ra.pri_res.cpu().numpy(), rb.pri_res.cpu().numpy(), rtol=1e-4, atol=1e-10)
 
 
 def test_batched_with_per_column_g():
@@ -80,7 +99,7 @@ def test_batched_max_iter_and_adaptive_off():
     prob = (plant.H, plant.g, plant.A, L[0], U[0])
     for kw in (dict(max_iter=60, eps_abs=1e-12), dict(adaptive_rho=False, max_iter=40), dict(max_iter=30)):
         m = gpu_model(prob, **kw)
-        res = m.solve_batch(L, U)
+        res = m.solve_batch(L, U, engine=1)
         ref = O.solve_batch(plant.H, plant.g, plant.A, L, U, **kw)
         for j, r in enumerate(ref):
             assert int(res.iter[j]) == r.iter and res.status[j] == r.status, (kw, j)

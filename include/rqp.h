@@ -179,11 +179,15 @@ typedef struct rqp_batch {
     void* dua_res;              /* [B] out                                               */
     void* rho_estimate;         /* [B] out                                               */
     /* GEMM engine: 0 auto (fp32 with W_hi/W_lo -> tcgen05 3xTF32 cta_group::2, else tiled SIMT),
-     * 1 SIMT, 2 tcgen05 cta_group::1 (128x128 tiles), 3 tcgen05 cta_group::2 (256x256 pair tiles) */
+     * 1 SIMT, 2 tcgen05 cta_group::1 (tile width picked per check window), 3 tcgen05
+     * cta_group::2 (256x256 pair tiles), 4 / 5 / 6 tcgen05 cta_group::1 with 128 / 64 / 32-column tiles */
     int32_t engine;
-    int32_t reserved;
-    const void* W_hi;           /* fp32 only: TF32 planes of W, same shape as W: W_hi = rna_tf32(W), */
-    const void* W_lo;           /*            W_lo = rna_tf32(W - W_hi)                            */
+    /* 1: W_hi / W_lo carry nc + 2 nx extra rows after the n_rho * D rows of the layer matrices: the TF32
+     * planes of the residual operator [A 0 0; H 0 0; 0 0 A'] (row-major, ldw), so that A x, H x and
+     * A' lambda of compute_residuals (reluqpth.py:309-311) run on the tensor path too */
+    int32_t res_planes;
+    const void* W_hi;           /* fp32 only: TF32 planes of W, [n_rho * D (+ nc + 2 nx)][ldw]:        */
+    const void* W_lo;           /* W_hi = rna_tf32(W), W_lo = rna_tf32(W - W_hi)                      */
     void* reserved_dbg;         /* NULL, or 16 x uint64 device counters (tcgen05 engine diagnostics) */
 } rqp_batch;
 

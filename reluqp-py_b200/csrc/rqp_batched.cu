@@ -21,7 +21,12 @@
 #include "rqp_host.h"
 #include "rqp_tc.h"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
 #include <type_traits>
+#include <vector>
 
 namespace rqp {
 
@@ -68,8 +73,9 @@ struct BatchCtx {
     int* starts;   // [n_rho + 1]
     int* cursor;   // [n_rho]
     int* tile_rho; // [cap / BALIGN]
+    int* btab;     // [64] bucket table for the 1-CTA tcgen05 kernels: {nb, (rho, first slot, count) x nb}
     int* n_active; // device copy
-    int* n_active_host;  // pinned, mapped
+    int* n_active_host;  // pinned, mapped: {active columns, column tiles at 32 / 64 / 128 columns per tile}
     int nx, nc, D, n_rho, ldv, cap, B;
     long long ldw;
     double thr_p, thr_d, eps_rel, rho_min, rho_max, tol;
@@ -104,23 +110,37 @@ __global__ void batch_hist(const int* __restrict__ key, int cap, int* counts) {
 }
 
 // one thread: aligned bucket starts, tile table, number of active columns
-__global__ void batch_scan(const int* counts, int* starts, int* cursor, int* tile_rho, int n_rho, int n_tiles,
-                           int* n_active, int* n_active_host) {
+__global__ void batch_scan(int* counts, int* starts, int* cursor, int* tile_rho, int* btab, int n_rho,
+                           int n_tiles, int* n_active, int* n_active_host) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int pos = 0, total = 0, t = 0;
+    int pos = 0, total = 0, t = 0, nb = 0, t32 = 0, t64 = 0, t128 = 0;
     for (int r = 0; r < n_rho; ++r) {
         starts[r] = pos;
         cursor[r] = 0;
         const int cnt = counts[r];
+        counts[r] = 0;                       // ready for the next check's fused histogram
         total += cnt;
+        if (cnt > 0 && nb < 21) {
+            btab[1 + 3 * nb] = r;
+            btab[2 + 3 * nb] = pos;
+            btab[3 + 3 * nb] = cnt;
+            nb += 1;
+            t32 += (cnt + 31) / 32;
+            t64 += (cnt + 63) / 64;
+            t128 += (cnt + 127) / 128;
+        }
         const int tiles = (cnt + BALIGN - 1) / BALIGN;
         for (int i = 0; i < tiles; ++i) tile_rho[t++] = r;
         pos += tiles * BALIGN;
     }
     starts[n_rho] = pos;
     for (; t < n_tiles; ++t) tile_rho[t] = -1;
+    btab[0] = nb;
     *n_active = total;
-    *n_active_host = total;
+    n_active_host[0] = total;
+    n_active_host[1] = t32;
+    n_active_host[2] = t64;
+    n_active_host[3] = t128;
 }
 
 // one warp per old slot: move the column to its new slot (other buffer) or write it out
@@ -144,9 +164,12 @@ __global__ void batch_scatter(BatchCtx<T> c, int vsrc, int src, int iter_now, in
             const T* sl = c.Vl[vsrc] + size_t(j) * c.ldv;
             T* dh = c.Vh[vsrc ^ 1] + size_t(slot) * c.ldv;
             T* dl = c.Vl[vsrc ^ 1] + size_t(slot) * c.ldv;
+            // the plain state travels too: the max_iter fall-through (and the final scatter) read it
+            T* dp = c.V[vsrc ^ 1] + size_t(slot) * c.ldv;
             for (int i = lane; i < c.ldv; i += 32) {
                 dh[i] = copy_state ? sh[i] : T(0);
                 dl[i] = copy_state ? sl[i] : T(0);
+                dp[i] = copy_state ? vrow[i] : T(0);
             }
         } else {
             T* drow = c.V[vsrc ^ 1] + size_t(slot) * c.ldv;
@@ -403,11 +426,14 @@ __device__ __forceinline__ double t_sqrt_b<double>(double x) { return sqrt(x); }
 
 template <typename T>
 __global__ void batch_check(BatchCtx<T> c, int vbuf, int buf, int final_pass) {
-    // vbuf: V buffer with the iterate to check; buf: current layout
+    // vbuf: V buffer with the iterate to check; buf: current layout.  Also the first two steps of the
+    // regroup that follows: the histogram of the new keys (counts[] is zero on entry: batch_scan clears it
+    // after reading) and the reset of the OTHER layout's slot map, which the scatter fills next.
     const int lane = threadIdx.x & 31;
     const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (j >= c.cap) return;
     const int o = c.orig[buf][j];
+    if (lane == 0) c.orig[buf ^ 1][j] = -1;
     if (o < 0) {
         if (lane == 0) c.key[j] = -1;
         return;
@@ -458,6 +484,7 @@ __global__ void batch_check(BatchCtx<T> c, int vbuf, int buf, int final_pass) {
         c.s_pri[j] = pr;
         c.s_dua[j] = du;
         c.key[j] = (done || final_pass) ? -1 : r;
+        if (!(done || final_pass)) atomicAdd(c.counts + r, 1);
     }
 }
 
@@ -466,10 +493,40 @@ __global__ void batch_check(BatchCtx<T> c, int vbuf, int buf, int final_pass) {
 // ------------------------------------------------------------------------------------------------
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Small pinned host records (the per-window counters the device writes over PCIe) are recycled:
+// cudaHostAlloc costs far more than a whole check window.
+static std::mutex g_pinned_mu;
+static std::vector<int*> g_pinned_free;
+static int* pinned_acquire() {
+    {
+        std::lock_guard<std::mutex> lk(g_pinned_mu);
+        if (!g_pinned_free.empty()) {
+            int* p = g_pinned_free.back();
+            g_pinned_free.pop_back();
+            return p;
+        }
+    }
+    int* p = nullptr;
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&p), 16 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e != cudaSuccess) { set_last_cuda_error(e); return nullptr; }
+    return p;
+}
+static void pinned_release(int* p) {
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    g_pinned_free.push_back(p);
+}
+struct PinnedRecord {
+    int* p;
+    PinnedRecord() : p(pinned_acquire()) {}
+    ~PinnedRecord() { if (p) pinned_release(p); }
+    PinnedRecord(const PinnedRecord&) = delete;
+    PinnedRecord& operator=(const PinnedRecord&) = delete;
+};
+
 struct BatchLayout {
     int cap, n_tiles;
     size_t off_V[2], off_Vh[2], off_Vl[2], off_Bias[2], off_orig[2], off_ri[2], off_rhoc[2], off_T, off_key, off_pri, off_dua,
-        off_counts, off_starts, off_cursor, off_tile, off_nact, total;
+        off_counts, off_starts, off_cursor, off_tile, off_btab, off_nact, total;
 };
 
 static BatchLayout batch_layout(const rqp_problem* p, int B, int ldv, bool with_g) {
@@ -496,6 +553,7 @@ static BatchLayout batch_layout(const rqp_problem* p, int B, int ldv, bool with_
     l.off_starts = take(size_t(p->n_rho + 1) * 4);
     l.off_cursor = take(size_t(p->n_rho) * 4);
     l.off_tile = take(size_t(l.n_tiles) * 4);
+    l.off_btab = take(64 * 4);
     l.off_nact = take(4);
     l.total = o;
     return l;
@@ -539,10 +597,10 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     bool use_tc = false;
     if (std::is_same<T, float>::value) {
         const bool have_planes = bt->W_hi != nullptr && bt->W_lo != nullptr;
-        if (bt->engine == 2 && !have_planes) return RQP_ERR_BAD_ARG;
-        if (bt->engine == 3 && !have_planes) return RQP_ERR_BAD_ARG;
+        if (bt->engine < 0 || bt->engine > 6) return RQP_ERR_BAD_ARG;
+        if (bt->engine >= 2 && !have_planes) return RQP_ERR_BAD_ARG;
         use_tc = have_planes && bt->engine != 1;
-    } else if (bt->engine == 2 || bt->engine == 3) {
+    } else if (bt->engine >= 2) {
         return RQP_ERR_UNSUPPORTED;   // tcgen05 has no fp64 kind; fp64 keeps the SIMT engine
     }
     c.tc = use_tc ? 1 : 0;
@@ -563,6 +621,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     c.starts = reinterpret_cast<int*>(w8 + lay.off_starts);
     c.cursor = reinterpret_cast<int*>(w8 + lay.off_cursor);
     c.tile_rho = reinterpret_cast<int*>(w8 + lay.off_tile);
+    c.btab = reinterpret_cast<int*>(w8 + lay.off_btab);
     c.n_active = reinterpret_cast<int*>(w8 + lay.off_nact);
     c.nx = nx; c.nc = nc; c.D = D; c.n_rho = prob->n_rho; c.ldv = ldv; c.cap = lay.cap; c.B = B;
     c.ldw = prob->ldw;
@@ -571,9 +630,10 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     c.eps_rel = stng->eps_rel; c.rho_min = stng->rho_min; c.rho_max = stng->rho_max;
     c.tol = stng->adaptive_rho_tolerance;
 
-    int* nact_host = nullptr;
-    RQP_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&nact_host), sizeof(int), cudaHostAllocMapped));
-    *nact_host = B;
+    PinnedRecord nact_rec;
+    int* nact_host = nact_rec.p;
+    if (!nact_host) return RQP_ERR_CUDA;
+    nact_host[0] = B; nact_host[1] = nact_host[2] = nact_host[3] = 0;
     c.n_active_host = nact_host;
 
     const int cap = lay.cap;
@@ -584,49 +644,77 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     int lcur = 1;  // current layout
     // regroup: key[] filled for the current layout -> histogram, aligned starts, scatter into the
     // other V buffer / other layout; both indices flip
-    auto regroup = [&](int iter_now, int status_out, int copy_state) -> int {
-        RQP_CUDA_TRY(cudaMemsetAsync(c.counts, 0, size_t(c.n_rho) * 4, st));
-        RQP_CUDA_TRY(cudaMemsetAsync(c.orig[lcur ^ 1], 0xff, size_t(cap) * 4, st));
-        batch_hist<<<(cap + thr - 1) / thr, thr, 0, st>>>(c.key, cap, c.counts);
-        batch_scan<<<1, 32, 0, st>>>(c.counts, c.starts, c.cursor, c.tile_rho, c.n_rho, lay.n_tiles, c.n_active,
-                                     c.n_active_host);
+    // after_check: batch_check already built the histogram and reset the other layout's slot map
+    auto regroup = [&](int iter_now, int status_out, int copy_state, bool after_check) -> int {
+        if (!after_check) {
+            RQP_CUDA_TRY(cudaMemsetAsync(c.counts, 0, size_t(c.n_rho) * 4, st));
+            RQP_CUDA_TRY(cudaMemsetAsync(c.orig[lcur ^ 1], 0xff, size_t(cap) * 4, st));
+            batch_hist<<<(cap + thr - 1) / thr, thr, 0, st>>>(c.key, cap, c.counts);
+        }
+        batch_scan<<<1, 32, 0, st>>>(c.counts, c.starts, c.cursor, c.tile_rho, c.btab, c.n_rho, lay.n_tiles,
+                                     c.n_active, c.n_active_host);
         batch_scatter<T><<<warp_blocks, thr, 0, st>>>(c, cur, lcur, iter_now, status_out, copy_state);
         RQP_CUDA_TRY(cudaGetLastError());
         cur ^= 1;
         lcur ^= 1;
         return RQP_OK;
     };
-    CUtensorMap map_wh, map_wl, map_xh[2], map_xl[2];
+    const bool pdl_ok = getenv("RQP_NO_PDL") == nullptr;
+    // residual products A x, H x, A' lambda on the tensor path: the W planes carry the residual operator
+    // after the n_rho layer matrices (rqp_batch.res_planes)
+    const bool res_tc = use_tc && bt->res_planes != 0 && getenv("RQP_NO_RES_TC") == nullptr;
+    const bool tc_split = getenv("RQP_TC_SPLIT") != nullptr;
+    // tensor maps: W planes (128-row boxes) and the state planes with 128 / 64 / 32-row boxes
+    CUtensorMap map_wh, map_wl, map_xh[3][2], map_xl[3][2];
+    static const int kBoxRows[3] = {128, 64, 32};
     if (use_tc) {
-        int rc0 = tc_make_map(&map_wh, bt->W_hi, (long long)prob->n_rho * D, c.ldw, c.ldw);
-        if (rc0 == RQP_OK) rc0 = tc_make_map(&map_wl, bt->W_lo, (long long)prob->n_rho * D, c.ldw, c.ldw);
-        for (int i = 0; i < 2 && rc0 == RQP_OK; ++i) {
-            rc0 = tc_make_map(&map_xh[i], c.Vh[i], cap, ldv, ldv);
-            if (rc0 == RQP_OK) rc0 = tc_make_map(&map_xl[i], c.Vl[i], cap, ldv, ldv);
-        }
-        if (rc0 != RQP_OK) { cudaFreeHost(nact_host); return rc0; }
+        const long long w_rows = (long long)prob->n_rho * D + (res_tc ? nc + 2 * nx : 0);
+        int rc0 = tc_make_map(&map_wh, bt->W_hi, w_rows, c.ldw, c.ldw);
+        if (rc0 == RQP_OK) rc0 = tc_make_map(&map_wl, bt->W_lo, w_rows, c.ldw, c.ldw);
+        for (int b = 0; b < 3 && rc0 == RQP_OK; ++b)
+            for (int i = 0; i < 2 && rc0 == RQP_OK; ++i) {
+                rc0 = tc_make_map(&map_xh[b][i], c.Vh[i], cap, ldv, ldv, kBoxRows[b]);
+                if (rc0 == RQP_OK) rc0 = tc_make_map(&map_xl[b][i], c.Vl[i], cap, ldv, ldv, kBoxRows[b]);
+            }
+        if (rc0 != RQP_OK) return rc0;
     }
-    auto gemm_iter_tc = [&](int src, bool write_plain) -> int {
+    auto pick_bn = [&](int n_row_tiles, int forced) -> int {   // index into kBoxRows
+        if (forced == 4) return 0;
+        if (forced == 5) return 1;
+        if (forced == 6) return 2;
+        if (nact_host[3] * n_row_tiles > sm_count) return 0;              // more than one wave anyway
+        if (nact_host[1] * n_row_tiles <= sm_count) return 2;
+        if (nact_host[2] * n_row_tiles <= sm_count) return 1;
+        return 0;
+    };
+    // pdl: this launch directly follows another 1-CTA tcgen05 iteration kernel of the same window
+    auto gemm_iter_tc = [&](int src, bool write_plain, bool pdl) -> int {
         TcArgs a;
-        a.tile_rho = c.tile_rho; a.orig = c.orig[lcur];
+        a.tile_rho = c.tile_rho; a.btab = c.btab; a.orig = c.orig[lcur];
         a.b_all = reinterpret_cast<const float*>(c.b_all);
         a.bias_cols = with_g ? reinterpret_cast<const float*>(c.Bias[lcur]) : nullptr;
         a.L = reinterpret_cast<const float*>(c.L); a.U = reinterpret_cast<const float*>(c.U);
         a.Yh = reinterpret_cast<float*>(c.Vh[src ^ 1]); a.Yl = reinterpret_cast<float*>(c.Vl[src ^ 1]);
         a.Yplain = write_plain ? reinterpret_cast<float*>(c.V[src ^ 1]) : nullptr;
         a.D = D; a.nx = nx; a.nc = nc; a.ldv = ldv;
+        a.raw = 0; a.M = D; a.w_row0 = 0;
         a.k_blocks = (D + 31) / 32;
         a.dbg = static_cast<unsigned long long*>(bt->reserved_dbg);
         // auto: the CTA-pair kernel pays off once there are enough column tiles to fill the chip
         // (measured crossover ~8k active columns at D = 960); below that the 1-CTA kernel has twice
         // the parallelism per active column
-        const bool one_sm = bt->engine == 2 || (bt->engine != 3 && *nact_host < 8192);
-        if (one_sm) {                 // 1-CTA tiles: 128 rows x 128 columns
-            a.n_col_tiles = cap / 128; a.n_row_tiles = (D + 127) / 128;
-            return tc_launch(map_wh, map_wl, map_xh[src], map_xl[src], a, sm_count, st);
+        const bool one_sm = bt->engine == 2 || bt->engine >= 4 || (bt->engine != 3 && nact_host[0] < 8192);
+        if (one_sm) {
+            // 1-CTA tiles of 128 rows x BN columns.  BN is the widest tile that still gives every active
+            // column tile its own SM in one wave (engine 4 / 5 / 6 force 128 / 64 / 32).
+            a.n_row_tiles = (D + 127) / 128;
+            const int b = pick_bn(a.n_row_tiles, bt->engine);
+            a.n_col_tiles = 0;
+            const int bound = nact_host[3 - b] * a.n_row_tiles;
+            return tc_launch(map_wh, map_wl, map_xh[b][src], map_xl[b][src], a, kBoxRows[b], bound, pdl, tc_split, sm_count, st);
         }
         a.n_col_tiles = cap / 256; a.n_row_tiles = (D + 255) / 256;   // CTA-pair tiles: 256 x 256
-        return tc2_launch(map_wh, map_wl, map_xh[src], map_xl[src], a, sm_count, st);
+        return tc2_launch(map_wh, map_wl, map_xh[0][src], map_xl[0][src], a, sm_count, st);
     };
     auto gemm_iter = [&](int src) {
         GemmArgs<T> a;
@@ -636,11 +724,27 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.M = D; a.K = D; a.tile_rho = c.tile_rho;
         a.b_all = c.b_all; a.bias_cols = with_g ? c.Bias[lcur] : nullptr;
         a.L = c.L; a.U = c.U; a.orig = c.orig[lcur]; a.nx = nx; a.nc = nc; a.D = D;
-        if (*nact_host < 2048) {
+        if (nact_host[0] < 2048) {
             bgemm_simt64<T, EPI_ITER><<<dim3((D + SM64 - 1) / SM64, cap / SM64), 256, 0, st>>>(a);
         } else {
             bgemm_simt<T, EPI_ITER><<<dim3((D + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
         }
+    };
+    auto gemm_res_tc = [&](int src) -> int {
+        TcArgs a;
+        a.tile_rho = c.tile_rho; a.btab = c.btab; a.orig = c.orig[lcur];
+        a.b_all = nullptr; a.bias_cols = nullptr; a.L = nullptr; a.U = nullptr;
+        a.Yh = nullptr; a.Yl = nullptr;
+        a.Yplain = reinterpret_cast<float*>(c.Tres);
+        a.D = D; a.nx = nx; a.nc = nc; a.ldv = nc + 2 * nx;
+        a.raw = 1; a.M = nc + 2 * nx; a.w_row0 = prob->n_rho * D;
+        a.k_blocks = (D + 31) / 32;
+        a.n_col_tiles = 0; a.n_row_tiles = (a.M + 127) / 128;
+        a.dbg = nullptr;
+        const int b = pick_bn(a.n_row_tiles, bt->engine);
+        const int bound = nact_host[3 - b] * a.n_row_tiles;
+        return tc_launch(map_wh, map_wl, map_xh[b][src], map_xl[b][src], a, kBoxRows[b], bound, false, tc_split,
+                         sm_count, st);
     };
     auto gemm_res = [&](int src) {
         GemmArgs<T> a;
@@ -649,7 +753,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.orig = c.orig[lcur]; a.nx = nx; a.nc = nc; a.D = D;
         // A x
         a.mat = c.A; a.ldm = nx; a.M = nc; a.K = nx; a.ko = 0; a.mo = 0;
-        const bool small = *nact_host < 2048;
+        const bool small = nact_host[0] < 2048;
         if (small) bgemm_simt64<T, EPI_RAW><<<dim3((nc + SM64 - 1) / SM64, cap / SM64), 256, 0, st>>>(a);
         else bgemm_simt<T, EPI_RAW><<<dim3((nc + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
         // H x
@@ -664,45 +768,75 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
 
     // ---- start: v = 0, rho index from the caller, first grouping into buffer 0
     batch_init_keys<T><<<(cap + thr - 1) / thr, thr, 0, st>>>(c);
-    int rc = regroup(0, RQP_STATUS_MAX_ITER, 0);
-    if (rc != RQP_OK) { cudaFreeHost(nact_host); return rc; }
+    int rc = regroup(0, RQP_STATUS_MAX_ITER, 0, false);
+    if (rc != RQP_OK) return rc;
+    if (use_tc) {   // the kernel choice of the first window reads the tile counts written by the scan
+        cudaError_t e0 = cudaStreamSynchronize(st);
+        if (e0 != cudaSuccess) { set_last_cuda_error(e0); return RQP_ERR_CUDA; }
+    }
     int k = 0, sweeps = 0;
     const int ci = stng->check_interval;
+    const bool trace_windows = getenv("RQP_BATCH_TRACE") != nullptr;   // per-window host timing on stderr
+    auto now_us = []() {
+        return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    };
     bool all_done = false;
     while (k < stng->max_iter && !all_done) {
         int steps = ci - (k % ci);
         if (k + steps > stng->max_iter) steps = stng->max_iter - k;
+        const double tw0 = trace_windows ? now_us() : 0.0;
+        const int nact_w = nact_host[0], t32_w = nact_host[1];
         for (int s = 0; s < steps; ++s) {
             if (use_tc) {
-                rc = gemm_iter_tc(cur, s == steps - 1);   // last step of a window also writes the plain state
-                if (rc != RQP_OK) { cudaFreeHost(nact_host); return rc; }
+                // last step of a window also writes the plain state; steps 2.. are programmatic
+                // dependents of the previous step (the pair kernel ignores the flag)
+                rc = gemm_iter_tc(cur, s == steps - 1, s > 0 && pdl_ok);
+                if (rc != RQP_OK) return rc;
             } else {
                 gemm_iter(cur);
             }
             cur ^= 1;
         }
         k += steps;
+        const double tw1 = trace_windows ? now_us() : 0.0;
+        if (trace_windows) {
+            cudaStreamSynchronize(st);
+            fprintf(stderr, "[rqp batch] window ending at k=%d: %d active columns (%d tiles of 32), %d iterations: "
+                            "enqueue %.1f us, device done after %.1f us\n", k, nact_w, t32_w, steps, tw1 - tw0,
+                    now_us() - tw0);
+        }
+        const double tc0 = trace_windows ? now_us() : 0.0;
         if (stng->adaptive_rho && (k % ci) == 0) {
-            gemm_res(cur);
+            if (res_tc) {
+                rc = gemm_res_tc(cur);
+                if (rc != RQP_OK) return rc;
+            } else {
+                gemm_res(cur);
+            }
             batch_check<T><<<warp_blocks, thr, 0, st>>>(c, cur, lcur, 0);
-            rc = regroup(k, RQP_STATUS_SOLVED, 1);
-            if (rc != RQP_OK) { cudaFreeHost(nact_host); return rc; }
+            rc = regroup(k, RQP_STATUS_SOLVED, 1, true);
+            if (rc != RQP_OK) return rc;
             sweeps += 1;
             RQP_CUDA_TRY(cudaStreamSynchronize(st));
-            all_done = (*nact_host == 0);
+            all_done = (nact_host[0] == 0);
+            if (trace_windows) fprintf(stderr, "[rqp batch]   check + regroup: %.1f us\n", now_us() - tc0);
         }
     }
     if (!all_done) {
         // fall-through for the columns still active (reluqpth.py:243-248)
-        gemm_res(cur);
+        if (res_tc && (k % ci) == 0) {     // the planes are current only right after a full window
+            rc = gemm_res_tc(cur);
+            if (rc != RQP_OK) return rc;
+        } else {
+            gemm_res(cur);
+        }
         batch_check<T><<<warp_blocks, thr, 0, st>>>(c, cur, lcur, 1);
-        rc = regroup(stng->max_iter, RQP_STATUS_MAX_ITER, 1);
-        if (rc != RQP_OK) { cudaFreeHost(nact_host); return rc; }
+        rc = regroup(stng->max_iter, RQP_STATUS_MAX_ITER, 1, true);
+        if (rc != RQP_OK) return rc;
         RQP_CUDA_TRY(cudaStreamSynchronize(st));
     }
     RQP_CUDA_TRY(cudaGetLastError());
     if (sweeps_host) *sweeps_host = sweeps;
-    cudaFreeHost(nact_host);
     return RQP_OK;
 }
 

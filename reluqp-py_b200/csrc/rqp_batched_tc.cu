@@ -26,16 +26,30 @@
 namespace rqp {
 
 constexpr int TC_BM = 128;       // state rows per tile (UMMA M)
-constexpr int TC_BN = 128;       // columns per tile (UMMA N) == BALIGN
+constexpr int TC_BN = 128;       // columns per tile (UMMA N) of the full-size 1-CTA kernel
 constexpr int TC_BK = 32;        // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                 // 16 KB per operand plane
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;                // W_hi, W_lo, X_hi, X_lo
 constexpr int TC_ACC_STAGES = 2;
-constexpr int TC_TMEM_COLS = TC_ACC_STAGES * TC_BN;              // 256
 constexpr int TC_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr int TC_EPI_WARPS = 8;
 constexpr size_t TC_SMEM_BYTES = size_t(TC_STAGES) * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+// 1-CTA kernel, templated on the column-tile width BN.  Narrow tiles (64, 32 columns) are for check
+// windows with few active columns: the per-iteration latency of a tile is the time one SM needs to
+// stream its 128 rows of W_hi / W_lo from L2 plus BN-proportional MMA and epilogue time, and narrow
+// tiles spread a small active set over many more SMs.
+template <int BN>
+struct TcCfg {
+    static constexpr int X_TILE_BYTES = BN * TC_BK * 4;
+    static constexpr int STAGE_BYTES = 2 * TC_TILE_BYTES + 2 * X_TILE_BYTES;
+    static constexpr int STAGES = BN == 128 ? 3 : (BN == 64 ? 4 : 5);
+    static constexpr int TMEM_COLS = TC_ACC_STAGES * BN;          // 256 / 128 / 64 (powers of two >= 32)
+    static constexpr int EPI_WARPS = BN >= 64 ? 8 : 4;
+    static constexpr int COLS_PER_EPI_WARP = BN / (EPI_WARPS / 4);
+    static constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers, bucket table*/;
+};
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -126,6 +140,11 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 
+// Programmatic dependent launch: the next iteration's kernel may start while this one still runs; it
+// must not touch anything the previous kernel writes (the state planes) before grid_dep_wait().
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -209,127 +228,239 @@ __device__ __forceinline__ EpiRow make_epi_row(const TcArgs& a, int m, int rho) 
     return e;
 }
 
+// Bucket table written by the regroup pass (batch_scan): btab[0] = number of non-empty rho buckets,
+// then {rho index, first slot, active columns} per bucket.  Column tiles are enumerated bucket by
+// bucket over the ACTIVE columns only (padding slots never become tiles); tile t -> (rho, first slot,
+// row tile).  Returns false past the last tile.
+template <int BN>
+__device__ __forceinline__ bool tc_tile_lookup(const int* sb, int t, int n_row_tiles, int& rho, int& col0, int& rt) {
+    int ct = t / n_row_tiles;
+    rt = t - ct * n_row_tiles;
+    const int nb = sb[0];
+    for (int i = 0; i < nb; ++i) {
+        const int nct = (sb[3 + 3 * i] + BN - 1) / BN;
+        if (ct < nct) {
+            rho = sb[1 + 3 * i];
+            col0 = sb[2 + 3 * i] + ct * BN;
+            return true;
+        }
+        ct -= nct;
+    }
+    return false;
+}
+// Rows of the W planes and the k-block range a row tile needs.  Iteration tiles (raw == 0): rows of
+// W_rho, all of K.  Residual tiles (raw == 1): rows of the residual operator [A 0 0; H 0 0; 0 0 A'] stored
+// after the n_rho layer matrices; its row blocks only touch the x columns or the lambda columns of the
+// state, so most k-blocks are structurally zero and are skipped.
+__device__ __forceinline__ void tc_tile_rows(const TcArgs& a, int rho, int rt, int& wrow, int& kb_lo, int& kb_hi) {
+    if (!a.raw) {
+        wrow = rho * a.D + rt * TC_BM;
+        kb_lo = 0;
+        kb_hi = a.k_blocks;
+        return;
+    }
+    wrow = a.w_row0 + rt * TC_BM;
+    const int r0 = rt * TC_BM, r1 = min(r0 + TC_BM, a.M);
+    const int split = a.nc + a.nx;                 // rows >= split are A' lambda
+    int k0 = 0, k1 = a.D;
+    if (r1 <= split) k1 = a.nx;                    // A x and H x: x columns only
+    else if (r0 >= split) k0 = a.nx + a.nc;        // A' lambda: lambda columns only
+    kb_lo = k0 / TC_BK;
+    kb_hi = (k1 + TC_BK - 1) / TC_BK;
+}
+
+// Residual epilogue: the accumulator goes out as plain fp32, Out[slot][m] (ld = a.ldv).
+__device__ __forceinline__ void tc_epilogue_raw(const TcArgs& a, int m, const uint32_t (&r)[32], int n0, int lane) {
+    const int o_lane = __ldg(a.orig + n0 + lane);
+    const bool m_ok = m < a.M;
+    float* pp = a.Yplain + size_t(n0) * a.ldv + (m_ok ? m : 0);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int oj = __shfl_sync(0xffffffffu, o_lane, j);
+        if (oj >= 0 && m_ok) pp[0] = __uint_as_float(r[j]);
+        pp += a.ldv;
+    }
+}
+
+template <int BN>
+__device__ __forceinline__ int tc_tile_count(const int* sb, int n_row_tiles) {
+    int n = 0;
+    const int nb = sb[0];
+    for (int i = 0; i < nb; ++i) n += (sb[3 + 3 * i] + BN - 1) / BN;
+    return n * n_row_tiles;
+}
+
+template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
                       const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                       const TcArgs a) {
+    using Cfg = TcCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
+    constexpr int XT = Cfg::X_TILE_BYTES;
     extern __shared__ unsigned char tc_smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) &
                                                             ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + size_t(TC_STAGES) * TC_STAGE_BYTES);
-    uint64_t* full = bars;                           // [TC_STAGES]
-    uint64_t* empty = bars + TC_STAGES;              // [TC_STAGES]
-    uint64_t* acc_full = bars + 2 * TC_STAGES;       // [TC_ACC_STAGES]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + size_t(STAGES) * STAGE_BYTES);
+    uint64_t* full = bars;                           // [STAGES]
+    uint64_t* empty = bars + STAGES;                 // [STAGES]
+    uint64_t* acc_full = bars + 2 * STAGES;          // [TC_ACC_STAGES]
     uint64_t* acc_empty = acc_full + TC_ACC_STAGES;  // [TC_ACC_STAGES]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + TC_ACC_STAGES);
+    int* sb = reinterpret_cast<int*>(tmem_slot + 2);  // [64] bucket table
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_tiles = a.n_col_tiles * a.n_row_tiles;
 
+    // the bucket table was written by the regroup pass, which completed before the FIRST kernel of this
+    // check window started; kernels 2..n of the window (the ones launched as programmatic dependents)
+    // may therefore read it before grid_dep_wait()
+    if (threadIdx.x < 64) sb[threadIdx.x] = __ldg(a.btab + threadIdx.x);
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_wh); prefetch_tmap(&map_wl); prefetch_tmap(&map_xh); prefetch_tmap(&map_xl);
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < TC_ACC_STAGES; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, TC_EPI_WARPS); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < TC_ACC_STAGES; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, Cfg::EPI_WARPS); }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TC_TMEM_COLS);
+    // SPLIT: the cross terms (W_hi x_lo + W_lo x_hi, 2^-11 of the main term) get their own accumulator, so
+    // the main sum W_hi x_hi is truncated once per k-step instead of three times and the cross sum keeps
+    // its low bits; the epilogue adds the two in fp32
+    constexpr int ACC_COLS = SPLIT ? 2 * BN : BN;
+    constexpr int TMEM_COLS = TC_ACC_STAGES * ACC_COLS;
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    grid_dep_launch();       // let the next iteration's kernel start its prologue / W prefetch
     const uint32_t tmem_base = *tmem_slot;
+    const int n_tiles = tc_tile_count<BN>(sb, a.n_row_tiles);
 
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            bool first = true;
             long long w_empty = 0, t_all = clock64();
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int ct = t / a.n_row_tiles, rt = t % a.n_row_tiles;
-                const int rho = a.tile_rho[ct >> 1];          // tile_rho is per 256-column bucket tile
-                if (rho < 0) continue;
-                const int wrow = rho * a.D + rt * TC_BM;
-                const int xrow = ct * TC_BN;
-                for (int kb = 0; kb < a.k_blocks; ++kb) {
+                int rho, xrow, rt;
+                if (!tc_tile_lookup<BN>(sb, t, a.n_row_tiles, rho, xrow, rt)) break;
+                int wrow, kb_lo, kb_hi;
+                tc_tile_rows(a, rho, rt, wrow, kb_lo, kb_hi);
+                int kb0 = kb_lo;
+                if (first) {
+                    // W does not depend on the previous iteration: fill the ring with W planes first, then
+                    // wait for the previous kernel and add the state planes
+                    first = false;
+                    const int P = (kb_hi - kb_lo) < STAGES ? (kb_hi - kb_lo) : STAGES;
+                    for (int s = 0; s < P; ++s) {
+                        unsigned char* sp = base + size_t(s) * STAGE_BYTES;
+                        mbar_expect_tx(full + s, STAGE_BYTES);
+                        tma_load_2d(sp, &map_wh, (kb_lo + s) * TC_BK, wrow, full + s);
+                        tma_load_2d(sp + TC_TILE_BYTES, &map_wl, (kb_lo + s) * TC_BK, wrow, full + s);
+                    }
+                    grid_dep_wait();
+                    for (int s = 0; s < P; ++s) {
+                        unsigned char* sp = base + size_t(s) * STAGE_BYTES;
+                        tma_load_2d(sp + 2 * TC_TILE_BYTES, &map_xh, (kb_lo + s) * TC_BK, xrow, full + s);
+                        tma_load_2d(sp + 2 * TC_TILE_BYTES + XT, &map_xl, (kb_lo + s) * TC_BK, xrow, full + s);
+                    }
+                    if (P == STAGES) { stage = 0; phase = 1u; } else { stage = uint32_t(P); }
+                    kb0 = kb_lo + P;
+                }
+                for (int kb = kb0; kb < kb_hi; ++kb) {
                     const long long tw = clock64();
                     mbar_wait(empty + stage, phase ^ 1u);
                     w_empty += clock64() - tw;
-                    unsigned char* sp = base + size_t(stage) * TC_STAGE_BYTES;
-                    mbar_expect_tx(full + stage, TC_STAGE_BYTES);
+                    unsigned char* sp = base + size_t(stage) * STAGE_BYTES;
+                    mbar_expect_tx(full + stage, STAGE_BYTES);
                     tma_load_2d(sp, &map_wh, kb * TC_BK, wrow, full + stage);
                     tma_load_2d(sp + TC_TILE_BYTES, &map_wl, kb * TC_BK, wrow, full + stage);
                     tma_load_2d(sp + 2 * TC_TILE_BYTES, &map_xh, kb * TC_BK, xrow, full + stage);
-                    tma_load_2d(sp + 3 * TC_TILE_BYTES, &map_xl, kb * TC_BK, xrow, full + stage);
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                    tma_load_2d(sp + 2 * TC_TILE_BYTES + XT, &map_xl, kb * TC_BK, xrow, full + stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
+            if (first) grid_dep_wait();
             if (a.dbg && blockIdx.x == 0) { a.dbg[0] = w_empty; a.dbg[1] = clock64() - t_all; }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
+        constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
         long long w_full = 0, w_acc = 0, t_all = clock64(), ntile = 0;
+        grid_dep_wait();
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const int ct = t / a.n_row_tiles;
-            if (a.tile_rho[ct >> 1] < 0) continue;
+            int rho, col0, rt, wrow, kb_lo, kb_hi;
+            if (!tc_tile_lookup<BN>(sb, t, a.n_row_tiles, rho, col0, rt)) break;
+            tc_tile_rows(a, rho, rt, wrow, kb_lo, kb_hi);
             ntile++;
             long long tw = clock64();
             mbar_wait(acc_empty + acc, acc_phase ^ 1u);   // epilogue has drained this accumulator
             w_acc += clock64() - tw;
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * TC_BN;
-            for (int kb = 0; kb < a.k_blocks; ++kb) {
+            const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+            const uint32_t d_cross = SPLIT ? d_tmem + BN : d_tmem;
+            for (int kb = kb_lo; kb < kb_hi; ++kb) {
                 tw = clock64();
                 mbar_wait(full + stage, phase);
                 w_full += clock64() - tw;
                 tc_fence_after();
                 if (elect_one()) {
-                    unsigned char* sp = base + size_t(stage) * TC_STAGE_BYTES;
+                    unsigned char* sp = base + size_t(stage) * STAGE_BYTES;
                     const uint64_t dwh = make_kmajor_sw128_desc(sp);
                     const uint64_t dwl = make_kmajor_sw128_desc(sp + TC_TILE_BYTES);
                     const uint64_t dxh = make_kmajor_sw128_desc(sp + 2 * TC_TILE_BYTES);
-                    const uint64_t dxl = make_kmajor_sw128_desc(sp + 3 * TC_TILE_BYTES);
+                    const uint64_t dxl = make_kmajor_sw128_desc(sp + 2 * TC_TILE_BYTES + XT);
+                    const bool first_kb = kb == kb_lo;
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {
                         const uint64_t off = uint64_t((k * 8 * 4) >> 4);   // advance 32 bytes inside the swizzle row
-                        umma_tf32(d_tmem, dwh + off, dxh + off, idesc, (kb | k) != 0 ? 1u : 0u);
-                        umma_tf32(d_tmem, dwh + off, dxl + off, idesc, 1u);
-                        umma_tf32(d_tmem, dwl + off, dxh + off, idesc, 1u);
+                        umma_tf32(d_tmem, dwh + off, dxh + off, idesc, (first_kb && k == 0) ? 0u : 1u);
+                        umma_tf32(d_cross, dwh + off, dxl + off, idesc, (SPLIT && first_kb && k == 0) ? 0u : 1u);
+                        umma_tf32(d_cross, dwl + off, dxh + off, idesc, 1u);
                     }
                     umma_commit(empty + stage);                       // smem slot free when these MMAs retire
-                    if (kb == a.k_blocks - 1) umma_commit(acc_full + acc);  // accumulator complete
+                    if (kb == kb_hi - 1) umma_commit(acc_full + acc);  // accumulator complete
                 }
                 __syncwarp();
-                if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
             if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
         }
         if (a.dbg && blockIdx.x == 0 && lane == 0) {
             a.dbg[2] = w_full; a.dbg[3] = w_acc; a.dbg[4] = clock64() - t_all; a.dbg[5] = ntile;
         }
-    } else {
-        // ================= epilogue (warps 2..5) =================
+    } else if (warp - 2 < Cfg::EPI_WARPS) {
+        // ================= epilogue =================
         const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter + 32)
+        const int half = (warp - 2) >> 2;             // which share of the tile's columns
         uint32_t acc = 0, acc_phase = 0;
         long long w_accf = 0, t_all = clock64();
+        grid_dep_wait();
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const int ct = t / a.n_row_tiles, rt = t % a.n_row_tiles;
-            const int rho = a.tile_rho[ct >> 1];
-            if (rho < 0) continue;
+            int rho, col0, rt;
+            if (!tc_tile_lookup<BN>(sb, t, a.n_row_tiles, rho, col0, rt)) break;
             const long long tw = clock64();
             mbar_wait(acc_full + acc, acc_phase);
             w_accf += clock64() - tw;
             tc_fence_after();
             const int m = rt * TC_BM + quarter * 32 + lane;      // state row of this thread
-            const EpiRow e = make_epi_row(a, m, rho);
-            const uint32_t taddr = tmem_base + acc * TC_BN + (uint32_t(quarter * 32) << 16);
-            const int half = (warp - 2) >> 2;                     // which half of the tile's columns
+            EpiRow e{};
+            if (!a.raw) e = make_epi_row(a, m, rho);
+            const uint32_t taddr = tmem_base + acc * ACC_COLS + (uint32_t(quarter * 32) << 16);
 #pragma unroll 1
-            for (int c0 = half * (TC_BN / 2); c0 < (half + 1) * (TC_BN / 2); c0 += 32) {
+            for (int c0 = half * Cfg::COLS_PER_EPI_WARP; c0 < (half + 1) * Cfg::COLS_PER_EPI_WARP; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(taddr + c0, r);
-                tc_epilogue_chunk(a, e, r, ct * TC_BN + c0, lane);
+                if (SPLIT) {
+                    uint32_t rc[32];
+                    tmem_ld32(taddr + BN + c0, rc);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
+                }
+                if (a.raw) tc_epilogue_raw(a, m, r, col0 + c0, lane);
+                else tc_epilogue_chunk(a, e, r, col0 + c0, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -340,7 +471,7 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // =============================================================================================
@@ -548,13 +679,13 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D fp32 row-major [rows][ld] tensor, box = 32 columns (128 B) x 128 rows, SWIZZLE_128B, zero OOB fill
-int tc_make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld) {
+// 2-D fp32 row-major [rows][ld] tensor, box = 32 columns (128 B) x box_rows rows, SWIZZLE_128B, zero OOB fill
+int tc_make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return RQP_ERR_UNSUPPORTED;
     cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
     cuuint64_t strides[1] = {cuuint64_t(ld) * 4};
-    cuuint32_t box[2] = {TC_BK, TC_BM};
+    cuuint32_t box[2] = {TC_BK, cuuint32_t(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -578,19 +709,51 @@ int tc2_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& 
     return RQP_OK;
 }
 
-int tc_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,
-              const TcArgs& args, int sm_count, cudaStream_t st) {
+template <int BN, bool SPLIT>
+static int tc_launch_bn(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,
+                        const TcArgs& args, int grid, bool pdl, cudaStream_t st) {
     static bool attr_set = false;
+    auto kern = rqp_batched_tc_kernel<BN, SPLIT>;
     if (!attr_set) {
-        RQP_CUDA_TRY(cudaFuncSetAttribute(rqp_batched_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          int(TC_SMEM_BYTES)));
+        RQP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          int(TcCfg<BN>::SMEM_BYTES)));
         attr_set = true;
     }
-    const int n_tiles = args.n_col_tiles * args.n_row_tiles;
-    const int grid = n_tiles < sm_count ? n_tiles : sm_count;
-    rqp_batched_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(wh, wl, xh, xl, args);
-    RQP_CUDA_TRY(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(grid));
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TcCfg<BN>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    RQP_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, wh, wl, xh, xl, args));
     return RQP_OK;
+}
+
+// bn: column-tile width (128, 64 or 32; the X tensor maps must have been made with the same box rows);
+// n_tiles_bound: upper bound on the number of tiles (the kernel derives the exact list from args.btab);
+// pdl: launch as a programmatic dependent of the previous kernel in the stream
+int tc_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,
+              const TcArgs& args, int bn, int n_tiles_bound, bool pdl, bool split, int sm_count, cudaStream_t st) {
+    int grid = n_tiles_bound < sm_count ? n_tiles_bound : sm_count;
+    if (grid < 1) grid = 1;
+    if (split) {
+        switch (bn) {
+            case 128: return tc_launch_bn<128, true>(wh, wl, xh, xl, args, grid, pdl, st);
+            case 64: return tc_launch_bn<64, true>(wh, wl, xh, xl, args, grid, pdl, st);
+            case 32: return tc_launch_bn<32, true>(wh, wl, xh, xl, args, grid, pdl, st);
+        }
+        return RQP_ERR_BAD_ARG;
+    }
+    switch (bn) {
+        case 128: return tc_launch_bn<128, false>(wh, wl, xh, xl, args, grid, pdl, st);
+        case 64: return tc_launch_bn<64, false>(wh, wl, xh, xl, args, grid, pdl, st);
+        case 32: return tc_launch_bn<32, false>(wh, wl, xh, xl, args, grid, pdl, st);
+    }
+    return RQP_ERR_BAD_ARG;
 }
 
 }  // namespace rqp

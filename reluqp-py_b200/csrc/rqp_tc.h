@@ -6,7 +6,8 @@
 namespace rqp {
 
 struct TcArgs {
-    const int* tile_rho;    // [n_col_tiles]
+    const int* tile_rho;    // [cap / 256] rho index per 256-slot group (pair kernel)
+    const int* btab;        // bucket table: {nb, (rho, first slot, active columns) x nb} (1-CTA kernels)
     const int* orig;        // [cap]
     const float* b_all;     // [n_rho][D]
     const float* bias_cols; // [cap][D] or null
@@ -16,15 +17,18 @@ struct TcArgs {
     float* Yl;
     float* Yplain;          // [cap][ldv] or null
     int D, nx, nc, ldv;
+    int raw;                // 1: residual GEMM (rows of [A 0 0; H 0 0; 0 0 A'] at W-plane row w_row0), plain output
+    int M;                  // output rows: D (iteration) or nc + 2 nx (residual)
+    int w_row0;
     int n_col_tiles, n_row_tiles, k_blocks;
     unsigned long long* dbg;  // optional [16] cycle counters written by CTA 0 (diagnostics)
 };
 
-// 2-D fp32 row-major [rows][ld] tensor, box = 32 columns (128 B) x 128 rows, SWIZZLE_128B, zero OOB fill
-int tc_make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld);
+// 2-D fp32 row-major [rows][ld] tensor, box = 32 columns (128 B) x box_rows rows, SWIZZLE_128B, zero OOB fill
+int tc_make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows = 128);
 int tc2_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,
                const TcArgs& args, int sm_count, cudaStream_t st);
 int tc_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,
-              const TcArgs& args, int sm_count, cudaStream_t st);
+              const TcArgs& args, int bn, int n_tiles_bound, bool pdl, bool split, int sm_count, cudaStream_t st);
 
 }  // namespace rqp

@@ -36,14 +36,26 @@ class BatchEngine(object):
         """fp32 only: W ~= W_hi + W_lo with W_hi = rna_tf32(W) (nearest, ties away: add half an ulp of
         the 10-bit mantissa to the bit pattern, clear the low 13 bits) and W_lo = rna_tf32(W - W_hi)
         (W - W_hi is exact in fp32; rounding it keeps the hardware from truncating it one-sidedly).
-        Operands of the tcgen05 3xTF32 engine; split once per setup."""
+        Operands of the tcgen05 3xTF32 engine; split once per setup.  After the n_rho * D rows of the
+        layer matrices come nc + 2 nx rows of the residual operator [A 0 0; H 0 0; 0 0 A'] of
+        ``compute_residuals`` (``reluqpth.py:309-311``), so the per-window checks use the same engine."""
         if self.W_hi is None:
             def rna(t):
                 return ((t.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
-            W = self.solver.layers.W_all
-            hi = rna(W)
+            sv = self.solver
+            qp = sv.QP
+            nx, nc = qp.nx, qp.nc
+            W = sv.layers.W_all                      # [n_rho, D, ldw]
+            n_rho, D, ldw = W.shape
+            full = torch.zeros((n_rho * D + nc + 2 * nx, ldw), dtype=torch.float32, device=W.device)
+            full[:n_rho * D] = W.reshape(n_rho * D, ldw)
+            r0 = n_rho * D
+            full[r0:r0 + nc, :nx] = qp.A
+            full[r0 + nc:r0 + nc + nx, :nx] = qp.H
+            full[r0 + nc + nx:, nx + nc:nx + 2 * nc] = qp.A.t()
+            hi = rna(full)
             self.W_hi = hi.contiguous()
-            self.W_lo = rna((W - hi).contiguous()).contiguous()
+            self.W_lo = rna((full - hi).contiguous()).contiguous()
         return self.W_hi, self.W_lo
 
     def _settings(self):
@@ -108,6 +120,7 @@ class BatchEngine(object):
         if dt == torch.float32 and engine != 1:
             wh, wl = self._tf32_planes()
             bt.W_hi, bt.W_lo = wh.data_ptr(), wl.data_ptr()
+            bt.res_planes = 1
         self.dbg = None
         if getattr(self, "want_dbg", False):
             self.dbg = torch.zeros(16, dtype=torch.int64, device=dev)

@@ -129,7 +129,9 @@ def test_tc_engine_matches_simt_for_fixed_iterations():
         vs = torch.cat([rs.x, rs.z, rs.lam], 1).double()
         scale = float(v64.abs().max())
         vts = []
-        for eng in (2, 3):            # cta_group::1 (128x128 tiles) and cta_group::2 (256x256 pair tiles)
+        # cta_group::1 (auto tile width), cta_group::2 (256x256 pair tiles), cta_group::1 with 128 / 64 / 32
+        # column tiles forced
+        for eng in (2, 3, 4, 5, 6):
             rt = m32.solve_batch(L, U, engine=eng)
             vt = torch.cat([rt.x, rt.z, rt.lam], 1).double()
             assert not torch.isnan(vt).any()
@@ -138,8 +140,45 @@ def test_tc_engine_matches_simt_for_fixed_iterations():
             assert float((vt - v64).abs().max()) <= 4 * float((vs - v64).abs().max()) + 1e-6 * scale, (it, eng)
             assert rt.status == ["max_iters_reached"] * 256 and int(rt.iter[0]) == it
             vts.append(vt)
-        # both tcgen05 kernels execute the same MMAs in the same k order: bit-identical results
-        assert torch.equal(vts[0], vts[1]), it
+        # all tcgen05 kernels execute the same MMAs per output element in the same k order: bit-identical
+        for vt in vts[1:]:
+            assert torch.equal(vts[0], vt), it
+
+
+def test_tc_engine_max_iter_fall_through_and_reported_residuals():
+    """tcgen05 engine at the max_iter fall-through (reluqpth.py:243), on and off a check boundary: same
+    status / iteration count as the SIMT fp32 engine, state within fp32 accuracy, and the reported
+    residuals (computed by the tensor-path residual GEMM) equal to an fp64 evaluation of the returned
+    iterate."""
+    plant, L, U = _fp32_setup()
+    prob = (plant.H, plant.g, plant.A, L[0], U[0])
+    H, g, A = (torch.as_tensor(t, dtype=torch.float64, device="cuda") for t in (plant.H, plant.g, plant.A))
+    for max_iter in (50, 60, 25, 10):
+        m32 = gpu_model(prob, precision=torch.float32, max_iter=max_iter, eps_abs=1e-9)
+        rs = m32.solve_batch(L, U, engine=1)
+        vs = torch.cat([rs.x, rs.z, rs.lam], 1).double()
+        scale = vs.abs().amax(1)
+        first = None
+        for eng in (0, 3, 6):
+            rt = m32.solve_batch(L, U, engine=eng)
+            assert rt.status == rs.status == ["max_iters_reached"] * 256, (max_iter, eng)
+            assert int(rt.iter.min()) == int(rt.iter.max()) == max_iter
+            vt = torch.cat([rt.x, rt.z, rt.lam], 1).double()
+            # every tcgen05 kernel runs the same MMAs per element: identical state, whatever the tile widths
+            if first is None:
+                first = vt
+            assert torch.equal(vt, first), (max_iter, eng)
+            # against plain fp32 FMA: same rho path -> fp32-grade agreement; a column whose rho estimate sits
+            # on a switching threshold may legitimately take the other branch (SURVEY F3), so a few may differ
+            same_path = rt.rho_ind == rs.rho_ind
+            err = (vt - vs).abs().amax(1) / scale
+            assert float(same_path.float().mean()) > 0.9, (max_iter, eng)
+            assert float(err[same_path].max()) <= 5e-3, (max_iter, eng, float(err[same_path].max()))
+            x, z, lam = rt.x.double(), rt.z.double(), rt.lam.double()
+            pri = (x @ A.T - z).abs().amax(1)
+            dua = (x @ H.T + lam @ A + g).abs().amax(1)
+            assert torch.allclose(rt.pri_res.double(), pri, rtol=1e-3, atol=1e-5), (max_iter, eng)
+            assert torch.allclose(rt.dua_res.double(), dua, rtol=1e-3, atol=1e-4), (max_iter, eng)
 
 
 def test_batched_fp32_solution_quality(capsys):
@@ -158,7 +197,8 @@ def test_batched_fp32_solution_quality(capsys):
     H, g, A = (torch.as_tensor(t, dtype=torch.float64, device="cuda") for t in (plant.H, plant.g, plant.A))
     # the fp32 solver clamps against the fp32-rounded bounds
     Ld, Ud = (torch.as_tensor(t, dtype=torch.float32, device="cuda").double() for t in (L, U))
-    for eng, name in ((1, "simt fp32"), (2, "tcgen05 3xTF32 1-CTA"), (3, "tcgen05 3xTF32 CTA pair")):
+    for eng, name in ((1, "simt fp32"), (0, "tcgen05 3xTF32 auto"), (3, "tcgen05 3xTF32 CTA pair"),
+                      (6, "tcgen05 3xTF32 32-column tiles")):
         r = m32.solve_batch(L, U, engine=eng)
         e32 = ((r.x.double() - xstar).abs().amax(1) / scale).cpu().numpy()
         x, z, lam = r.x.double(), r.z.double(), r.lam.double()

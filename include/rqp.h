@@ -200,6 +200,15 @@ int rqp_solve_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_bat
                       void* stream);
 
 /*
+ * Host-side plumbing of ReLU_QP.update / solve (reluqpth.py:167-174 copies the new vectors to the
+ * device, :298 synchronises): an asynchronous copy from (pinned) host memory into the solver's
+ * device buffers on the caller's stream, and a wait for that stream.  Thin wrappers, here so that a
+ * binding needs no second CUDA library.
+ */
+int rqp_copy_h2d(void* dst_dev, const void* src_host, size_t bytes, void* stream);
+int rqp_stream_sync(void* stream);
+
+/*
  * Measurement helper for bench.py's roofline denominators: reads `bytes` of `buf` `reps`
  * times with 128-bit loads from every SM and reports the average milliseconds per pass
  * (synchronises).  A buffer smaller than L2 measures L2 bandwidth, a larger one HBM.

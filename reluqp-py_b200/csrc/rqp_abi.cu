@@ -155,6 +155,18 @@ int rqp_solve_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_bat
                           static_cast<cudaStream_t>(stream));
 }
 
+int rqp_copy_h2d(void* dst_dev, const void* src_host, size_t bytes, void* stream) {
+    if (!dst_dev || !src_host) return RQP_ERR_BAD_ARG;
+    if (bytes == 0) return RQP_OK;
+    RQP_CUDA_TRY(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+    return RQP_OK;
+}
+
+int rqp_stream_sync(void* stream) {
+    RQP_CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return RQP_OK;
+}
+
 int rqp_probe_bandwidth(const void* buf, size_t bytes, int32_t reps, float* ms_per_pass, void* stream) {
     if (!buf || bytes < 16 || reps < 1 || !ms_per_pass) return RQP_ERR_BAD_ARG;
     rqp_caps caps;

@@ -660,6 +660,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         return RQP_OK;
     };
     const bool pdl_ok = getenv("RQP_NO_PDL") == nullptr;
+    const int pair_min = getenv("RQP_PAIR_MIN") ? atoi(getenv("RQP_PAIR_MIN")) : 8192;
     // residual products A x, H x, A' lambda on the tensor path: the W planes carry the residual operator
     // after the n_rho layer matrices (rqp_batch.res_planes)
     const bool res_tc = use_tc && bt->res_planes != 0 && getenv("RQP_NO_RES_TC") == nullptr;
@@ -703,7 +704,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         // auto: the CTA-pair kernel pays off once there are enough column tiles to fill the chip
         // (measured crossover ~8k active columns at D = 960); below that the 1-CTA kernel has twice
         // the parallelism per active column
-        const bool one_sm = bt->engine == 2 || bt->engine >= 4 || (bt->engine != 3 && nact_host[0] < 8192);
+        const bool one_sm = bt->engine == 2 || bt->engine >= 4 || (bt->engine != 3 && nact_host[0] < pair_min);
         if (one_sm) {
             // 1-CTA tiles of 128 rows x BN columns.  BN is the widest tile that still gives every active
             // column tile its own SM in one wave (engine 4 / 5 / 6 force 128 / 64 / 32).

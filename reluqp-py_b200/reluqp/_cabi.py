@@ -18,7 +18,8 @@ RQP_TRACE_STRIDE = 5
 EPOCH_LIMIT = 0x70000000
 
 EXPORTS = ("rqp_query", "rqp_workspace_size", "rqp_solve", "rqp_update_bias",
-           "rqp_batch_workspace_size", "rqp_solve_batched", "rqp_probe_bandwidth",
+           "rqp_batch_workspace_size", "rqp_solve_batched", "rqp_copy_h2d", "rqp_stream_sync",
+           "rqp_probe_bandwidth",
            "rqp_strerror", "rqp_last_cuda_error")
 
 
@@ -93,6 +94,8 @@ def load():
     lib.rqp_solve_batched.argtypes = [C.POINTER(rqp_problem), C.POINTER(rqp_settings), C.POINTER(rqp_batch),
                                       vp, sz, C.POINTER(i32), vp]
     lib.rqp_probe_bandwidth.argtypes = [vp, sz, i32, C.POINTER(C.c_float), vp]
+    lib.rqp_copy_h2d.argtypes = [vp, vp, sz, vp]
+    lib.rqp_stream_sync.argtypes = [vp]
     for name in EXPORTS:
         getattr(lib, name).restype = C.c_int
     lib.rqp_strerror.argtypes = [C.c_int]
@@ -101,6 +104,15 @@ def load():
     lib.rqp_last_cuda_error.restype = C.c_char_p
     _lib = lib
     return lib
+
+
+def raw_stream(device_index):
+    """cudaStream_t of torch's current stream on that device, as an int (the cheap way when torch has it)."""
+    import torch
+    try:
+        return torch._C._cuda_getCurrentRawStream(device_index)
+    except AttributeError:                       # pragma: no cover - older / newer torch layouts
+        return torch.cuda.current_stream(device_index).cuda_stream
 
 
 def check(rc, what):

@@ -243,7 +243,7 @@ class _Engine(object):
         self.state.rho_ind = int(rho_ind)
         self.state.epoch = self.epoch
         res_ptr = self.res_host.data_ptr() if self.mapped else self.res_dev.data_ptr()
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        stream = _cabi.raw_stream(self.device.index)
         rc = self.lib.rqp_solve(C.byref(self.prob), C.byref(self.stng), C.byref(self.state), res_ptr,
                                 self.trace.data_ptr() if self.trace is not None else None,
                                 self.trace_cap, self.ws.data_ptr(), self.ws.numel(), stream)
@@ -254,7 +254,7 @@ class _Engine(object):
 
     def finish(self):
         """Wait for the stream and return the result record (a live ctypes view)."""
-        torch.cuda.current_stream(self.device).synchronize()
+        _cabi.check(self.lib.rqp_stream_sync(_cabi.raw_stream(self.device.index)), "rqp_stream_sync")
         r = self.res_view
         if r.error != 0:
             self.ws.zero_()       # exchange cells may hold flags of an aborted epoch
@@ -371,20 +371,39 @@ class ReLU_QP(object):
         self._glu_np = self._glu_host.numpy()
         self._glu_event = torch.cuda.Event() if st.device.type == "cuda" else None
         self._glu_pending = False
+        self._glu_ptr, self._glu_host_ptr = buf.data_ptr(), self._glu_host.data_ptr()
+        self._glu_es = buf.element_size()
 
     def _stage(self, lo, hi, value):
         """value (numpy / torch / sequence) -> staging buffer [lo, hi); device tensors go direct."""
         if torch.is_tensor(value) and value.device.type != "cpu":
             self._glu[lo:hi].copy_(value.to(self.settings.precision), non_blocking=True)
             return None
-        if self._glu_pending:                     # the previous async copy may still read the staging buffer
-            self._glu_event.synchronize()
+        if self._glu_pending:                     # an earlier async copy may still read the staging buffer
+            if self._engine is not None:
+                _cabi.check(self._engine.lib.rqp_stream_sync(_cabi.raw_stream(self.settings.device.index)),
+                            "rqp_stream_sync")
+            elif self._glu_event is not None:
+                self._glu_event.synchronize()
             self._glu_pending = False
         if torch.is_tensor(value):
             self._glu_host[lo:hi].copy_(value)
         else:
             np.copyto(self._glu_np[lo:hi], np.asarray(value), casting="unsafe")
         return (lo, hi)
+
+    def _push(self, lo, hi):
+        """staging [lo, hi) -> device buffer, asynchronously on the current stream"""
+        eng = self._engine
+        if eng is not None and torch.cuda.current_device() == self.settings.device.index:
+            es = self._glu_es
+            _cabi.check(eng.lib.rqp_copy_h2d(self._glu_ptr + lo * es, self._glu_host_ptr + lo * es, (hi - lo) * es,
+                                             _cabi.raw_stream(self.settings.device.index)), "rqp_copy_h2d")
+        else:
+            self._glu[lo:hi].copy_(self._glu_host[lo:hi], non_blocking=True)
+            if self._glu_event is not None:
+                self._glu_event.record()
+        self._glu_pending = self._glu_event is not None
 
     def update(self, g=None, l=None, u=None, Hx=None, Ax=None):
         """Update ReLU-QP problem vectors (``reluqpth.py:159-183``).  numpy arrays or torch
@@ -402,12 +421,9 @@ class ReLU_QP(object):
             lo, hi = min(a for a, _ in spans), max(b for _, b in spans)
             if len(spans) == 2 and spans[0][1] != spans[1][0]:     # g and u only: two copies
                 for a, b in spans:
-                    self._glu[a:b].copy_(self._glu_host[a:b], non_blocking=True)
+                    self._push(a, b)
             else:
-                self._glu[lo:hi].copy_(self._glu_host[lo:hi], non_blocking=True)
-            if self._glu_event is not None:
-                self._glu_event.record()
-                self._glu_pending = True
+                self._push(lo, hi)
         if g is not None:
             L = self.layers
             if self._engine is not None:
@@ -455,6 +471,7 @@ class ReLU_QP(object):
         if st.verbose and st.adaptive_rho:
             eng.enable_trace(st.max_iter // max(1, st.check_interval) + 2)
         r = eng.run(self.output, self.rho_ind)
+        self._glu_pending = False       # run() ended with a stream synchronise: the staging buffer is free
         if st.verbose and eng.trace is not None:
             tr = eng.trace[:min(r.n_checks, eng.trace_cap) * _cabi.RQP_TRACE_STRIDE].cpu().view(-1, 5)
             for k, _, pri, dua, rho in tr.tolist():
@@ -495,10 +512,8 @@ class ReLU_QP(object):
         self.results.z = self.z
         info.iter = iter
         info.status = status
-        info.obj_val = torch.tensor(obj_val, dtype=dt)
-        info.pri_res = torch.tensor(pri_res, dtype=dt)
-        info.dua_res = torch.tensor(dua_res, dtype=dt)
-        info.rho_estimate = torch.tensor(rho_estimate, dtype=dt)
+        info.obj_val, info.pri_res, info.dua_res, info.rho_estimate = torch.tensor(
+            (obj_val, pri_res, dua_res, rho_estimate), dtype=dt).unbind(0)
         run_time = self._timer.toc(sync=False)
         info.run_time = run_time
         info.solve_time = info.update_time + run_time
@@ -510,7 +525,16 @@ class ReLU_QP(object):
         fresh state vector is allocated, so earlier ``results.x`` keep their values."""
         st = self.settings
         nx, nc = self.QP.nx, self.QP.nc
-        self.output = torch.zeros(nx + 2 * nc, device=st.device, dtype=st.precision)
+        # zero state vectors are cut from a pre-zeroed chunk (one allocation + memset per 32 cold solves);
+        # a row is handed out once, so earlier results keep their values exactly as with a fresh tensor
+        D = nx + 2 * nc
+        pool = getattr(self, "_zero_pool", None)
+        if pool is None or pool[1] >= pool[0].shape[0] or pool[0].device != st.device or pool[0].dtype != st.precision \
+                or pool[0].shape[1] != D:
+            pool = [torch.zeros((32, D), device=st.device, dtype=st.precision), 0]
+            self._zero_pool = pool
+        self.output = pool[0][pool[1]]
+        pool[1] += 1
         self.x, self.z, self.lam = self.output[:nx], self.output[nx:nx + nc], self.output[nx + nc:]
         if getattr(self, "_rho_ind0", None) is None or self._rho_ind0[0] is not self.layers:
             self._rho_ind0 = (self.layers, int(np.argmin(np.abs(np.asarray(self.layers.rho_list) - st.rho))))

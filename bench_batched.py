@@ -93,7 +93,7 @@ def run_batched(args, rank, world, dev):
                                 "eps_abs=1e-3, cold start".format(B),
                     multi_gpu="columns sharded, no per-iteration collective, final all-gather of (iter,status)",
                     l2="flushed between steps (512 MiB fill)", timing="CUDA events around rqp_solve_batched"),
-        engine={0: "auto (tcgen05: 1-CTA below 8192 active columns, CTA pair above)", 1: "simt", 2: "tcgen05 cta_group::1", 3: "tcgen05 cta_group::2"}[args.batch_engine],
+        engine={0: "auto (tcgen05 cta_group::1, 128x{128,64,32} tiles picked per check window, chunked accumulation of the x rows, PDL)", 1: "simt", 2: "tcgen05 cta_group::1", 3: "tcgen05 cta_group::2"}[args.batch_engine],
         iters_per_solve=float(iters.mean().item()), iters_max=int(iters.max().item()), sweeps=res.sweeps,
         all_solved=bool(res.status_code.eq(0).all().item()),
         roofline=dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,

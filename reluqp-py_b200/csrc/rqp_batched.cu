@@ -660,11 +660,18 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         return RQP_OK;
     };
     const bool pdl_ok = getenv("RQP_NO_PDL") == nullptr;
-    const int pair_min = getenv("RQP_PAIR_MIN") ? atoi(getenv("RQP_PAIR_MIN")) : 8192;
+    // auto never picks the CTA-pair kernel: it accumulates all of K in one TMEM accumulator, and the extra
+    // ADMM iterations that costs (see chunk_kb) outweigh its better operand reuse; engine 3 forces it
+    const int pair_min = getenv("RQP_PAIR_MIN") ? atoi(getenv("RQP_PAIR_MIN")) : 0x7fffffff;
     // residual products A x, H x, A' lambda on the tensor path: the W planes carry the residual operator
     // after the n_rho layer matrices (rqp_batch.res_planes)
     const bool res_tc = use_tc && bt->res_planes != 0 && getenv("RQP_NO_RES_TC") == nullptr;
-    const bool tc_split = getenv("RQP_TC_SPLIT") != nullptr;
+    // chunked accumulation of the 1-CTA kernels (rqp_batched_tc.cu): partial sums leave the tensor core every
+    // 2 k-blocks (64 state elements) for the rows of the x block -- the rows whose rounding error the next
+    // iteration multiplies by 1e3 * rho; measured on the C4 family: 169 -> 128 mean ADMM iterations, the
+    // same as plain fp32 FMA.  RQP_TC_CHUNK=0 turns it off, RQP_TC_CHUNK_ALL=1 chunks every row tile.
+    const int tc_chunk = getenv("RQP_TC_CHUNK") ? atoi(getenv("RQP_TC_CHUNK")) : 2;
+    const bool tc_chunk_x = getenv("RQP_TC_CHUNK_ALL") == nullptr;
     // tensor maps: W planes (128-row boxes) and the state planes with 128 / 64 / 32-row boxes
     CUtensorMap map_wh, map_wl, map_xh[3][2], map_xl[3][2];
     static const int kBoxRows[3] = {128, 64, 32};
@@ -698,7 +705,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.Yh = reinterpret_cast<float*>(c.Vh[src ^ 1]); a.Yl = reinterpret_cast<float*>(c.Vl[src ^ 1]);
         a.Yplain = write_plain ? reinterpret_cast<float*>(c.V[src ^ 1]) : nullptr;
         a.D = D; a.nx = nx; a.nc = nc; a.ldv = ldv;
-        a.raw = 0; a.M = D; a.w_row0 = 0;
+        a.raw = 0; a.M = D; a.w_row0 = 0; a.chunk_kb = tc_chunk; a.chunk_rows = tc_chunk_x ? nx : 0;
         a.k_blocks = (D + 31) / 32;
         a.dbg = static_cast<unsigned long long*>(bt->reserved_dbg);
         // auto: the CTA-pair kernel pays off once there are enough column tiles to fill the chip
@@ -712,7 +719,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
             const int b = pick_bn(a.n_row_tiles, bt->engine);
             a.n_col_tiles = 0;
             const int bound = nact_host[3 - b] * a.n_row_tiles;
-            return tc_launch(map_wh, map_wl, map_xh[b][src], map_xl[b][src], a, kBoxRows[b], bound, pdl, tc_split, sm_count, st);
+            return tc_launch(map_wh, map_wl, map_xh[b][src], map_xl[b][src], a, kBoxRows[b], bound, pdl, sm_count, st);
         }
         a.n_col_tiles = cap / 256; a.n_row_tiles = (D + 255) / 256;   // CTA-pair tiles: 256 x 256
         return tc2_launch(map_wh, map_wl, map_xh[0][src], map_xl[0][src], a, sm_count, st);
@@ -738,14 +745,13 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.Yh = nullptr; a.Yl = nullptr;
         a.Yplain = reinterpret_cast<float*>(c.Tres);
         a.D = D; a.nx = nx; a.nc = nc; a.ldv = nc + 2 * nx;
-        a.raw = 1; a.M = nc + 2 * nx; a.w_row0 = prob->n_rho * D;
+        a.raw = 1; a.M = nc + 2 * nx; a.w_row0 = prob->n_rho * D; a.chunk_kb = tc_chunk; a.chunk_rows = 0;
         a.k_blocks = (D + 31) / 32;
         a.n_col_tiles = 0; a.n_row_tiles = (a.M + 127) / 128;
         a.dbg = nullptr;
         const int b = pick_bn(a.n_row_tiles, bt->engine);
         const int bound = nact_host[3 - b] * a.n_row_tiles;
-        return tc_launch(map_wh, map_wl, map_xh[b][src], map_xl[b][src], a, kBoxRows[b], bound, false, tc_split,
-                         sm_count, st);
+        return tc_launch(map_wh, map_wl, map_xh[b][src], map_xl[b][src], a, kBoxRows[b], bound, false, sm_count, st);
     };
     auto gemm_res = [&](int src) {
         GemmArgs<T> a;

@@ -290,7 +290,7 @@ __device__ __forceinline__ int tc_tile_count(const int* sb, int n_row_tiles) {
     return n * n_row_tiles;
 }
 
-template <int BN, bool SPLIT>
+template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
                       const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
@@ -305,9 +305,15 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + size_t(STAGES) * STAGE_BYTES);
     uint64_t* full = bars;                           // [STAGES]
     uint64_t* empty = bars + STAGES;                 // [STAGES]
-    uint64_t* acc_full = bars + 2 * STAGES;          // [TC_ACC_STAGES]
-    uint64_t* acc_empty = acc_full + TC_ACC_STAGES;  // [TC_ACC_STAGES]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + TC_ACC_STAGES);
+    // Chunked accumulation (a.chunk_kb > 0): the tensor core's fp32 accumulator truncates, and over the 360
+    // MMAs of a K = 960 dot product that bias costs the ADMM iteration its last digits (the x rows feed the
+    // 1e3 * rho equality rows of the next iteration).  Every chunk_kb k-blocks the accumulator is handed to
+    // the epilogue warps, which add the partial sums in fp32 round-to-nearest in registers while the tensor
+    // core fills the next of NACC TMEM stages; the K order per element is unchanged.
+    constexpr int NACC = 4;
+    uint64_t* acc_full = bars + 2 * STAGES;          // [NACC]
+    uint64_t* acc_empty = acc_full + NACC;           // [NACC]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
     int* sb = reinterpret_cast<int*>(tmem_slot + 2);  // [64] bucket table
 
     const int warp = threadIdx.x >> 5;
@@ -320,14 +326,10 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_wh); prefetch_tmap(&map_wl); prefetch_tmap(&map_xh); prefetch_tmap(&map_xl);
         for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < TC_ACC_STAGES; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, Cfg::EPI_WARPS); }
+        for (int s = 0; s < NACC; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, Cfg::EPI_WARPS); }
         fence_mbar_init();
     }
-    // SPLIT: the cross terms (W_hi x_lo + W_lo x_hi, 2^-11 of the main term) get their own accumulator, so
-    // the main sum W_hi x_hi is truncated once per k-step instead of three times and the cross sum keeps
-    // its low bits; the epilogue adds the two in fp32
-    constexpr int ACC_COLS = SPLIT ? 2 * BN : BN;
-    constexpr int TMEM_COLS = TC_ACC_STAGES * ACC_COLS;
+    constexpr int TMEM_COLS = NACC * BN;             // 512 / 256 / 128
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
@@ -395,77 +397,102 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
             if (!tc_tile_lookup<BN>(sb, t, a.n_row_tiles, rho, col0, rt)) break;
             tc_tile_rows(a, rho, rt, wrow, kb_lo, kb_hi);
             ntile++;
-            long long tw = clock64();
-            mbar_wait(acc_empty + acc, acc_phase ^ 1u);   // epilogue has drained this accumulator
-            w_acc += clock64() - tw;
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-            const uint32_t d_cross = SPLIT ? d_tmem + BN : d_tmem;
+            const int nk = kb_hi - kb_lo;
+            const int chunk = (a.chunk_kb > 0 && a.chunk_kb < nk && (a.chunk_rows <= 0 || rt * TC_BM < a.chunk_rows))
+                                  ? a.chunk_kb : nk;
+            int in_chunk = 0;
             for (int kb = kb_lo; kb < kb_hi; ++kb) {
-                tw = clock64();
+                long long tw = clock64();
+                if (in_chunk == 0) {
+                    mbar_wait(acc_empty + acc, acc_phase ^ 1u);   // epilogue has drained this accumulator stage
+                    w_acc += clock64() - tw;
+                    tc_fence_after();
+                    tw = clock64();
+                }
                 mbar_wait(full + stage, phase);
                 w_full += clock64() - tw;
                 tc_fence_after();
+                const bool last = in_chunk == chunk - 1 || kb == kb_hi - 1;
                 if (elect_one()) {
+                    const uint32_t d_tmem = tmem_base + acc * BN;
                     unsigned char* sp = base + size_t(stage) * STAGE_BYTES;
                     const uint64_t dwh = make_kmajor_sw128_desc(sp);
                     const uint64_t dwl = make_kmajor_sw128_desc(sp + TC_TILE_BYTES);
                     const uint64_t dxh = make_kmajor_sw128_desc(sp + 2 * TC_TILE_BYTES);
                     const uint64_t dxl = make_kmajor_sw128_desc(sp + 2 * TC_TILE_BYTES + XT);
-                    const bool first_kb = kb == kb_lo;
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {
                         const uint64_t off = uint64_t((k * 8 * 4) >> 4);   // advance 32 bytes inside the swizzle row
-                        umma_tf32(d_tmem, dwh + off, dxh + off, idesc, (first_kb && k == 0) ? 0u : 1u);
-                        umma_tf32(d_cross, dwh + off, dxl + off, idesc, (SPLIT && first_kb && k == 0) ? 0u : 1u);
-                        umma_tf32(d_cross, dwl + off, dxh + off, idesc, 1u);
+                        umma_tf32(d_tmem, dwh + off, dxh + off, idesc, (in_chunk == 0 && k == 0) ? 0u : 1u);
+                        umma_tf32(d_tmem, dwh + off, dxl + off, idesc, 1u);
+                        umma_tf32(d_tmem, dwl + off, dxh + off, idesc, 1u);
                     }
-                    umma_commit(empty + stage);                       // smem slot free when these MMAs retire
-                    if (kb == kb_hi - 1) umma_commit(acc_full + acc);  // accumulator complete
+                    umma_commit(empty + stage);               // smem slot free when these MMAs retire
+                    if (last) umma_commit(acc_full + acc);    // partial (or complete) accumulator ready
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                if (last) {
+                    in_chunk = 0;
+                    if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
+                } else {
+                    ++in_chunk;
+                }
             }
-            if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
         }
         if (a.dbg && blockIdx.x == 0 && lane == 0) {
             a.dbg[2] = w_full; a.dbg[3] = w_acc; a.dbg[4] = clock64() - t_all; a.dbg[5] = ntile;
         }
     } else if (warp - 2 < Cfg::EPI_WARPS) {
         // ================= epilogue =================
+        constexpr int NCH = Cfg::COLS_PER_EPI_WARP / 32;   // 32-column register chunks per thread (1 or 2)
         const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter + 32)
         const int half = (warp - 2) >> 2;             // which share of the tile's columns
         uint32_t acc = 0, acc_phase = 0;
         long long w_accf = 0, t_all = clock64();
         grid_dep_wait();
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            int rho, col0, rt;
+            int rho, col0, rt, wrow, kb_lo, kb_hi;
             if (!tc_tile_lookup<BN>(sb, t, a.n_row_tiles, rho, col0, rt)) break;
-            const long long tw = clock64();
-            mbar_wait(acc_full + acc, acc_phase);
-            w_accf += clock64() - tw;
-            tc_fence_after();
+            tc_tile_rows(a, rho, rt, wrow, kb_lo, kb_hi);
+            const int nk = kb_hi - kb_lo;
+            const int chunk = (a.chunk_kb > 0 && a.chunk_kb < nk && (a.chunk_rows <= 0 || rt * TC_BM < a.chunk_rows))
+                                  ? a.chunk_kb : nk;
+            const int nchunks = (nk + chunk - 1) / chunk;
+            uint32_t sum[NCH][32];
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const long long tw = clock64();
+                mbar_wait(acc_full + acc, acc_phase);
+                w_accf += clock64() - tw;
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + acc * BN + (uint32_t(quarter * 32) << 16) +
+                                       uint32_t(half * Cfg::COLS_PER_EPI_WARP);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    if (ch == 0) {
+                        tmem_ld32(taddr + c * 32, sum[c]);
+                    } else {
+                        uint32_t r[32];
+                        tmem_ld32(taddr + c * 32, r);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            sum[c][j] = __float_as_uint(__uint_as_float(sum[c][j]) + __uint_as_float(r[j]));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + acc);
+                if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
+            }
             const int m = rt * TC_BM + quarter * 32 + lane;      // state row of this thread
             EpiRow e{};
             if (!a.raw) e = make_epi_row(a, m, rho);
-            const uint32_t taddr = tmem_base + acc * ACC_COLS + (uint32_t(quarter * 32) << 16);
-#pragma unroll 1
-            for (int c0 = half * Cfg::COLS_PER_EPI_WARP; c0 < (half + 1) * Cfg::COLS_PER_EPI_WARP; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(taddr + c0, r);
-                if (SPLIT) {
-                    uint32_t rc[32];
-                    tmem_ld32(taddr + BN + c0, rc);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
-                }
-                if (a.raw) tc_epilogue_raw(a, m, r, col0 + c0, lane);
-                else tc_epilogue_chunk(a, e, r, col0 + c0, lane);
+            for (int c = 0; c < NCH; ++c) {
+                const int n0 = col0 + half * Cfg::COLS_PER_EPI_WARP + c * 32;
+                if (a.raw) tc_epilogue_raw(a, m, sum[c], n0, lane);
+                else tc_epilogue_chunk(a, e, sum[c], n0, lane);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + acc);
-            if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
         }
         if (a.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) { a.dbg[6] = w_accf; a.dbg[7] = clock64() - t_all; }
     }
@@ -709,11 +736,11 @@ int tc2_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& 
     return RQP_OK;
 }
 
-template <int BN, bool SPLIT>
+template <int BN>
 static int tc_launch_bn(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,
                         const TcArgs& args, int grid, bool pdl, cudaStream_t st) {
     static bool attr_set = false;
-    auto kern = rqp_batched_tc_kernel<BN, SPLIT>;
+    auto kern = rqp_batched_tc_kernel<BN>;
     if (!attr_set) {
         RQP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           int(TcCfg<BN>::SMEM_BYTES)));
@@ -737,21 +764,13 @@ static int tc_launch_bn(const CUtensorMap& wh, const CUtensorMap& wl, const CUte
 // n_tiles_bound: upper bound on the number of tiles (the kernel derives the exact list from args.btab);
 // pdl: launch as a programmatic dependent of the previous kernel in the stream
 int tc_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,
-              const TcArgs& args, int bn, int n_tiles_bound, bool pdl, bool split, int sm_count, cudaStream_t st) {
+              const TcArgs& args, int bn, int n_tiles_bound, bool pdl, int sm_count, cudaStream_t st) {
     int grid = n_tiles_bound < sm_count ? n_tiles_bound : sm_count;
     if (grid < 1) grid = 1;
-    if (split) {
-        switch (bn) {
-            case 128: return tc_launch_bn<128, true>(wh, wl, xh, xl, args, grid, pdl, st);
-            case 64: return tc_launch_bn<64, true>(wh, wl, xh, xl, args, grid, pdl, st);
-            case 32: return tc_launch_bn<32, true>(wh, wl, xh, xl, args, grid, pdl, st);
-        }
-        return RQP_ERR_BAD_ARG;
-    }
     switch (bn) {
-        case 128: return tc_launch_bn<128, false>(wh, wl, xh, xl, args, grid, pdl, st);
-        case 64: return tc_launch_bn<64, false>(wh, wl, xh, xl, args, grid, pdl, st);
-        case 32: return tc_launch_bn<32, false>(wh, wl, xh, xl, args, grid, pdl, st);
+        case 128: return tc_launch_bn<128>(wh, wl, xh, xl, args, grid, pdl, st);
+        case 64: return tc_launch_bn<64>(wh, wl, xh, xl, args, grid, pdl, st);
+        case 32: return tc_launch_bn<32>(wh, wl, xh, xl, args, grid, pdl, st);
     }
     return RQP_ERR_BAD_ARG;
 }

@@ -20,6 +20,8 @@ struct TcArgs {
     int raw;                // 1: residual GEMM (rows of [A 0 0; H 0 0; 0 0 A'] at W-plane row w_row0), plain output
     int M;                  // output rows: D (iteration) or nc + 2 nx (residual)
     int w_row0;
+    int chunk_rows;         // > 0: only row tiles starting below this row are chunked (the x block)
+    int chunk_kb;           // 1-CTA kernels: k-blocks per accumulator chunk (0: one accumulator over all of K)
     int n_col_tiles, n_row_tiles, k_blocks;
     unsigned long long* dbg;  // optional [16] cycle counters written by CTA 0 (diagnostics)
 };
@@ -29,6 +31,6 @@ int tc_make_map(CUtensorMap* map, const void* ptr, long long rows, long long col
 int tc2_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,
                const TcArgs& args, int sm_count, cudaStream_t st);
 int tc_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,
-              const TcArgs& args, int bn, int n_tiles_bound, bool pdl, bool split, int sm_count, cudaStream_t st);
+              const TcArgs& args, int bn, int n_tiles_bound, bool pdl, int sm_count, cudaStream_t st);
 
 }  // namespace rqp

@@ -449,8 +449,9 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
         const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter + 32)
         const int half = (warp - 2) >> 2;             // which share of the tile's columns
         uint32_t acc = 0, acc_phase = 0;
-        long long w_accf = 0, t_all = clock64();
+        long long w_accf = 0, t_store = 0;
         grid_dep_wait();
+        long long t_all = clock64();
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             int rho, col0, rt, wrow, kb_lo, kb_hi;
             if (!tc_tile_lookup<BN>(sb, t, a.n_row_tiles, rho, col0, rt)) break;
@@ -484,6 +485,7 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                 if (lane == 0) mbar_arrive(acc_empty + acc);
                 if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
             }
+            const long long ts0 = clock64();
             const int m = rt * TC_BM + quarter * 32 + lane;      // state row of this thread
             EpiRow e{};
             if (!a.raw) e = make_epi_row(a, m, rho);
@@ -493,8 +495,11 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                 if (a.raw) tc_epilogue_raw(a, m, sum[c], n0, lane);
                 else tc_epilogue_chunk(a, e, sum[c], n0, lane);
             }
+            t_store += clock64() - ts0;
         }
-        if (a.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) { a.dbg[6] = w_accf; a.dbg[7] = clock64() - t_all; }
+        if (a.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) {
+            a.dbg[6] = w_accf; a.dbg[7] = clock64() - t_all; a.dbg[8] = t_store;
+        }
     }
     tc_fence_before();
     __syncthreads();

@@ -335,6 +335,202 @@ __global__ void __launch_bounds__(256, 1) bgemm_simt(GemmArgs<T> a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp64 tensor-core GEMM (mma.sync.m8n8k4.f64, SASS DMMA): same contract as bgemm_simt<double>.
+// tcgen05 has no fp64 kind, so this is the tensor path of the reference dtype.  On this B200 a register-
+// tiled DFMA loop tops out at ~26 TFLOP/s (operand-register bandwidth) and DMMA at ~31.6 of the nominal 37
+// (tools/scratch/ubench): DMMA needs one A and one B register per 512 flops.
+// CTA tile 128 (rows of Mat) x 128 (columns), K step 16, 256 threads = 8 warps as 4 (m) x 2 (n), warp tile
+// 32 x 64 = 4 x 8 DMMA tiles (64 accumulator doubles per thread).  Both operands are K-major in global
+// memory (W rows, state columns), so tiles go global -> shared with 16-byte cp.async through a 4-stage ring,
+// rows padded to 20 doubles: a fragment load (lane -> row lane/4, k lane%4) is conflict free.
+// ------------------------------------------------------------------------------------------------
+constexpr int DK = 16, DLD = 20, DSTAGES = 4;
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+
+// WM x WN warp tiles of 32 (rows) x 64 (columns): CTA tile (32 WM) x (64 WN); KS warps share one warp tile
+// and split K between them (warp group g takes the g-th k4 step of every 16-wide stage; partial sums are
+// added through shared memory in a fixed order at the end).  A warp is bound by its scheduler's DMMA pipe
+// (one m8n8k4 per ~16 cycles), so the latency of a tile is set by the DMMAs PER WARP:
+// <4,2,1> = 128 x 128, 8 warps: 7680 DMMAs per warp, for full batches (least operand traffic per flop);
+// <2,1,4> =  64 x  64, 8 warps: 1920 DMMAs per warp, for small active sets (4x the CTAs, ~1/4 the latency).
+template <int EPI, int WM, int WN, int KS>
+__global__ void __launch_bounds__(32 * WM * WN * KS, 1) bgemm_dmma(GemmArgs<double> a) {
+    static_assert(KS == 1 || KS == DK / 4, "K split is one k4 step of a stage per warp group");
+    constexpr int DM = 32 * WM, DN = 64 * WN, NT = 32 * WM * WN * KS;
+    constexpr int STAGE_DOUBLES = (DM + DN) * DLD;
+    constexpr int PIECES = (DM + DN) * (DK / 2) / NT;    // 16-byte pieces per thread and stage
+    const int n0 = blockIdx.y * DN;
+    const int rho_i = a.tile_rho[n0 / BALIGN];
+    if (rho_i < 0) return;
+    if (a.orig[n0] < 0) return;                          // columns are compacted at the bucket start
+    const int m0 = blockIdx.x * DM;
+    const double* __restrict__ Mat = a.mat + (EPI == EPI_ITER ? size_t(rho_i) * a.mat_stride : 0);
+    extern __shared__ __align__(16) double dsm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wt = warp % (WM * WN), kg = warp / (WM * WN);   // warp tile, K group
+    const int wm = wt % WM, wn = wt / WM;                // warp tile origin: rows 32 wm, columns 64 wn
+    const int fr = lane >> 2, fk = lane & 3;             // fragment row / k of this lane
+
+    const int n_k = (a.K + DK - 1) / DK;
+    auto load_stage = [&](int kb, int stage) {
+        double* As = dsm + size_t(stage) * STAGE_DOUBLES;
+        double* Bs = As + DM * DLD;
+        const int k0 = kb * DK;
+#pragma unroll
+        for (int i = 0; i < PIECES; ++i) {
+            const int p = tid + i * NT;                  // piece index
+            const int row = p >> 3, kk = (p & 7) * 2;    // tile row, k offset 0,2,..,14
+            const int k = k0 + kk;
+            int bytes = (a.K - k) * 8;
+            bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+            if (row < DM) {
+                const int m = m0 + row;
+                const double* src = Mat + size_t(m < a.M ? m : a.M - 1) * a.ldm + (bytes ? k : 0);
+                cp_async16_zfill(As + row * DLD + kk, src, m < a.M ? bytes : 0);
+            } else {
+                const int n = n0 + row - DM;
+                const double* src = a.X + size_t(n) * a.ldx + a.ko + (bytes ? k : 0);
+                cp_async16_zfill(Bs + (row - DM) * DLD + kk, src, bytes);
+            }
+        }
+    };
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < DSTAGES - 1; ++s) {
+        if (s < n_k) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kb = 0; kb < n_k; ++kb) {
+        cp_async_wait<DSTAGES - 2>();
+        __syncthreads();                                  // stage kb landed; stage kb-1 is free for reuse
+        if (kb + DSTAGES - 1 < n_k) load_stage(kb + DSTAGES - 1, (kb + DSTAGES - 1) % DSTAGES);
+        cp_async_commit();
+        const double* As = dsm + size_t(kb % DSTAGES) * STAGE_DOUBLES + (32 * wm + fr) * DLD + fk;
+        const double* Bs = dsm + size_t(kb % DSTAGES) * STAGE_DOUBLES + DM * DLD + (64 * wn + fr) * DLD + fk;
+#pragma unroll
+        for (int s4 = 0; s4 < (KS == 1 ? DK / 4 : 1); ++s4) {
+            const int k4 = KS == 1 ? s4 : kg;
+            double af[4], bf[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = As[i * 8 * DLD + k4 * 4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bf[j] = Bs[j * 8 * DLD + k4 * 4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma884(acc[i][j], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+    if (KS > 1) {
+        // K groups 1..KS-1 hand their partial sums to group 0, one group at a time (fixed order)
+        __syncthreads();                                  // every warp is done with the stage ring
+        double* red = dsm + (size_t(wt) * 64) * 32 + lane;
+        for (int g = 1; g < KS; ++g) {
+            if (kg == g) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        red[((i * 8 + j) * 2 + 0) * 32] = acc[i][j][0];
+                        red[((i * 8 + j) * 2 + 1) * 32] = acc[i][j][1];
+                    }
+            }
+            __syncthreads();
+            if (kg == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        acc[i][j][0] += red[((i * 8 + j) * 2 + 0) * 32];
+                        acc[i][j][1] += red[((i * 8 + j) * 2 + 1) * 32];
+                    }
+            }
+            __syncthreads();
+        }
+        if (kg != 0) return;
+    }
+
+    // epilogue: acc[i][j][e] is row m0 + 32 wm + 8 i + lane/4, column n0 + 64 wn + 8 j + 2 (lane%4) + e
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int n = n0 + 64 * wn + 8 * j + 2 * fk + e;
+            int o = 0;
+            if (EPI == EPI_ITER) {
+                o = a.orig[n];
+                if (o < 0) continue;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int m = m0 + 32 * wm + 8 * i + fr;
+                if (m >= a.M) continue;
+                double y = acc[i][j][e];
+                if (EPI == EPI_ITER) {
+                    y += a.bias_cols ? a.bias_cols[size_t(n) * a.D + m] : __ldg(a.b_all + size_t(rho_i) * a.D + m);
+                    if (m >= a.nx && m < a.nx + a.nc) {
+                        const double lo = __ldg(a.L + size_t(o) * a.nc + (m - a.nx));
+                        const double hi = __ldg(a.U + size_t(o) * a.nc + (m - a.nx));
+                        y = clamp_keep_nan(y, lo, hi);
+                    }
+                }
+                a.out[size_t(n) * a.ldo + a.mo + m] = y;
+            }
+        }
+    }
+}
+
+template <typename T, int EPI>
+struct DmmaLaunch {
+    static bool ok(const GemmArgs<T>&) { return false; }
+    static void go(const GemmArgs<T>&, int, int, bool, cudaStream_t) {}
+};
+template <int EPI>
+struct DmmaLaunch<double, EPI> {
+    // 16-byte cp.async needs even leading dimensions / offsets and 16-byte aligned bases
+    static bool ok(const GemmArgs<double>& a) {
+        return (a.ldm % 2) == 0 && (a.ldx % 2) == 0 && (a.ko % 2) == 0 && (a.mat_stride % 2) == 0 &&
+               (reinterpret_cast<uintptr_t>(a.mat) % 16) == 0 && (reinterpret_cast<uintptr_t>(a.X) % 16) == 0;
+    }
+    template <int WM, int WN, int KS>
+    static void launch(const GemmArgs<double>& a, int Mrows, int cap, cudaStream_t st) {
+        constexpr size_t ring = size_t(DSTAGES) * (32 * WM + 64 * WN) * DLD * sizeof(double);
+        constexpr size_t red = KS > 1 ? size_t(WM * WN) * 64 * 32 * sizeof(double) : 0;
+        constexpr size_t smem = ring > red ? ring : red;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(bgemm_dmma<EPI, WM, WN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            attr_set = true;
+        }
+        bgemm_dmma<EPI, WM, WN, KS>
+            <<<dim3((Mrows + 32 * WM - 1) / (32 * WM), cap / (64 * WN)), 32 * WM * WN * KS, smem, st>>>(a);
+    }
+    static void go(const GemmArgs<double>& a, int Mrows, int cap, bool big, cudaStream_t st) {
+        if (big) launch<4, 2, 1>(a, Mrows, cap, st);
+        else launch<2, 1, 4>(a, Mrows, cap, st);
+    }
+};
+
 // Small-tile variant (64 x 64 x 16, 4 x 4 per thread): four times as many CTAs per active column, used
 // while few columns are active (latency matters more than shared-memory traffic there).
 constexpr int SM64 = 64, SK64 = 16;
@@ -660,6 +856,13 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         return RQP_OK;
     };
     const bool pdl_ok = getenv("RQP_NO_PDL") == nullptr;
+    // fp64: DMMA tensor-core GEMM (engine 1 forces the SIMT kernels)
+    const bool use_dmma = std::is_same<T, double>::value && bt->engine != 1 && getenv("RQP_NO_DMMA") == nullptr;
+    const int dmma_min = getenv("RQP_DMMA_MIN") ? atoi(getenv("RQP_DMMA_MIN")) : 1;
+    // 64 x 64 split-K tiles (a quarter of the latency per tile) while they fit in two waves of SMs,
+    // 128 x 128 tiles (half the operand traffic per flop) above
+    const int dmma_big = getenv("RQP_DMMA_BIG") ? atoi(getenv("RQP_DMMA_BIG"))
+                                                : 64 * (2 * sm_count / ((D + 63) / 64)) + 1;
     // auto never picks the CTA-pair kernel: it accumulates all of K in one TMEM accumulator, and the extra
     // ADMM iterations that costs (see chunk_kb) outweigh its better operand reuse; engine 3 forces it
     const int pair_min = getenv("RQP_PAIR_MIN") ? atoi(getenv("RQP_PAIR_MIN")) : 0x7fffffff;
@@ -732,7 +935,9 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.M = D; a.K = D; a.tile_rho = c.tile_rho;
         a.b_all = c.b_all; a.bias_cols = with_g ? c.Bias[lcur] : nullptr;
         a.L = c.L; a.U = c.U; a.orig = c.orig[lcur]; a.nx = nx; a.nc = nc; a.D = D;
-        if (nact_host[0] < 2048) {
+        if (use_dmma && nact_host[0] >= dmma_min && DmmaLaunch<T, EPI_ITER>::ok(a)) {
+            DmmaLaunch<T, EPI_ITER>::go(a, D, cap, nact_host[0] >= dmma_big, st);
+        } else if (nact_host[0] < 2048) {
             bgemm_simt64<T, EPI_ITER><<<dim3((D + SM64 - 1) / SM64, cap / SM64), 256, 0, st>>>(a);
         } else {
             bgemm_simt<T, EPI_ITER><<<dim3((D + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
@@ -758,19 +963,24 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.ldm = 0; a.mat_stride = 0; a.X = c.V[src]; a.ldx = ldv; a.out = c.Tres; a.ldo = nc + 2 * nx;
         a.tile_rho = c.tile_rho; a.b_all = nullptr; a.bias_cols = nullptr; a.L = nullptr; a.U = nullptr;
         a.orig = c.orig[lcur]; a.nx = nx; a.nc = nc; a.D = D;
+        const bool small = nact_host[0] < 2048;
+        auto one = [&](int Mrows) {
+            if (use_dmma && nact_host[0] >= dmma_min && DmmaLaunch<T, EPI_RAW>::ok(a))
+                DmmaLaunch<T, EPI_RAW>::go(a, Mrows, cap, nact_host[0] >= dmma_big, st);
+            else if (small)
+                bgemm_simt64<T, EPI_RAW><<<dim3((Mrows + SM64 - 1) / SM64, cap / SM64), 256, 0, st>>>(a);
+            else
+                bgemm_simt<T, EPI_RAW><<<dim3((Mrows + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
+        };
         // A x
         a.mat = c.A; a.ldm = nx; a.M = nc; a.K = nx; a.ko = 0; a.mo = 0;
-        const bool small = nact_host[0] < 2048;
-        if (small) bgemm_simt64<T, EPI_RAW><<<dim3((nc + SM64 - 1) / SM64, cap / SM64), 256, 0, st>>>(a);
-        else bgemm_simt<T, EPI_RAW><<<dim3((nc + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
+        one(nc);
         // H x
         a.mat = c.H; a.ldm = nx; a.M = nx; a.K = nx; a.ko = 0; a.mo = nc;
-        if (small) bgemm_simt64<T, EPI_RAW><<<dim3((nx + SM64 - 1) / SM64, cap / SM64), 256, 0, st>>>(a);
-        else bgemm_simt<T, EPI_RAW><<<dim3((nx + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
+        one(nx);
         // A' lambda
         a.mat = c.AT; a.ldm = nc; a.M = nx; a.K = nc; a.ko = nx + nc; a.mo = nc + nx;
-        if (small) bgemm_simt64<T, EPI_RAW><<<dim3((nx + SM64 - 1) / SM64, cap / SM64), 256, 0, st>>>(a);
-        else bgemm_simt<T, EPI_RAW><<<dim3((nx + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
+        one(nx);
     };
 
     // ---- start: v = 0, rho index from the caller, first grouping into buffer 0

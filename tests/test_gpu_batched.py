@@ -59,6 +59,42 @@ def test_c2_columns_match_reference_and_single_path(golden):
         assert rel_err(res.x[j].cpu().numpy(), r1.x.cpu().numpy()) < 1e-9
 
 
+def test_fp64_dmma_engine_matches_reference(golden, monkeypatch):
+    """The fp64 tensor-core GEMM (mma.sync.m8n8k4.f64) is used from 512 active columns up; forced here for
+    every window so that the 32 golden C2 columns (iteration counts 75..125, several rho buckets) and the
+    per-column-g / fall-through cases run through it.  Same iteration counts as the real reference, x / z to
+    1e-6, and agreement with the SIMT engine to summation-order rounding."""
+    monkeypatch.setenv("RQP_DMMA_MIN", "1")
+    plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+    X0 = plant.sample_x0(32)
+    L, U = plant.bounds(X0)
+    m = gpu_model((plant.H, plant.g, plant.A, L[0], U[0]))
+    res = m.solve_batch(L, U, engine=2 - 2)          # auto -> DMMA (32 columns is below the small-batch cut-off
+    assert res.sweeps == 0                            # ... which routes to the single-QP kernel), so force below
+    big_L, big_U = np.tile(L, (4, 1)), np.tile(U, (4, 1))   # 128 columns: batched engine, DMMA forced by the env
+    res = m.solve_batch(big_L, big_U)
+    assert res.sweeps > 0
+    ref = m.solve_batch(big_L, big_U, engine=1)
+    np.testing.assert_array_equal(res.iter.cpu().numpy(), ref.iter.cpu().numpy())
+    assert float((res.x - ref.x).abs().max()) < 1e-9 * float(ref.x.abs().max()) + 1e-12
+    for j in range(128):
+        gold = golden.case("mpc", "mpc_col{}".format(j % 32))
+        assert int(res.iter[j]) == gold["iter"], j
+        assert rel_err(res.x[j].cpu().numpy(), gold["x"]) < 1e-6, j
+        assert rel_err(res.z[j].cpu().numpy(), gold["z"]) < 1e-6, j
+    # max_iter fall-through on and off a check boundary, against the live oracle
+    plant2 = RandomLinMPC(nx=4, nu=2, horizon=5, seed=3, u_max=0.1)
+    L2, U2 = plant2.bounds(plant2.sample_x0(70))
+    for kw in (dict(max_iter=60, eps_abs=1e-12), dict(max_iter=50, eps_abs=1e-12)):
+        m2 = gpu_model((plant2.H, plant2.g, plant2.A, L2[0], U2[0]), **kw)
+        r2 = m2.solve_batch(L2, U2)
+        assert r2.sweeps > 0
+        refs = O.solve_batch(plant2.H, plant2.g, plant2.A, L2[:6], U2[:6], **kw)
+        for j, r in enumerate(refs):
+            assert int(r2.iter[j]) == r.iter and r2.status[j] == r.status, (kw, j)
+            assert rel_err(r2.x[j].cpu().numpy(), r.x.numpy()) < 1e-6, (kw, j)
+
+
 def test_small_batch_dispatch_matches_batched_engine():
     """B <= 64 (fp64) is routed to the persistent single-QP kernel; the result must be the same as
     the batched engine's (forced with engine=1) column by column."""

@@ -462,6 +462,7 @@ def run_single(args, rank, world, dev):
         us_per_admm_iter_in_kernel=sum(loop_us) / sum(iters),
         iters_per_solve=sum(iters) / len(iters),
         all_solved=all(s == 0 for s in statuses),
+        setup_ms=1e3 * float(m.results.info.setup_time),   # one-time, batched over the rho grid; never in solves/s
         phase_cycles_per_iter=dict(zip(
             ["wait_v", "gemv_reduce", "cta_barrier", "finalize_publish", "checks", "failed_poll_rounds", "slab_loads"],
             [round(sum(ph[i] for ph in phases) / sum(iters), 1) for i in range(7)])),

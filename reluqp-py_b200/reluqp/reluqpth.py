@@ -115,14 +115,17 @@ class ReLU_Layer(object):
 
     def setup_matrices(self):
         """W_rho (3x3 blocks over [x; z; lambda]), B_rho = [-K; -AK; 0], b_rho = B_rho g with
-        K = (H + sigma I + A' R A)^-1 (``reluqpth.py:52-77``).  Blocks are written
-        straight into the strided destination; the diagonal factors R, R^-1 are applied as row
-        / column scalings (bit-identical to the reference's products with diag matrices)."""
+        K = (H + sigma I + A' R A)^-1 (``reluqpth.py:52-77``), for ALL rho at once: the
+        reference's loop over the rho grid (18 latency-bound inversions and ~180 small GEMMs) becomes
+        batched tensor ops over a leading rho dimension -- one batched LU inverse, batched GEMMs -- in
+        chunks that keep the intermediates under ~2 GB.  Products follow the reference's association
+        order; the diagonal factors R, R^-1 are applied as row / column scalings (bit-identical to
+        multiplying by diag matrices); blocks are written straight into the strided destination."""
         st = self.settings
         q = self._setup_QP
         sdt = q.H.dtype
         dev = q.H.device
-        H, g, A, l, u = q.H, q.g, q.A, q.l, q.u
+        H, A, l, u = q.H, q.A, q.l, q.u
         nx, nc = q.nx, q.nc
         D = nx + 2 * nc
         ldw = _round_up(D, 4)
@@ -133,28 +136,35 @@ class ReLU_Layer(object):
         Ix = torch.eye(nx, device=dev, dtype=sdt)
         Ic = torch.eye(nc, device=dev, dtype=sdt)
         At = A.T
-        for i, rs in enumerate(self.rho_list):
-            rvec = torch.full((nc,), rs, device=dev, dtype=sdt)
-            rvec[eq] = rs * 1e3
-            RA = rvec[:, None] * A                       # R A
-            AtRA = At @ RA
+        # rho vectors in double (the reference forms rho * 1e3 in Python floats), then the setup dtype
+        rho64 = torch.tensor(self.rho_list, device=dev, dtype=torch.float64)
+        rvec_all = rho64[:, None].repeat(1, nc)
+        rvec_all[:, eq] = (rho64 * 1e3)[:, None]
+        rvec_all = rvec_all.to(sdt)
+        per_rho = 8 * (3 * nx * nx + 3 * nx * nc + nc * nc) * H.element_size() // 8
+        chunk = max(1, min(n, int((2 << 30) // max(1, per_rho))))
+        for c0 in range(0, n, chunk):
+            rvec = rvec_all[c0:c0 + chunk]                # [m, nc]
+            m = rvec.shape[0]
+            RA = rvec[:, :, None] * A                     # R A          [m, nc, nx]
+            AtRA = At @ RA                                #              [m, nx, nx]
             K = torch.linalg.inv(H + st.sigma * Ix + AtRA)
             S = st.sigma * Ix - AtRA
-            KAt = K @ At
-            AK = A @ K
-            AKAt = AK @ At
-            W = W_all[i]
-            W[:nx, :nx] = K @ S
-            W[:nx, nx:nx + nc] = (2 * KAt) * rvec
-            W[:nx, nx + nc:D] = -KAt
-            W[nx:nx + nc, :nx] = AK @ S + A
-            W[nx:nx + nc, nx:nx + nc] = (2 * AKAt) * rvec - Ic
-            W[nx:nx + nc, nx + nc:D] = -AKAt + torch.diag(1.0 / rvec)
-            W[nx + nc:, :nx] = RA
-            W[nx + nc:, nx:nx + nc] = -torch.diag(rvec)
-            W[nx + nc:, nx + nc:D] = Ic
-            B_all[i, :nx] = -K
-            B_all[i, nx:nx + nc] = -AK
+            KAt = K @ At                                  #              [m, nx, nc]
+            AK = A @ K                                    #              [m, nc, nx]
+            AKAt = AK @ At                                #              [m, nc, nc]
+            W = W_all[c0:c0 + m]
+            W[:, :nx, :nx] = K @ S
+            W[:, :nx, nx:nx + nc] = (2 * KAt) * rvec[:, None, :]
+            W[:, :nx, nx + nc:D] = -KAt
+            W[:, nx:nx + nc, :nx] = AK @ S + A
+            W[:, nx:nx + nc, nx:nx + nc] = (2 * AKAt) * rvec[:, None, :] - Ic
+            W[:, nx:nx + nc, nx + nc:D] = -AKAt + torch.diag_embed(1.0 / rvec)
+            W[:, nx + nc:, :nx] = RA
+            W[:, nx + nc:, nx:nx + nc] = -torch.diag_embed(rvec)
+            W[:, nx + nc:, nx + nc:D] = Ic
+            B_all[c0:c0 + m, :nx] = -K
+            B_all[c0:c0 + m, nx:nx + nc] = -AK
         b_all = torch.matmul(B_all, self.QP.g).contiguous()
         return W_all, B_all, b_all
 

@@ -81,7 +81,8 @@ def run_batched(args, rank, world, dev):
         peak, peak_note = peaks["bf16_tflops_sustained"] / 2.0, \
             "TF32 dense = half of the measured sustained bf16 cuBLAS rate; 3xTF32 executes 3x the algorithmic flops"
     else:
-        peak, peak_note = 40.0, "nominal B200 fp64 (no measured fp64 peak in MEASURED_PEAKS.json)"
+        peak, peak_note = 37.1, ("fp64 DMMA rate measured on a B200 of this pool with tools/scratch/ubench/fp64_rate.cu "
+                                 "(no fp64 figure in MEASURED_PEAKS.json)")
     iters = res.iter.float()
     line = dict(
         metric="qp_solves_per_sec", value=B * args.steps * world / float(tmax.item()), unit="solves/s",
@@ -93,19 +94,24 @@ def run_batched(args, rank, world, dev):
                                 "eps_abs=1e-3, cold start".format(B),
                     multi_gpu="columns sharded, no per-iteration collective, final all-gather of (iter,status)",
                     l2="flushed between steps (512 MiB fill)", timing="CUDA events around rqp_solve_batched"),
-        engine={0: "auto (tcgen05 cta_group::1, 128x{128,64,32} tiles picked per check window, chunked accumulation of the x rows, PDL)", 1: "simt", 2: "tcgen05 cta_group::1", 3: "tcgen05 cta_group::2"}[args.batch_engine],
+        engine={0: "auto (tcgen05 cta_group::1, 128x{128,64,32} tiles picked per check window, chunked accumulation of the x rows, PDL)", 1: "simt", 2: "tcgen05 cta_group::1", 3: "tcgen05 cta_group::2"}[args.batch_engine] if dt == torch.float32 else {0: "fp64 DMMA (mma.sync.m8n8k4.f64)", 1: "fp64 simt"}.get(args.batch_engine, "?"),
         iters_per_solve=float(iters.mean().item()), iters_max=int(iters.max().item()), sweeps=res.sweeps,
         all_solved=bool(res.status_code.eq(0).all().item()),
         roofline=dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
-                      traffic=None, peak_source=peaks["source"], note=peak_note +
-                      "; achieved = ALGORITHMIC flops 2*D^2 per column-iteration actually run / time"),
+                      traffic=None, peak_source=peaks["source"],
+                      executed=achieved * (3.0 if dt == torch.float32 and args.batch_engine != 1 else 1.0),
+                      executed_frac=achieved * (3.0 if dt == torch.float32 and args.batch_engine != 1 else 1.0) / peak,
+                      note=peak_note + "; achieved = ALGORITHMIC flops 2*D^2 per column-iteration actually run / "
+                      "time over WHOLE solves (checks, regroups and the straggler tail included); executed = what "
+                      "the tensor pipe runs (3 TF32 MMAs per product)"),
         e2e=dict(value=B * args.steps * world / float(te.item()), unit="solves/s",
                  h2d_bytes_per_step=2 * B * nc * elem, d2h_bytes_per_step=B * nx * elem,
                  ms_per_step=1e3 * float(te.item()) / args.steps,
                  api="ReLU_QP.solve_batch(l=numpy, u=numpy); results.x.cpu()"),
         gpu_launches=None, clocks=clocks)
-    # kernels per step: sweeps * (check_interval GEMMs + 3 residual GEMMs + check + 3 regroup) (+ init)
-    line["gpu_launches"] = args.steps * (res.sweeps * (25 + 3 + 1 + 3) + 4)
+    # kernels per step: sweeps * (check_interval iteration GEMMs + residual GEMM(s) + check + scan + scatter) (+ init)
+    n_res = 1 if (dt == torch.float32 and args.batch_engine != 1) else 3
+    line["gpu_launches"] = args.steps * (res.sweeps * (25 + n_res + 3) + 4)
     if not args.no_cpu_baseline:
         wl = make_workload("mpc_batched")
         wl["L"], wl["U"] = L[:64], U[:64]

@@ -517,10 +517,11 @@ struct DmmaLaunch<double, EPI> {
         constexpr size_t ring = size_t(DSTAGES) * (32 * WM + 64 * WN) * DLD * sizeof(double);
         constexpr size_t red = KS > 1 ? size_t(WM * WN) * 64 * 32 * sizeof(double) : 0;
         constexpr size_t smem = ring > red ? ring : red;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static bool attr_set[kMaxDevices] = {};
+        const int dev = current_device_slot();
+        if (!attr_set[dev]) {
             cudaFuncSetAttribute(bgemm_dmma<EPI, WM, WN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-            attr_set = true;
+            attr_set[dev] = true;
         }
         bgemm_dmma<EPI, WM, WN, KS>
             <<<dim3((Mrows + 32 * WM - 1) / (32 * WM), cap / (64 * WN)), 32 * WM * WN * KS, smem, st>>>(a);

@@ -727,11 +727,12 @@ int tc_make_map(CUtensorMap* map, const void* ptr, long long rows, long long col
 
 int tc2_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,
                const TcArgs& args, int sm_count, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[kMaxDevices] = {};
+    const int dev = current_device_slot();
+    if (!attr_set[dev]) {
         RQP_CUDA_TRY(cudaFuncSetAttribute(rqp_batched_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           int(TC_SMEM_BYTES)));
-        attr_set = true;
+        attr_set[dev] = true;
     }
     const int n_tiles = args.n_col_tiles * args.n_row_tiles;
     int pairs = sm_count / 2;
@@ -744,12 +745,13 @@ int tc2_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& 
 template <int BN>
 static int tc_launch_bn(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,
                         const TcArgs& args, int grid, bool pdl, cudaStream_t st) {
-    static bool attr_set = false;
+    static bool attr_set[kMaxDevices] = {};
+    const int dev = current_device_slot();
     auto kern = rqp_batched_tc_kernel<BN>;
-    if (!attr_set) {
+    if (!attr_set[dev]) {
         RQP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           int(TcCfg<BN>::SMEM_BYTES)));
-        attr_set = true;
+        attr_set[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(grid));

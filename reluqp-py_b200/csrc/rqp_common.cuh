@@ -20,6 +20,15 @@ void set_last_cuda_error(cudaError_t e);
         }                                          \
     } while (0)
 
+// Function attributes (dynamic shared memory opt-in) are per device: a process that drives several
+// GPUs must set them once on each, so the "already done" caches are indexed by the current device.
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Small device utilities.
 // ---------------------------------------------------------------------------------------------

@@ -735,7 +735,8 @@ static int launch_one(const SingleParams& prm, const SinglePlan& plan, cudaStrea
     auto kern = rqp_single_kernel<T, CPT, NT, RMODE>;
     // per-instantiation cache of the largest dynamic shared memory size already opted into (and
     // checked to be launchable); saves two runtime calls per solve
-    static size_t smem_ok = 0;
+    static size_t smem_ok_dev[kMaxDevices] = {};
+    size_t& smem_ok = smem_ok_dev[current_device_slot()];
     if (plan.smem_bytes > smem_ok || smem_ok == 0) {
         RQP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes)));
         int occ = 0;

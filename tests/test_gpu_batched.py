@@ -96,7 +96,7 @@ def test_fp64_dmma_engine_matches_reference(golden, monkeypatch):
 
 
 def test_small_batch_dispatch_matches_batched_engine():
-    """B <= 64 (fp64) is routed to the persistent single-QP kernel; the result must be the same as
+    """B <= 40 (fp64) is routed to the persistent single-QP kernel; the result must be the same as
     the batched engine's (forced with engine=1) column by column."""
     plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
     L, U = plant.bounds(plant.sample_x0(6))

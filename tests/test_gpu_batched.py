@@ -221,6 +221,53 @@ def test_tc_engine_max_iter_fall_through_and_reported_residuals():
             assert torch.allclose(rt.dua_res.double(), dua, rtol=1e-3, atol=1e-4), (max_iter, eng)
 
 
+def test_tc_engine_odd_sizes_and_per_column_g(capsys):
+    """tcgen05 engine away from the MPC shape: D = 58 and D = 171 (not multiples of the 32-element k-block or
+    of the 128-row tile: TMA zero fill, partial row tiles, short K ranges for the residual operator) with a
+    per-column g (bias recomputed per column and rho bucket, generic epilogue) and 70 / 300 columns.
+    Asserted: every column solved like fp64; the reported residuals equal an fp64 evaluation of the returned
+    iterate and satisfy the termination thresholds; x agrees with the fp64 solve to the accuracy eps_abs
+    allows.  Iteration counts are REPORTED: on this dense random family the fp32 engines sit on
+    their rounding floor (fp64 ~52, fp32 FMA ~68, 3xTF32 ~96 iterations for nx=30: two TF32 planes carry
+    ~23 bits of W and of the state, one less than fp32)."""
+    for (nx, ne, ni, B, seed) in ((30, 7, 7, 70, 4), (85, 20, 23, 300, 6)):
+        H, g, A, l, u, _ = utils.rand_qp(nx, ne, ni, seed=seed, compute_sol=False)
+        Gs, Ls, Us = [], [], []
+        for sd in range(B):
+            _, g2, _, l2, u2, _ = utils.update_qp(H, A, ne, ni, seed=100 + sd, compute_sol=False)
+            Gs.append(g2); Ls.append(l2); Us.append(u2)
+        G, L, U = np.stack(Gs), np.stack(Ls), np.stack(Us)
+        nc = ne + ni
+        r64 = gpu_model((H, g, A, l, u), eps_abs=1e-3).solve_batch(L, U, g=G)
+        m = gpu_model((H, g, A, l, u), precision=torch.float32, eps_abs=1e-3)
+        rs = m.solve_batch(L, U, g=G, engine=1)
+        Hd, Ad = (torch.as_tensor(t, dtype=torch.float64, device="cuda") for t in (H, A))
+        Gd = torch.as_tensor(G, dtype=torch.float32, device="cuda").double()
+        scale = r64.x.abs().amax(1)
+        e_simt = float(((rs.x.double() - r64.x).abs().amax(1) / scale).max())
+        for eng in (0, 6, 3):
+            rt = m.solve_batch(L, U, g=G, engine=eng)
+            with capsys.disabled():
+                print("\n[nx={} engine {}] iterations mean {:.1f} max {} (fp32 FMA {:.1f} / {}, fp64 {:.1f} / {})".format(
+                    nx, eng, rt.iter.float().mean().item(), int(rt.iter.max()), rs.iter.float().mean().item(),
+                    int(rs.iter.max()), r64.iter.float().mean().item(), int(r64.iter.max())))
+            assert rt.status == rs.status == r64.status == ["solved"] * B, (nx, eng)
+            assert rt.iter.float().mean().item() <= 2.0 * rs.iter.float().mean().item(), (nx, eng)
+            x, z, lam = rt.x.double(), rt.z.double(), rt.lam.double()
+            pri = (x @ Ad.T - z).abs().amax(1)
+            dua = (x @ Hd.T + lam @ Ad + Gd).abs().amax(1)
+            # fp32 residuals are differences of large terms: they agree with an fp64 evaluation to a few fp32
+            # ulps of the term magnitudes |H||x| + |A'||lam| + |g| (resp. |A||x| + |z|)
+            thr_p, thr_d = 1e-3 * np.sqrt(nc), 1e-3 * np.sqrt(nx)
+            mag_p = (x.abs() @ Ad.abs().T + z.abs()).amax(1)
+            mag_d = (x.abs() @ Hd.abs().T + lam.abs() @ Ad.abs() + Gd.abs()).amax(1)
+            assert bool(((rt.pri_res.double() - pri).abs() <= 2e-6 * mag_p).all()), (nx, eng)
+            assert bool(((rt.dua_res.double() - dua).abs() <= 2e-6 * mag_d).all()), (nx, eng)
+            assert bool((pri < thr_p + 2e-6 * mag_p).all()) and bool((dua < thr_d + 2e-6 * mag_d).all()), (nx, eng)
+            e_tc = float(((x - r64.x).abs().amax(1) / scale).max())
+            assert e_tc < 3 * e_simt + 1e-3, (nx, eng, e_tc, e_simt)
+
+
 def test_batched_fp32_solution_quality(capsys):
     """fp32 contract on the MPC family (fp32 iteration counts are rounding-chaotic, so they
     are REPORTED).  Asserted: every column reaches 'solved' like fp64; the fp32 solution satisfies the

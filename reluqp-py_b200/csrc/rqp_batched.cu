@@ -723,7 +723,7 @@ struct PinnedRecord {
 struct BatchLayout {
     int cap, n_tiles;
     size_t off_V[2], off_Vh[2], off_Vl[2], off_Bias[2], off_orig[2], off_ri[2], off_rhoc[2], off_T, off_key, off_pri, off_dua,
-        off_counts, off_starts, off_cursor, off_tile, off_btab, off_nact, total;
+        off_counts, off_starts, off_cursor, off_tile, off_btab, off_done, off_nact, total;
 };
 
 static BatchLayout batch_layout(const rqp_problem* p, int B, int ldv, bool with_g) {
@@ -751,6 +751,7 @@ static BatchLayout batch_layout(const rqp_problem* p, int B, int ldv, bool with_
     l.off_cursor = take(size_t(p->n_rho) * 4);
     l.off_tile = take(size_t(l.n_tiles) * 4);
     l.off_btab = take(64 * 4);
+    l.off_done = take(size_t(l.cap / 32 + 1) * 4);      // window kernel: one completion counter per column tile
     l.off_nact = take(4);
     l.total = o;
     return l;
@@ -857,6 +858,8 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         return RQP_OK;
     };
     const bool pdl_ok = getenv("RQP_NO_PDL") == nullptr;
+    // one launch per check window (1-CTA tcgen05 kernels): 0 never, 1 when CTAs own several tiles, 2 always
+    const int tc_window = getenv("RQP_NO_WINDOW") ? 0 : (getenv("RQP_WINDOW") ? atoi(getenv("RQP_WINDOW")) : 1);
     // fp64: DMMA tensor-core GEMM (engine 1 forces the SIMT kernels)
     const bool use_dmma = std::is_same<T, double>::value && bt->engine != 1 && getenv("RQP_NO_DMMA") == nullptr;
     const int dmma_min = getenv("RQP_DMMA_MIN") ? atoi(getenv("RQP_DMMA_MIN")) : 1;
@@ -900,31 +903,43 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         return 0;
     };
     // pdl: this launch directly follows another 1-CTA tcgen05 iteration kernel of the same window
-    auto gemm_iter_tc = [&](int src, bool write_plain, bool pdl) -> int {
+    // One launch = `steps` iterations starting from buffer `src`.  steps > 1 is the window mode of the 1-CTA
+    // kernel (one cooperative launch per check window, per-column-tile dependencies inside the kernel);
+    // steps == 1 is one iteration, `pdl`: launched as a programmatic dependent of the previous iteration.
+    // The plain fp32 state is written by the last iteration of the launch when write_plain is set.
+    auto one_sm_engine = [&]() {
+        return bt->engine == 2 || bt->engine >= 4 || (bt->engine != 3 && nact_host[0] < pair_min);
+    };
+    auto gemm_iter_tc = [&](int src, int steps, bool write_plain, bool pdl) -> int {
         TcArgs a;
         a.tile_rho = c.tile_rho; a.btab = c.btab; a.orig = c.orig[lcur];
         a.b_all = reinterpret_cast<const float*>(c.b_all);
         a.bias_cols = with_g ? reinterpret_cast<const float*>(c.Bias[lcur]) : nullptr;
         a.L = reinterpret_cast<const float*>(c.L); a.U = reinterpret_cast<const float*>(c.U);
         a.Yh = reinterpret_cast<float*>(c.Vh[src ^ 1]); a.Yl = reinterpret_cast<float*>(c.Vl[src ^ 1]);
-        a.Yplain = write_plain ? reinterpret_cast<float*>(c.V[src ^ 1]) : nullptr;
+        a.Yh_alt = reinterpret_cast<float*>(c.Vh[src]); a.Yl_alt = reinterpret_cast<float*>(c.Vl[src]);
+        const int last_dst = (steps & 1) ? (src ^ 1) : src;
+        a.Yplain = write_plain ? reinterpret_cast<float*>(c.V[last_dst]) : nullptr;
         a.D = D; a.nx = nx; a.nc = nc; a.ldv = ldv;
         a.raw = 0; a.M = D; a.w_row0 = 0; a.chunk_kb = tc_chunk; a.chunk_rows = tc_chunk_x ? nx : 0;
         a.k_blocks = (D + 31) / 32;
+        a.steps = steps; a.done = nullptr;
         a.dbg = static_cast<unsigned long long*>(bt->reserved_dbg);
-        // auto: the CTA-pair kernel pays off once there are enough column tiles to fill the chip
-        // (measured crossover ~8k active columns at D = 960); below that the 1-CTA kernel has twice
-        // the parallelism per active column
-        const bool one_sm = bt->engine == 2 || bt->engine >= 4 || (bt->engine != 3 && nact_host[0] < pair_min);
-        if (one_sm) {
+        if (one_sm_engine()) {
             // 1-CTA tiles of 128 rows x BN columns.  BN is the widest tile that still gives every active
             // column tile its own SM in one wave (engine 4 / 5 / 6 force 128 / 64 / 32).
             a.n_row_tiles = (D + 127) / 128;
             const int b = pick_bn(a.n_row_tiles, bt->engine);
             a.n_col_tiles = 0;
             const int bound = nact_host[3 - b] * a.n_row_tiles;
-            return tc_launch(map_wh, map_wl, map_xh[b][src], map_xl[b][src], a, kBoxRows[b], bound, pdl, sm_count, st);
+            if (steps > 1) {
+                a.done = reinterpret_cast<unsigned int*>(w8 + lay.off_done);
+                RQP_CUDA_TRY(cudaMemsetAsync(a.done, 0, size_t(cap / 32 + 1) * 4, st));
+            }
+            return tc_launch(map_wh, map_wl, map_xh[b][src], map_xl[b][src], map_xh[b][src ^ 1], map_xl[b][src ^ 1], a,
+                             kBoxRows[b], bound, pdl, sm_count, st);
         }
+        if (steps != 1) return RQP_ERR_BAD_ARG;
         a.n_col_tiles = cap / 256; a.n_row_tiles = (D + 255) / 256;   // CTA-pair tiles: 256 x 256
         return tc2_launch(map_wh, map_wl, map_xh[0][src], map_xl[0][src], a, sm_count, st);
     };
@@ -952,12 +967,14 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.Yplain = reinterpret_cast<float*>(c.Tres);
         a.D = D; a.nx = nx; a.nc = nc; a.ldv = nc + 2 * nx;
         a.raw = 1; a.M = nc + 2 * nx; a.w_row0 = prob->n_rho * D; a.chunk_kb = tc_chunk; a.chunk_rows = 0;
+        a.steps = 1; a.done = nullptr; a.Yh_alt = nullptr; a.Yl_alt = nullptr;
         a.k_blocks = (D + 31) / 32;
         a.n_col_tiles = 0; a.n_row_tiles = (a.M + 127) / 128;
         a.dbg = nullptr;
         const int b = pick_bn(a.n_row_tiles, bt->engine);
         const int bound = nact_host[3 - b] * a.n_row_tiles;
-        return tc_launch(map_wh, map_wl, map_xh[b][src], map_xl[b][src], a, kBoxRows[b], bound, false, sm_count, st);
+        return tc_launch(map_wh, map_wl, map_xh[b][src], map_xl[b][src], map_xh[b][src], map_xl[b][src], a, kBoxRows[b],
+                         bound, false, sm_count, st);
     };
     auto gemm_res = [&](int src) {
         GemmArgs<T> a;
@@ -1004,16 +1021,28 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         if (k + steps > stng->max_iter) steps = stng->max_iter - k;
         const double tw0 = trace_windows ? now_us() : 0.0;
         const int nact_w = nact_host[0], t32_w = nact_host[1];
-        for (int s = 0; s < steps; ++s) {
-            if (use_tc) {
-                // last step of a window also writes the plain state; steps 2.. are programmatic
-                // dependents of the previous step (the pair kernel ignores the flag)
-                rc = gemm_iter_tc(cur, s == steps - 1, s > 0 && pdl_ok);
-                if (rc != RQP_OK) return rc;
-            } else {
-                gemm_iter(cur);
+        // Window mode pays when a CTA owns more than one tile (the epilogue of one overlaps the mainloop of
+        // the next across iterations: 1.47 -> 1.25 ms per window at 4096 columns); with one tile per CTA the
+        // chain mainloop -> epilogue -> next mainloop is serial either way and PDL launches are as fast.
+        const int n_rt128 = (D + 127) / 128;
+        const bool multi_tile = use_tc && nact_host[3 - pick_bn(n_rt128, bt->engine)] * n_rt128 > sm_count;
+        if (use_tc && steps > 1 && one_sm_engine() && (tc_window == 2 || (tc_window == 1 && multi_tile))) {
+            // the whole window in one cooperative launch
+            rc = gemm_iter_tc(cur, steps, true, false);
+            if (rc != RQP_OK) return rc;
+            cur ^= (steps & 1);
+        } else {
+            for (int s = 0; s < steps; ++s) {
+                if (use_tc) {
+                    // last step of a window also writes the plain state; steps 2.. are programmatic
+                    // dependents of the previous step (the pair kernel ignores the flag)
+                    rc = gemm_iter_tc(cur, 1, s == steps - 1, s > 0 && pdl_ok);
+                    if (rc != RQP_OK) return rc;
+                } else {
+                    gemm_iter(cur);
+                }
+                cur ^= 1;
             }
-            cur ^= 1;
         }
         k += steps;
         const double tw1 = trace_windows ? now_us() : 0.0;

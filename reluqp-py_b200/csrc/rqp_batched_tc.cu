@@ -145,6 +145,18 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Cross-CTA dataflow of the window kernel: a consumer's TMA (async proxy) reads what another CTA's
+// epilogue wrote with ordinary stores (generic proxy).
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add_u32(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -212,7 +224,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcArgs& a, const EpiRow&
     }
 }
 
-__device__ __forceinline__ EpiRow make_epi_row(const TcArgs& a, int m, int rho) {
+__device__ __forceinline__ EpiRow make_epi_row(const TcArgs& a, int m, int rho, float* yh, float* yl, float* yp) {
     EpiRow e;
     e.m_ok = m < a.D;
     e.is_z = e.m_ok && m >= a.nx && m < a.nx + a.nc;
@@ -221,9 +233,9 @@ __device__ __forceinline__ EpiRow make_epi_row(const TcArgs& a, int m, int rho) 
     e.Uz = a.U + mz;
     const int mc = e.m_ok ? m : 0;
     e.bcol = a.bias_cols ? a.bias_cols + mc : nullptr;
-    e.ph = a.Yh + mc;
-    e.pl = a.Yl + mc;
-    e.pp = a.Yplain ? a.Yplain + mc : nullptr;
+    e.ph = yh + mc;
+    e.pl = yl + mc;
+    e.pp = yp ? yp + mc : nullptr;
     e.bias_shared = (e.m_ok && a.bias_cols == nullptr) ? __ldg(a.b_all + size_t(rho) * a.D + m) : 0.f;
     return e;
 }
@@ -294,7 +306,17 @@ template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
                       const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                      const __grid_constant__ CUtensorMap map_xh1, const __grid_constant__ CUtensorMap map_xl1,
                       const TcArgs a) {
+    // Window mode (a.steps > 1, a.done != null): ONE launch runs all iterations of a check window.  Tiles
+    // keep their CTA from iteration to iteration; iteration i reads the state planes behind map_x{h,l}
+    // (i even) or map_x{h,l}1 (i odd) and writes the other pair.  The only dependency between iterations is
+    // per COLUMN tile: tile (ct, rt) of iteration i+1 needs the rows of all row tiles of column tile ct from
+    // iteration i (and may overwrite what they read only after they are done).  Each epilogue warp counts
+    // itself into done[ct] after its stores; a producer waits for the count of the previous iteration before
+    // it loads state planes.  Different column tiles drift freely, so the epilogue of one tile overlaps the
+    // mainloop of the CTA's next tile ACROSS iterations, and there is one launch per window instead of 25.
+    // All CTAs must be co-resident (cooperative launch, grid <= number of SMs).
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
@@ -343,47 +365,69 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             bool first = true;
-            long long w_empty = 0, t_all = clock64();
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                int rho, xrow, rt;
-                if (!tc_tile_lookup<BN>(sb, t, a.n_row_tiles, rho, xrow, rt)) break;
-                int wrow, kb_lo, kb_hi;
-                tc_tile_rows(a, rho, rt, wrow, kb_lo, kb_hi);
-                int kb0 = kb_lo;
-                if (first) {
-                    // W does not depend on the previous iteration: fill the ring with W planes first, then
-                    // wait for the previous kernel and add the state planes
-                    first = false;
-                    const int P = (kb_hi - kb_lo) < STAGES ? (kb_hi - kb_lo) : STAGES;
-                    for (int s = 0; s < P; ++s) {
-                        unsigned char* sp = base + size_t(s) * STAGE_BYTES;
-                        mbar_expect_tx(full + s, STAGE_BYTES);
-                        tma_load_2d(sp, &map_wh, (kb_lo + s) * TC_BK, wrow, full + s);
-                        tma_load_2d(sp + TC_TILE_BYTES, &map_wl, (kb_lo + s) * TC_BK, wrow, full + s);
+            long long w_empty = 0, w_dep = 0, t_all = clock64();
+            for (int it = 0; it < a.steps; ++it) {
+                const CUtensorMap* mxh = (it & 1) ? &map_xh1 : &map_xh;
+                const CUtensorMap* mxl = (it & 1) ? &map_xl1 : &map_xl;
+                for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                    int rho, xrow, rt;
+                    if (!tc_tile_lookup<BN>(sb, t, a.n_row_tiles, rho, xrow, rt)) break;
+                    int wrow, kb_lo, kb_hi;
+                    tc_tile_rows(a, rho, rt, wrow, kb_lo, kb_hi);
+                    // Is there something to wait for before this tile's state planes may be read: the previous
+                    // kernel (first tile of a PDL launch) or the previous iteration of this column tile (window
+                    // mode)?  Then W, which depends on neither, goes first: up to a ring-full of W planes is
+                    // issued before the wait, the state planes follow.  Otherwise k-blocks stream normally.
+                    const uint32_t need = uint32_t(it) * uint32_t(a.n_row_tiles) * Cfg::EPI_WARPS;
+                    const uint32_t* cnt = a.done != nullptr ? a.done + t / a.n_row_tiles : nullptr;
+                    const bool dep = cnt != nullptr && it > 0 && ld_acquire_u32(cnt) < need;
+                    int P = 0;
+                    if (first || dep) {
+                        P = (kb_hi - kb_lo) < STAGES ? (kb_hi - kb_lo) : STAGES;
+                        uint32_t st2 = stage, ph2 = phase;
+                        for (int s = 0; s < P; ++s) {
+                            const long long tw = clock64();
+                            mbar_wait(empty + st2, ph2 ^ 1u);
+                            w_empty += clock64() - tw;
+                            unsigned char* sp = base + size_t(st2) * STAGE_BYTES;
+                            mbar_expect_tx(full + st2, STAGE_BYTES);
+                            tma_load_2d(sp, &map_wh, (kb_lo + s) * TC_BK, wrow, full + st2);
+                            tma_load_2d(sp + TC_TILE_BYTES, &map_wl, (kb_lo + s) * TC_BK, wrow, full + st2);
+                            if (++st2 == STAGES) { st2 = 0; ph2 ^= 1u; }
+                        }
+                        if (first) { grid_dep_wait(); first = false; }
+                        if (dep) {
+                            const long long tw = clock64();
+                            uint32_t spins = 0;
+                            while (ld_acquire_u32(cnt) < need) {
+                                if (++spins > (1u << 24)) __trap();
+                            }
+                            w_dep += clock64() - tw;
+                        }
                     }
-                    grid_dep_wait();
+                    if (cnt != nullptr && it > 0) fence_proxy_async_all();   // acquire above -> TMA reads below
                     for (int s = 0; s < P; ++s) {
-                        unsigned char* sp = base + size_t(s) * STAGE_BYTES;
-                        tma_load_2d(sp + 2 * TC_TILE_BYTES, &map_xh, (kb_lo + s) * TC_BK, xrow, full + s);
-                        tma_load_2d(sp + 2 * TC_TILE_BYTES + XT, &map_xl, (kb_lo + s) * TC_BK, xrow, full + s);
+                        unsigned char* sp = base + size_t(stage) * STAGE_BYTES;
+                        tma_load_2d(sp + 2 * TC_TILE_BYTES, mxh, (kb_lo + s) * TC_BK, xrow, full + stage);
+                        tma_load_2d(sp + 2 * TC_TILE_BYTES + XT, mxl, (kb_lo + s) * TC_BK, xrow, full + stage);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
-                    if (P == STAGES) { stage = 0; phase = 1u; } else { stage = uint32_t(P); }
-                    kb0 = kb_lo + P;
-                }
-                for (int kb = kb0; kb < kb_hi; ++kb) {
-                    const long long tw = clock64();
-                    mbar_wait(empty + stage, phase ^ 1u);
-                    w_empty += clock64() - tw;
-                    unsigned char* sp = base + size_t(stage) * STAGE_BYTES;
-                    mbar_expect_tx(full + stage, STAGE_BYTES);
-                    tma_load_2d(sp, &map_wh, kb * TC_BK, wrow, full + stage);
-                    tma_load_2d(sp + TC_TILE_BYTES, &map_wl, kb * TC_BK, wrow, full + stage);
-                    tma_load_2d(sp + 2 * TC_TILE_BYTES, &map_xh, kb * TC_BK, xrow, full + stage);
-                    tma_load_2d(sp + 2 * TC_TILE_BYTES + XT, &map_xl, kb * TC_BK, xrow, full + stage);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    for (int kb = kb_lo + P; kb < kb_hi; ++kb) {
+                        const long long tw = clock64();
+                        mbar_wait(empty + stage, phase ^ 1u);
+                        w_empty += clock64() - tw;
+                        unsigned char* sp = base + size_t(stage) * STAGE_BYTES;
+                        mbar_expect_tx(full + stage, STAGE_BYTES);
+                        tma_load_2d(sp, &map_wh, kb * TC_BK, wrow, full + stage);
+                        tma_load_2d(sp + TC_TILE_BYTES, &map_wl, kb * TC_BK, wrow, full + stage);
+                        tma_load_2d(sp + 2 * TC_TILE_BYTES, mxh, kb * TC_BK, xrow, full + stage);
+                        tma_load_2d(sp + 2 * TC_TILE_BYTES + XT, mxl, kb * TC_BK, xrow, full + stage);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    }
                 }
             }
             if (first) grid_dep_wait();
+            if (a.dbg && blockIdx.x == 0) a.dbg[9] = w_dep;
             if (a.dbg && blockIdx.x == 0) { a.dbg[0] = w_empty; a.dbg[1] = clock64() - t_all; }
         }
     } else if (warp == 1) {
@@ -392,6 +436,7 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
         long long w_full = 0, w_acc = 0, t_all = clock64(), ntile = 0;
         grid_dep_wait();
+        for (int it = 0; it < a.steps; ++it)
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             int rho, col0, rt, wrow, kb_lo, kb_hi;
             if (!tc_tile_lookup<BN>(sb, t, a.n_row_tiles, rho, col0, rt)) break;
@@ -452,6 +497,7 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
         long long w_accf = 0, t_store = 0;
         grid_dep_wait();
         long long t_all = clock64();
+        for (int it = 0; it < a.steps; ++it)
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             int rho, col0, rt, wrow, kb_lo, kb_hi;
             if (!tc_tile_lookup<BN>(sb, t, a.n_row_tiles, rho, col0, rt)) break;
@@ -488,12 +534,22 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
             const long long ts0 = clock64();
             const int m = rt * TC_BM + quarter * 32 + lane;      // state row of this thread
             EpiRow e{};
-            if (!a.raw) e = make_epi_row(a, m, rho);
+            if (!a.raw)
+                e = make_epi_row(a, m, rho, (it & 1) ? a.Yh_alt : a.Yh, (it & 1) ? a.Yl_alt : a.Yl,
+                                 it == a.steps - 1 ? a.Yplain : nullptr);
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 const int n0 = col0 + half * Cfg::COLS_PER_EPI_WARP + c * 32;
                 if (a.raw) tc_epilogue_raw(a, m, sum[c], n0, lane);
                 else tc_epilogue_chunk(a, e, sum[c], n0, lane);
+            }
+            if (a.done != nullptr) {
+                // this warp's share of the tile is written: make it visible GPU-wide (to TMA readers too),
+                // then count the warp into the column tile's completion counter
+                __threadfence();
+                fence_proxy_async_all();
+                __syncwarp();
+                if (lane == 0) red_release_add_u32(a.done + t / a.n_row_tiles, 1u);
             }
             t_store += clock64() - ts0;
         }
@@ -672,7 +728,7 @@ rqp_batched_tc2_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_
             mbar_wait(acc_full + acc, acc_phase);
             tc_fence_after();
             const int m = rt * 256 + int(rank) * TC_BM + quarter * 32 + lane;
-            const EpiRow e = make_epi_row(a, m, rho);
+            const EpiRow e = make_epi_row(a, m, rho, a.Yh, a.Yl, a.Yplain);
             const uint32_t taddr = tmem_base + acc * TC2_BN + (uint32_t(quarter * 32) << 16);
             const int half = (warp - 2) >> 2;
 #pragma unroll 1
@@ -744,7 +800,8 @@ int tc2_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& 
 
 template <int BN>
 static int tc_launch_bn(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,
-                        const TcArgs& args, int grid, bool pdl, cudaStream_t st) {
+                        const CUtensorMap& xh1, const CUtensorMap& xl1, const TcArgs& args, int grid, bool pdl,
+                        cudaStream_t st) {
     static bool attr_set[kMaxDevices] = {};
     const int dev = current_device_slot();
     auto kern = rqp_batched_tc_kernel<BN>;
@@ -759,11 +816,18 @@ static int tc_launch_bn(const CUtensorMap& wh, const CUtensorMap& wl, const CUte
     cfg.dynamicSmemBytes = TcCfg<BN>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    RQP_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, wh, wl, xh, xl, args));
+    cfg.numAttrs = 0;
+    if (args.done != nullptr) {          // window mode: spin-waits between CTAs need co-residency
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.numAttrs = 1;
+    } else if (pdl) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.numAttrs = 1;
+    }
+    RQP_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, wh, wl, xh, xl, xh1, xl1, args));
     return RQP_OK;
 }
 
@@ -771,13 +835,14 @@ static int tc_launch_bn(const CUtensorMap& wh, const CUtensorMap& wl, const CUte
 // n_tiles_bound: upper bound on the number of tiles (the kernel derives the exact list from args.btab);
 // pdl: launch as a programmatic dependent of the previous kernel in the stream
 int tc_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,
-              const TcArgs& args, int bn, int n_tiles_bound, bool pdl, int sm_count, cudaStream_t st) {
+              const CUtensorMap& xh1, const CUtensorMap& xl1, const TcArgs& args, int bn, int n_tiles_bound, bool pdl,
+              int sm_count, cudaStream_t st) {
     int grid = n_tiles_bound < sm_count ? n_tiles_bound : sm_count;
     if (grid < 1) grid = 1;
     switch (bn) {
-        case 128: return tc_launch_bn<128>(wh, wl, xh, xl, args, grid, pdl, st);
-        case 64: return tc_launch_bn<64>(wh, wl, xh, xl, args, grid, pdl, st);
-        case 32: return tc_launch_bn<32>(wh, wl, xh, xl, args, grid, pdl, st);
+        case 128: return tc_launch_bn<128>(wh, wl, xh, xl, xh1, xl1, args, grid, pdl, st);
+        case 64: return tc_launch_bn<64>(wh, wl, xh, xl, xh1, xl1, args, grid, pdl, st);
+        case 32: return tc_launch_bn<32>(wh, wl, xh, xl, xh1, xl1, args, grid, pdl, st);
     }
     return RQP_ERR_BAD_ARG;
 }

@@ -15,7 +15,11 @@ struct TcArgs {
     const float* U;
     float* Yh;              // [cap][ldv]
     float* Yl;
-    float* Yplain;          // [cap][ldv] or null
+    float* Yplain;          // [cap][ldv] or null (window mode: written by the last iteration only)
+    float* Yh_alt;          // window mode: planes written by odd iterations (the buffer even iterations read)
+    float* Yl_alt;
+    unsigned int* done;     // window mode: per column tile completion counters (zeroed before the launch), else null
+    int steps;              // iterations in this launch (1 unless window mode)
     int D, nx, nc, ldv;
     int raw;                // 1: residual GEMM (rows of [A 0 0; H 0 0; 0 0 A'] at W-plane row w_row0), plain output
     int M;                  // output rows: D (iteration) or nc + 2 nx (residual)
@@ -30,7 +34,9 @@ struct TcArgs {
 int tc_make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows = 128);
 int tc2_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,
                const TcArgs& args, int sm_count, cudaStream_t st);
+// xh / xl: planes read by even iterations (the only ones unless window mode), xh1 / xl1: by odd iterations
 int tc_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,
-              const TcArgs& args, int bn, int n_tiles_bound, bool pdl, int sm_count, cudaStream_t st);
+              const CUtensorMap& xh1, const CUtensorMap& xl1, const TcArgs& args, int bn, int n_tiles_bound, bool pdl,
+              int sm_count, cudaStream_t st);
 
 }  // namespace rqp

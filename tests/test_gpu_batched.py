@@ -183,6 +183,33 @@ def test_tc_engine_matches_simt_for_fixed_iterations():
             assert torch.equal(vts[2], vts[eng]), (it, eng)
 
 
+def test_tc_window_kernel_is_bit_identical(monkeypatch):
+    """Window mode (one cooperative launch runs all iterations of a check window, column tiles synchronise
+    through completion counters, state planes written by one CTA are read by other CTAs' TMA) against one
+    launch per iteration: a stale or torn read anywhere would change bits.  Forced on for every window
+    (RQP_WINDOW=2) at batch sizes with one and with several tiles per CTA, all tile widths."""
+    plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+    L, U = plant.bounds(plant.sample_x0(2500))
+    prob = (plant.H, plant.g, plant.A, L[0], U[0])
+    mf = gpu_model(prob, precision=torch.float32, adaptive_rho=False, max_iter=60)     # windows of 25, 25, 10
+    ms = gpu_model(prob, precision=torch.float32)
+    for B in (90, 2500):
+        for eng in (0, 5, 6):
+            out = {}
+            for mode in ("2", "0"):
+                monkeypatch.setenv("RQP_WINDOW", mode)
+                if mode == "0":
+                    monkeypatch.setenv("RQP_NO_WINDOW", "1")
+                else:
+                    monkeypatch.delenv("RQP_NO_WINDOW", raising=False)
+                a = mf.solve_batch(L[:B], U[:B], engine=eng)
+                b = ms.solve_batch(L[:B], U[:B], engine=eng)
+                out[mode] = (torch.cat([a.x, a.z, a.lam], 1).clone(), b.iter.clone(), b.x.clone(), b.pri_res.clone())
+            assert torch.equal(out["2"][0], out["0"][0]), (B, eng)
+            assert torch.equal(out["2"][1], out["0"][1]) and torch.equal(out["2"][2], out["0"][2]), (B, eng)
+            assert torch.equal(out["2"][3], out["0"][3]), (B, eng)
+
+
 def test_tc_engine_max_iter_fall_through_and_reported_residuals():
     """tcgen05 engine at the max_iter fall-through (reluqpth.py:243), on and off a check boundary: same
     status / iteration count as the SIMT fp32 engine, state within fp32 accuracy, and the reported

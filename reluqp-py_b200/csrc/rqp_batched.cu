@@ -30,6 +30,7 @@
 
 namespace rqp {
 
+constexpr int kMaxSplitItems = 192;   // >= number of SMs: split-K work items (tile, rank) never exceed one per SM
 constexpr int BALIGN = 256;  // bucket alignment in slots = widest GEMM column tile (cta_group::2 pair tile)
 
 template <typename T>
@@ -723,7 +724,7 @@ struct PinnedRecord {
 struct BatchLayout {
     int cap, n_tiles;
     size_t off_V[2], off_Vh[2], off_Vl[2], off_Bias[2], off_orig[2], off_ri[2], off_rhoc[2], off_T, off_key, off_pri, off_dua,
-        off_counts, off_starts, off_cursor, off_tile, off_btab, off_done, off_nact, total;
+        off_counts, off_starts, off_cursor, off_tile, off_btab, off_done, off_kcnt, off_scratch, off_nact, total;
 };
 
 static BatchLayout batch_layout(const rqp_problem* p, int B, int ldv, bool with_g) {
@@ -752,6 +753,9 @@ static BatchLayout batch_layout(const rqp_problem* p, int B, int ldv, bool with_
     l.off_tile = take(size_t(l.n_tiles) * 4);
     l.off_btab = take(64 * 4);
     l.off_done = take(size_t(l.cap / 32 + 1) * 4);      // window kernel: one completion counter per column tile
+    // split-K of the tcgen05 kernels (fewer tiles than SMs): one work item per SM at most
+    l.off_kcnt = take(planes ? size_t(kMaxSplitItems) * 8 * 4 : 0);
+    l.off_scratch = take(planes ? size_t(kMaxSplitItems) * 128 * 128 * 4 : 0);
     l.off_nact = take(4);
     l.total = o;
     return l;
@@ -858,6 +862,8 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         return RQP_OK;
     };
     const bool pdl_ok = getenv("RQP_NO_PDL") == nullptr;
+    const bool tc_ksplit_ok = getenv("RQP_NO_KSPLIT") == nullptr;
+    const int tc_ksplit_max = getenv("RQP_KSPLIT_MAX") ? atoi(getenv("RQP_KSPLIT_MAX")) : 8;
     // one launch per check window (1-CTA tcgen05 kernels): 0 never, 1 when CTAs own several tiles, 2 always
     const int tc_window = getenv("RQP_NO_WINDOW") ? 0 : (getenv("RQP_WINDOW") ? atoi(getenv("RQP_WINDOW")) : 1);
     // fp64: DMMA tensor-core GEMM (engine 1 forces the SIMT kernels)
@@ -884,12 +890,15 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     static const int kBoxRows[3] = {128, 64, 32};
     if (use_tc) {
         const long long w_rows = (long long)prob->n_rho * D + (res_tc ? nc + 2 * nx : 0);
-        int rc0 = tc_make_map(&map_wh, bt->W_hi, w_rows, c.ldw, c.ldw);
-        if (rc0 == RQP_OK) rc0 = tc_make_map(&map_wl, bt->W_lo, w_rows, c.ldw, c.ldw);
+        // The maps' inner extent is D, not the padded leading dimension: elements D..ld-1 of a row are padding
+        // (never written in the state planes: stale memory there could be NaN, and 0 * NaN poisons a whole
+        // column) and must read as TMA out-of-bounds zeros.
+        int rc0 = tc_make_map(&map_wh, bt->W_hi, w_rows, D, c.ldw);
+        if (rc0 == RQP_OK) rc0 = tc_make_map(&map_wl, bt->W_lo, w_rows, D, c.ldw);
         for (int b = 0; b < 3 && rc0 == RQP_OK; ++b)
             for (int i = 0; i < 2 && rc0 == RQP_OK; ++i) {
-                rc0 = tc_make_map(&map_xh[b][i], c.Vh[i], cap, ldv, ldv, kBoxRows[b]);
-                if (rc0 == RQP_OK) rc0 = tc_make_map(&map_xl[b][i], c.Vl[i], cap, ldv, ldv, kBoxRows[b]);
+                rc0 = tc_make_map(&map_xh[b][i], c.Vh[i], cap, D, ldv, kBoxRows[b]);
+                if (rc0 == RQP_OK) rc0 = tc_make_map(&map_xl[b][i], c.Vl[i], cap, D, ldv, kBoxRows[b]);
             }
         if (rc0 != RQP_OK) return rc0;
     }
@@ -909,6 +918,27 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     // The plain fp32 state is written by the last iteration of the launch when write_plain is set.
     auto one_sm_engine = [&]() {
         return bt->engine == 2 || bt->engine >= 4 || (bt->engine != 3 && nact_host[0] < pair_min);
+    };
+    // split-K: with fewer tiles than SMs, `ks` CTAs share a tile's k-blocks (largest of 8 / 4 / 2 that still
+    // gives every work item its own SM); the per-tile latency -- 360 MMAs at ~66 cycles whatever the tile
+    // width -- drops accordingly.  Changes the summation order (partials are added in rank order), so the
+    // last bits differ from the unsplit kernels.
+    // nk_min: fewest k-blocks any row tile of the launch has (every rank must get at least one)
+    auto pick_ksplit = [&](int tiles, int nk_min) -> int {
+        if (!tc_ksplit_ok || tiles < 1) return 1;
+        const int lim = sm_count < kMaxSplitItems ? sm_count : kMaxSplitItems;
+        for (int ks = tc_ksplit_max; ks >= 2; ks >>= 1)
+            if (tiles * ks <= lim && ks <= nk_min) return ks;
+        return 1;
+    };
+    const int nk_iter = (D + 31) / 32;
+    const int nk_raw = ((nx < nc ? nx : nc) + 31) / 32;      // a residual row tile reads the x or the lambda columns
+    auto set_ksplit = [&](TcArgs& a, int tiles) -> int {
+        a.ksplit = pick_ksplit(tiles, a.raw ? nk_raw : nk_iter);
+        a.scratch = reinterpret_cast<float*>(w8 + lay.off_scratch);
+        a.kcnt = reinterpret_cast<unsigned int*>(w8 + lay.off_kcnt);
+        if (a.ksplit > 1) RQP_CUDA_TRY(cudaMemsetAsync(a.kcnt, 0, size_t(kMaxSplitItems) * 8 * 4, st));
+        return RQP_OK;
     };
     auto gemm_iter_tc = [&](int src, int steps, bool write_plain, bool pdl) -> int {
         TcArgs a;
@@ -931,7 +961,9 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
             a.n_row_tiles = (D + 127) / 128;
             const int b = pick_bn(a.n_row_tiles, bt->engine);
             a.n_col_tiles = 0;
-            const int bound = nact_host[3 - b] * a.n_row_tiles;
+            int rc1 = set_ksplit(a, nact_host[3 - b] * a.n_row_tiles);
+            if (rc1 != RQP_OK) return rc1;
+            const int bound = nact_host[3 - b] * a.n_row_tiles * a.ksplit;
             if (steps > 1) {
                 a.done = reinterpret_cast<unsigned int*>(w8 + lay.off_done);
                 RQP_CUDA_TRY(cudaMemsetAsync(a.done, 0, size_t(cap / 32 + 1) * 4, st));
@@ -940,6 +972,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
                              kBoxRows[b], bound, pdl, sm_count, st);
         }
         if (steps != 1) return RQP_ERR_BAD_ARG;
+        a.ksplit = 1; a.scratch = nullptr; a.kcnt = nullptr;
         a.n_col_tiles = cap / 256; a.n_row_tiles = (D + 255) / 256;   // CTA-pair tiles: 256 x 256
         return tc2_launch(map_wh, map_wl, map_xh[0][src], map_xl[0][src], a, sm_count, st);
     };
@@ -972,7 +1005,9 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.n_col_tiles = 0; a.n_row_tiles = (a.M + 127) / 128;
         a.dbg = nullptr;
         const int b = pick_bn(a.n_row_tiles, bt->engine);
-        const int bound = nact_host[3 - b] * a.n_row_tiles;
+        int rc1 = set_ksplit(a, nact_host[3 - b] * a.n_row_tiles);
+        if (rc1 != RQP_OK) return rc1;
+        const int bound = nact_host[3 - b] * a.n_row_tiles * a.ksplit;
         return tc_launch(map_wh, map_wl, map_xh[b][src], map_xl[b][src], map_xh[b][src], map_xl[b][src], a, kBoxRows[b],
                          bound, false, sm_count, st);
     };
@@ -1022,11 +1057,14 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         const double tw0 = trace_windows ? now_us() : 0.0;
         const int nact_w = nact_host[0], t32_w = nact_host[1];
         // Window mode pays when a CTA owns more than one tile (the epilogue of one overlaps the mainloop of
-        // the next across iterations: 1.47 -> 1.25 ms per window at 4096 columns); with one tile per CTA the
-        // chain mainloop -> epilogue -> next mainloop is serial either way and PDL launches are as fast.
+        // the next across iterations: 1.47 -> 1.25 ms per window at 4096 columns) and when tiles are split
+        // over K (short mainloops: the relaunch cost of one kernel per iteration would dominate; B = 32:
+        // 5.1 -> 3.2 ms per solve).  With one unsplit tile per CTA the chain mainloop -> epilogue -> next
+        // mainloop is serial either way and PDL launches are as fast.
         const int n_rt128 = (D + 127) / 128;
-        const bool multi_tile = use_tc && nact_host[3 - pick_bn(n_rt128, bt->engine)] * n_rt128 > sm_count;
-        if (use_tc && steps > 1 && one_sm_engine() && (tc_window == 2 || (tc_window == 1 && multi_tile))) {
+        const int tiles_w = use_tc ? nact_host[3 - pick_bn(n_rt128, bt->engine)] * n_rt128 : 0;
+        const bool window_pays = use_tc && (tiles_w > sm_count || pick_ksplit(tiles_w, nk_iter) > 1);
+        if (use_tc && steps > 1 && one_sm_engine() && (tc_window == 2 || (tc_window == 1 && window_pays))) {
             // the whole window in one cooperative launch
             rc = gemm_iter_tc(cur, steps, true, false);
             if (rc != RQP_OK) return rc;

@@ -302,6 +302,25 @@ __device__ __forceinline__ int tc_tile_count(const int* sb, int n_row_tiles) {
     return n * n_row_tiles;
 }
 
+// Work item u = tile * ksplit + rank: rank r of a tile accumulates the r-th slice of the tile's k-blocks
+// (split-K over independent CTAs when there are fewer tiles than SMs; the partial sums meet in a global
+// scratch buffer, see the epilogue).  Returns false past the last item.
+template <int BN>
+__device__ __forceinline__ bool tc_item(const int* sb, const TcArgs& a, int u, int& t, int& rank, int& rho, int& col0,
+                                        int& rt, int& wrow, int& kb_lo, int& kb_hi) {
+    const int ks = a.ksplit;
+    t = u / ks;
+    rank = u - t * ks;
+    if (!tc_tile_lookup<BN>(sb, t, a.n_row_tiles, rho, col0, rt)) return false;
+    tc_tile_rows(a, rho, rt, wrow, kb_lo, kb_hi);
+    if (ks > 1) {                                  // balanced slices; empty only if there are fewer k-blocks than ranks
+        const int nk = kb_hi - kb_lo, lo = kb_lo;
+        kb_lo = lo + (nk * rank) / ks;
+        kb_hi = lo + (nk * (rank + 1)) / ks;
+    }
+    return true;
+}
+
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
@@ -358,7 +377,7 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
     tc_fence_after();
     grid_dep_launch();       // let the next iteration's kernel start its prologue / W prefetch
     const uint32_t tmem_base = *tmem_slot;
-    const int n_tiles = tc_tile_count<BN>(sb, a.n_row_tiles);
+    const int n_items = tc_tile_count<BN>(sb, a.n_row_tiles) * a.ksplit;
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -369,11 +388,9 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
             for (int it = 0; it < a.steps; ++it) {
                 const CUtensorMap* mxh = (it & 1) ? &map_xh1 : &map_xh;
                 const CUtensorMap* mxl = (it & 1) ? &map_xl1 : &map_xl;
-                for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                    int rho, xrow, rt;
-                    if (!tc_tile_lookup<BN>(sb, t, a.n_row_tiles, rho, xrow, rt)) break;
-                    int wrow, kb_lo, kb_hi;
-                    tc_tile_rows(a, rho, rt, wrow, kb_lo, kb_hi);
+                for (int u = blockIdx.x; u < n_items; u += gridDim.x) {
+                    int t, rank, rho, xrow, rt, wrow, kb_lo, kb_hi;
+                    if (!tc_item<BN>(sb, a, u, t, rank, rho, xrow, rt, wrow, kb_lo, kb_hi)) break;
                     // Is there something to wait for before this tile's state planes may be read: the previous
                     // kernel (first tile of a PDL launch) or the previous iteration of this column tile (window
                     // mode)?  Then W, which depends on neither, goes first: up to a ring-full of W planes is
@@ -437,10 +454,9 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
         long long w_full = 0, w_acc = 0, t_all = clock64(), ntile = 0;
         grid_dep_wait();
         for (int it = 0; it < a.steps; ++it)
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            int rho, col0, rt, wrow, kb_lo, kb_hi;
-            if (!tc_tile_lookup<BN>(sb, t, a.n_row_tiles, rho, col0, rt)) break;
-            tc_tile_rows(a, rho, rt, wrow, kb_lo, kb_hi);
+        for (int u = blockIdx.x; u < n_items; u += gridDim.x) {
+            int t, rank, rho, col0, rt, wrow, kb_lo, kb_hi;
+            if (!tc_item<BN>(sb, a, u, t, rank, rho, col0, rt, wrow, kb_lo, kb_hi)) break;
             ntile++;
             const int nk = kb_hi - kb_lo;
             const int chunk = (a.chunk_kb > 0 && a.chunk_kb < nk && (a.chunk_rows <= 0 || rt * TC_BM < a.chunk_rows))
@@ -498,15 +514,29 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
         grid_dep_wait();
         long long t_all = clock64();
         for (int it = 0; it < a.steps; ++it)
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            int rho, col0, rt, wrow, kb_lo, kb_hi;
-            if (!tc_tile_lookup<BN>(sb, t, a.n_row_tiles, rho, col0, rt)) break;
-            tc_tile_rows(a, rho, rt, wrow, kb_lo, kb_hi);
+        for (int u = blockIdx.x; u < n_items; u += gridDim.x) {
+            int t, rank, rho, col0, rt, wrow, kb_lo, kb_hi;
+            if (!tc_item<BN>(sb, a, u, t, rank, rho, col0, rt, wrow, kb_lo, kb_hi)) break;
             const int nk = kb_hi - kb_lo;
             const int chunk = (a.chunk_kb > 0 && a.chunk_kb < nk && (a.chunk_rows <= 0 || rt * TC_BM < a.chunk_rows))
-                                  ? a.chunk_kb : nk;
+                                  ? a.chunk_kb : (nk > 0 ? nk : 1);
             const int nchunks = (nk + chunk - 1) / chunk;
             uint32_t sum[NCH][32];
+            if (nchunks == 0) {
+                // empty K slice (the host avoids it; kept correct): contributes zeros, but must not run ahead
+                // of the iteration order the other ranks get from their operand dependency
+                if (a.done != nullptr && it > 0) {
+                    const uint32_t need = uint32_t(it) * uint32_t(a.n_row_tiles) * Cfg::EPI_WARPS;
+                    uint32_t spins = 0;
+                    while (ld_acquire_u32(a.done + t / a.n_row_tiles) < need) {
+                        if (++spins > (1u << 24)) __trap();
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sum[c][j] = 0u;
+            }
             for (int ch = 0; ch < nchunks; ++ch) {
                 const long long tw = clock64();
                 mbar_wait(acc_full + acc, acc_phase);
@@ -532,6 +562,36 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                 if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
             }
             const long long ts0 = clock64();
+            if (a.ksplit > 1) {
+                // Split-K: every rank parks its partial sums of this warp's sub-block (32 rows x CPW columns)
+                // in the scratch buffer; the rank that arrives LAST at the sub-block's counter adds all
+                // partials in rank order (so the result does not depend on who is last) and runs the
+                // epilogue.  Counters only ever grow by ksplit per sub-block and iteration.
+                constexpr int SUB = Cfg::COLS_PER_EPI_WARP * 32;
+                const int w = warp - 2;
+                float* mine = a.scratch + ((size_t(t) * a.ksplit + rank) * Cfg::EPI_WARPS + w) * SUB + lane;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) __stcg(mine + (c * 32 + j) * 32, __uint_as_float(sum[c][j]));
+                __threadfence();
+                __syncwarp();
+                uint32_t old = 0;
+                if (lane == 0) old = atomicAdd(a.kcnt + size_t(t) * Cfg::EPI_WARPS + w, 1u);
+                old = __shfl_sync(0xffffffffu, old, 0);
+                if ((old % uint32_t(a.ksplit)) != uint32_t(a.ksplit - 1)) continue;   // a later rank finishes it
+                __threadfence();
+                for (int r = 0; r < a.ksplit; ++r) {
+                    const float* part = a.scratch + ((size_t(t) * a.ksplit + r) * Cfg::EPI_WARPS + w) * SUB + lane;
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float v = __ldcg(part + (c * 32 + j) * 32);
+                            sum[c][j] = __float_as_uint(r == 0 ? v : __uint_as_float(sum[c][j]) + v);
+                        }
+                }
+            }
             const int m = rt * TC_BM + quarter * 32 + lane;      // state row of this thread
             EpiRow e{};
             if (!a.raw)

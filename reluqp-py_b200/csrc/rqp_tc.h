@@ -20,6 +20,9 @@ struct TcArgs {
     float* Yl_alt;
     unsigned int* done;     // window mode: per column tile completion counters (zeroed before the launch), else null
     int steps;              // iterations in this launch (1 unless window mode)
+    int ksplit;             // ranks per tile (split-K over independent CTAs), 1 = off
+    float* scratch;         // ksplit > 1: [tiles][ksplit][128 x BN] partial sums
+    unsigned int* kcnt;     // ksplit > 1: [tiles][epilogue warps] arrival counters (multiples of ksplit between launches)
     int D, nx, nc, ldv;
     int raw;                // 1: residual GEMM (rows of [A 0 0; H 0 0; 0 0 A'] at W-plane row w_row0), plain output
     int M;                  // output rows: D (iteration) or nc + 2 nx (residual)

@@ -7,6 +7,7 @@ multi-GPU is plain data parallelism: each rank owns a contiguous block of column
 of the W set; there is no per-iteration collective, only one final gather of per-column results.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -78,6 +79,9 @@ class BatchEngine(object):
                                                               C.byref(sz)), "rqp_batch_workspace_size")
             self.ws = torch.empty(sz.value, dtype=torch.uint8, device=self.device)
             self.ws_B = B
+        poison = os.environ.get("RQP_POISON_WS")
+        if poison is not None:           # debugging aid: every solve starts from a workspace full of this byte
+            self.ws.fill_(int(poison))
         return self.ws
 
     def solve(self, l, u, g=None, engine=0):
@@ -101,7 +105,7 @@ class BatchEngine(object):
         ldv = (D + 3) // 4 * 4
         V = torch.zeros((B, ldv), dtype=dt, device=dev)
         rho_ind0 = int(np.argmin(np.abs(np.asarray(sv.layers.rho_list) - sv.settings.rho)))
-        small = 40 if dt == torch.float64 else 24
+        small = 40 if dt == torch.float64 else 16
         if engine == 0 and G is None and B <= small:
             return self._solve_small(L, U, V, rho_ind0, nx, nc, D)
         ws = self._workspace(B)

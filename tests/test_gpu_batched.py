@@ -150,10 +150,13 @@ def _fp32_setup():
     return plant, L, U
 
 
-def test_tc_engine_matches_simt_for_fixed_iterations():
+def test_tc_engine_matches_simt_for_fixed_iterations(monkeypatch):
     """The tcgen05 3xTF32 GEMM against the SIMT fp32 and fp64 engines after a FIXED number of
     iterations (no checks): same map applied the same number of times, so differences are pure
-    arithmetic.  1 iteration must be exact (v0 = 0 -> v1 = clamp(b)); later ones fp32-grade."""
+    arithmetic.  1 iteration must be exact (v0 = 0 -> v1 = clamp(b)); later ones fp32-grade.
+    Split-K is off here (it changes the summation order; it has its own test) so that the tile widths
+    can be compared bit for bit."""
+    monkeypatch.setenv("RQP_NO_KSPLIT", "1")
     plant, L, U = _fp32_setup()
     prob = (plant.H, plant.g, plant.A, L[0], U[0])
     for it, tol in ((1, 0.0), (2, 1e-6), (5, 1e-3), (30, 1e-3)):
@@ -188,6 +191,7 @@ def test_tc_window_kernel_is_bit_identical(monkeypatch):
     through completion counters, state planes written by one CTA are read by other CTAs' TMA) against one
     launch per iteration: a stale or torn read anywhere would change bits.  Forced on for every window
     (RQP_WINDOW=2) at batch sizes with one and with several tiles per CTA, all tile widths."""
+    monkeypatch.setenv("RQP_NO_KSPLIT", "1")
     plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
     L, U = plant.bounds(plant.sample_x0(2500))
     prob = (plant.H, plant.g, plant.A, L[0], U[0])
@@ -208,6 +212,46 @@ def test_tc_window_kernel_is_bit_identical(monkeypatch):
             assert torch.equal(out["2"][0], out["0"][0]), (B, eng)
             assert torch.equal(out["2"][1], out["0"][1]) and torch.equal(out["2"][2], out["0"][2]), (B, eng)
             assert torch.equal(out["2"][3], out["0"][3]), (B, eng)
+
+
+def test_tc_split_k(monkeypatch):
+    """Split-K of the tcgen05 kernels (fewer tiles than SMs: 2 / 4 / 8 CTAs share a tile's k-blocks, partial
+    sums meet in a scratch buffer and are added in rank order by whichever rank arrives last): run-to-run
+    reproducible, fp32-grade agreement with the unsplit kernels after a fixed number of iterations, same
+    results with and without window mode, and full solves that reach the thresholds."""
+    plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+    L, U = plant.bounds(plant.sample_x0(300))
+    prob = (plant.H, plant.g, plant.A, L[0], U[0])
+    mf = gpu_model(prob, precision=torch.float32, adaptive_rho=False, max_iter=30)
+    ms = gpu_model(prob, precision=torch.float32)
+    H, g, A = (torch.as_tensor(t, dtype=torch.float64, device="cuda") for t in (plant.H, plant.g, plant.A))
+    for B in (5, 40, 300):
+        monkeypatch.setenv("RQP_NO_KSPLIT", "1")
+        a = mf.solve_batch(L[:B], U[:B], engine=2)
+        va = torch.cat([a.x, a.z, a.lam], 1)
+        monkeypatch.delenv("RQP_NO_KSPLIT")
+        for ksmax in ("2", "8"):
+            monkeypatch.setenv("RQP_KSPLIT_MAX", ksmax)
+            outs = []
+            for win in ("2", "0", "2"):
+                monkeypatch.setenv("RQP_WINDOW", win)
+                if win == "0":
+                    monkeypatch.setenv("RQP_NO_WINDOW", "1")
+                else:
+                    monkeypatch.delenv("RQP_NO_WINDOW", raising=False)
+                b = mf.solve_batch(L[:B], U[:B], engine=2)
+                outs.append(torch.cat([b.x, b.z, b.lam], 1).clone())
+            assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), (B, ksmax)   # window == PDL, reproducible
+            assert not torch.isnan(outs[0]).any()
+            assert float((outs[0] - va).abs().max()) <= 1e-3 * float(va.abs().max()), (B, ksmax)
+        monkeypatch.delenv("RQP_KSPLIT_MAX")
+        monkeypatch.delenv("RQP_WINDOW")
+        monkeypatch.delenv("RQP_NO_WINDOW", raising=False)
+        r = ms.solve_batch(L[:B], U[:B])
+        assert r.status == ["solved"] * B
+        x, z, lam = r.x.double(), r.z.double(), r.lam.double()
+        assert float((x @ A.T - z).abs().amax(1).max()) < 1e-3 * np.sqrt(320) * 1.05
+        assert float((x @ H.T + lam @ A + g).abs().amax(1).max()) < 1e-3 * np.sqrt(320) * 1.05
 
 
 def test_tc_engine_max_iter_fall_through_and_reported_residuals():
@@ -248,8 +292,10 @@ def test_tc_engine_max_iter_fall_through_and_reported_residuals():
             assert torch.allclose(rt.dua_res.double(), dua, rtol=1e-3, atol=1e-4), (max_iter, eng)
 
 
-def test_tc_engine_odd_sizes_and_per_column_g(capsys):
-    """tcgen05 engine away from the MPC shape: D = 58 and D = 171 (not multiples of the 32-element k-block or
+def test_tc_engine_odd_sizes_and_per_column_g(capsys, monkeypatch):
+    """(Runs with the workspace pre-filled with 0xFF bytes = NaN, RQP_POISON_WS: the padding element of a
+    state-plane row -- D = 171 in a leading dimension of 172 -- is never written and must never be read.)
+    tcgen05 engine away from the MPC shape: D = 58 and D = 171 (not multiples of the 32-element k-block or
     of the 128-row tile: TMA zero fill, partial row tiles, short K ranges for the residual operator) with a
     per-column g (bias recomputed per column and rho bucket, generic epilogue) and 70 / 300 columns.
     Asserted: every column solved like fp64; the reported residuals equal an fp64 evaluation of the returned
@@ -257,6 +303,7 @@ def test_tc_engine_odd_sizes_and_per_column_g(capsys):
     allows.  Iteration counts are REPORTED: on this dense random family the fp32 engines sit on
     their rounding floor (fp64 ~52, fp32 FMA ~68, 3xTF32 ~96 iterations for nx=30: two TF32 planes carry
     ~23 bits of W and of the state, one less than fp32)."""
+    monkeypatch.setenv("RQP_POISON_WS", "255")
     for (nx, ne, ni, B, seed) in ((30, 7, 7, 70, 4), (85, 20, 23, 300, 6)):
         H, g, A, l, u, _ = utils.rand_qp(nx, ne, ni, seed=seed, compute_sol=False)
         Gs, Ls, Us = [], [], []

@@ -105,7 +105,7 @@ class BatchEngine(object):
         ldv = (D + 3) // 4 * 4
         V = torch.zeros((B, ldv), dtype=dt, device=dev)
         rho_ind0 = int(np.argmin(np.abs(np.asarray(sv.layers.rho_list) - sv.settings.rho)))
-        small = 40 if dt == torch.float64 else 16
+        small = 40 if dt == torch.float64 else 12
         if engine == 0 and G is None and B <= small:
             return self._solve_small(L, U, V, rho_ind0, nx, nc, D)
         ws = self._workspace(B)

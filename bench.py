@@ -343,6 +343,8 @@ def run_single(args, rank, world, dev):
     tuning = {k: v for k, v in dict(grid=args.grid, block=args.block, w_residency=args.w_residency,
                                            poll_backoff_ns=args.backoff, prepoll_cycles=args.prepoll,
                                            exchange_flags=args.exch_flags).items() if v}
+    # the first setup of a process also initialises cuSOLVER / cuBLAS: report the second one
+    reluqpth.ReLU_QP().setup(*wl["problem"], device=dev, precision=wl["dtype"], warm_starting=False, **wl["kw"])
     m = reluqpth.ReLU_QP()
     m.setup(*wl["problem"], device=dev, precision=wl["dtype"], warm_starting=False, **wl["kw"], **tuning)
     nx, nc = m.QP.nx, m.QP.nc

@@ -81,7 +81,7 @@ def run_batched(args, rank, world, dev):
         peak, peak_note = peaks["bf16_tflops_sustained"] / 2.0, \
             "TF32 dense = half of the measured sustained bf16 cuBLAS rate; 3xTF32 executes 3x the algorithmic flops"
     else:
-        peak, peak_note = 37.1, ("fp64 DMMA rate measured on a B200 of this pool with tools/scratch/ubench/fp64_rate.cu "
+        peak, peak_note = 37.1, ("fp64 DMMA rate measured on a B200 of this pool with tools/ubench/fp64_rate.cu "
                                  "(no fp64 figure in MEASURED_PEAKS.json)")
     iters = res.iter.float()
     line = dict(

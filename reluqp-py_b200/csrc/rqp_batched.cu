@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(256, 1) bgemm_simt(GemmArgs<T> a) {
 // fp64 tensor-core GEMM (mma.sync.m8n8k4.f64, SASS DMMA): same contract as bgemm_simt<double>.
 // tcgen05 has no fp64 kind, so this is the tensor path of the reference dtype.  On this B200 a register-
 // tiled DFMA loop tops out at ~26 TFLOP/s (operand-register bandwidth) and DMMA at ~31.6 of the nominal 37
-// (tools/scratch/ubench): DMMA needs one A and one B register per 512 flops.
+// (tools/ubench): DMMA needs one A and one B register per 512 flops.
 // CTA tile 128 (rows of Mat) x 128 (columns), K step 16, 256 threads = 8 warps as 4 (m) x 2 (n), warp tile
 // 32 x 64 = 4 x 8 DMMA tiles (64 accumulator doubles per thread).  Both operands are K-major in global
 // memory (W rows, state columns), so tiles go global -> shared with 16-byte cp.async through a 4-stage ring,

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-end style run: default bench (contract line), reference arm, then ncu launch list + one full capture
-cd "$(dirname "$0")/../.."
+cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 400 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"
 timeout 200 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "ref rc=$?"

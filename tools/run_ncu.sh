@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/../.."
+cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 CMD2="python bench.py --workload mpc_batched --steps 1 --warmup 1 --no-cpu-baseline --no-extras"
 timeout 200 $CMD2 > gpurun_out/plain2.log 2>&1; echo "plain2 rc=$?"

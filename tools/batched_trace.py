@@ -1,5 +1,5 @@
 import os, sys
-REPO = "/root/repo"
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(REPO, "reluqp-py_b200"), REPO]
 import numpy as np, torch
 from reluqp import reluqpth

@@ -190,6 +190,14 @@ typedef struct rqp_batch {
     const void* W_hi;           /* fp32 only: TF32 planes of W, [n_rho * D (+ nc + 2 nx)][ldw]:        */
     const void* W_lo;           /* W_hi = rna_tf32(W), W_lo = rna_tf32(W - W_hi)                      */
     void* reserved_dbg;         /* NULL, or 16 x uint64 device counters (tcgen05 engine diagnostics) */
+    /* Optional sparsity map of the layer matrices (NULL = treat every block as dense): uint64
+     * kmask[n_rho][ceil(D/64)], bit kb of entry (rho, t) set when rows [64 t, 64 t + 64) x columns
+     * [32 kb, 32 kb + 32) of W_rho hold a nonzero.  Only for D <= 2048 (64 column blocks).  The lambda
+     * rows of W_rho are [R A, -R, I] (reluqpth.py:75): their z and lambda column blocks are zero off the
+     * diagonal, and the GEMM engines skip blocks whose bit is clear (exact: they only add zeros).
+     * kmask_min_blocks = the fewest set bits any 128-row tile (two consecutive entries OR-ed) has. */
+    const void* kmask;
+    int32_t kmask_min_blocks;
 } rqp_batch;
 
 int rqp_batch_workspace_size(const rqp_problem* prob, const rqp_settings* stng, int32_t B,

@@ -239,6 +239,9 @@ struct GemmArgs {
     const T* U;
     const int* orig;
     int nx, nc, D;
+    // EPI_ITER, DMMA engine: sparsity map of the layer matrices (rqp_batch.kmask) or null
+    const unsigned long long* kmask;
+    int n_rt64;
 };
 
 template <typename T, int EPI>
@@ -385,7 +388,27 @@ __global__ void __launch_bounds__(32 * WM * WN * KS, 1) bgemm_dmma(GemmArgs<doub
     const int wm = wt % WM, wn = wt / WM;                // warp tile origin: rows 32 wm, columns 64 wn
     const int fr = lane >> 2, fk = lane & 3;             // fragment row / k of this lane
 
-    const int n_k = (a.K + DK - 1) / DK;
+    // K stages (16 columns each) this tile runs over: all of them, or -- with a sparsity map -- only those
+    // inside a 32-column block of W_rho that holds a nonzero for these rows (skipped stages would only add
+    // exact zeros: the lambda rows [R A, -R, I] are mostly zero blocks)
+    __shared__ unsigned char klist[128];
+    __shared__ int klist_n;
+    int n_k = (a.K + DK - 1) / DK;
+    const bool masked = EPI == EPI_ITER && a.kmask != nullptr && n_k <= 128;
+    if (masked) {
+        if (tid == 0) {
+            unsigned long long m = 0ull;
+            for (int t = m0 / 64; t < (m0 + DM + 63) / 64 && t < a.n_rt64; ++t)
+                m |= a.kmask[size_t(rho_i) * a.n_rt64 + t];
+            int n = 0;
+            for (int kb = 0; kb < n_k; ++kb)
+                if ((m >> (kb >> 1)) & 1ull) klist[n++] = (unsigned char)kb;
+            klist_n = n;
+        }
+        __syncthreads();
+        n_k = klist_n;
+    }
+    auto kstage = [&](int i) -> int { return masked ? int(klist[i]) : i; };
     auto load_stage = [&](int kb, int stage) {
         double* As = dsm + size_t(stage) * STAGE_DOUBLES;
         double* Bs = As + DM * DLD;
@@ -417,13 +440,13 @@ __global__ void __launch_bounds__(32 * WM * WN * KS, 1) bgemm_dmma(GemmArgs<doub
 
 #pragma unroll
     for (int s = 0; s < DSTAGES - 1; ++s) {
-        if (s < n_k) load_stage(s, s);
+        if (s < n_k) load_stage(kstage(s), s);
         cp_async_commit();
     }
     for (int kb = 0; kb < n_k; ++kb) {
         cp_async_wait<DSTAGES - 2>();
         __syncthreads();                                  // stage kb landed; stage kb-1 is free for reuse
-        if (kb + DSTAGES - 1 < n_k) load_stage(kb + DSTAGES - 1, (kb + DSTAGES - 1) % DSTAGES);
+        if (kb + DSTAGES - 1 < n_k) load_stage(kstage(kb + DSTAGES - 1), (kb + DSTAGES - 1) % DSTAGES);
         cp_async_commit();
         const double* As = dsm + size_t(kb % DSTAGES) * STAGE_DOUBLES + (32 * wm + fr) * DLD + fk;
         const double* Bs = dsm + size_t(kb % DSTAGES) * STAGE_DOUBLES + DM * DLD + (64 * wn + fr) * DLD + fk;
@@ -931,7 +954,21 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
             if (tiles * ks <= lim && ks <= nk_min) return ks;
         return 1;
     };
-    const int nk_iter = (D + 31) / 32;
+    // sparsity map of the layer matrices (rqp_batch.kmask): engines skip all-zero k-blocks
+    const unsigned long long* kmask = (D <= 2048 && getenv("RQP_NO_KMASK") == nullptr)
+                                          ? static_cast<const unsigned long long*>(bt->kmask) : nullptr;
+    const int n_rt64 = (D + 63) / 64;
+    const int nk_iter = (kmask != nullptr && bt->kmask_min_blocks > 0) ? bt->kmask_min_blocks : (D + 31) / 32;
+    // window mode: rotate the tile -> CTA assignment by `rot` CTAs per iteration (coprime with the grid, about
+    // a quarter of it, odd so that a CTA's row tile changes too); see tc_first_item
+    const bool tc_rotate = getenv("RQP_NO_ROTATE") == nullptr;
+    auto pick_rot = [&](int grid) -> int {
+        if (!tc_rotate || grid < 8) return 0;
+        auto gcd = [](int x, int y) { while (y) { const int t = x % y; x = y; y = t; } return x; };
+        for (int r = grid / 4 + 1; r < grid; ++r)
+            if ((r & 1) && gcd(r, grid) == 1) return r;
+        return 0;
+    };
     const int nk_raw = ((nx < nc ? nx : nc) + 31) / 32;      // a residual row tile reads the x or the lambda columns
     auto set_ksplit = [&](TcArgs& a, int tiles) -> int {
         a.ksplit = pick_ksplit(tiles, a.raw ? nk_raw : nk_iter);
@@ -954,6 +991,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.raw = 0; a.M = D; a.w_row0 = 0; a.chunk_kb = tc_chunk; a.chunk_rows = tc_chunk_x ? nx : 0;
         a.k_blocks = (D + 31) / 32;
         a.steps = steps; a.done = nullptr;
+        a.kmask = kmask; a.n_rt64 = n_rt64; a.rot = 0;
         a.dbg = static_cast<unsigned long long*>(bt->reserved_dbg);
         if (one_sm_engine()) {
             // 1-CTA tiles of 128 rows x BN columns.  BN is the widest tile that still gives every active
@@ -967,6 +1005,8 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
             if (steps > 1) {
                 a.done = reinterpret_cast<unsigned int*>(w8 + lay.off_done);
                 RQP_CUDA_TRY(cudaMemsetAsync(a.done, 0, size_t(cap / 32 + 1) * 4, st));
+                const int grid = bound < sm_count ? bound : sm_count;
+                if (bound > grid) a.rot = pick_rot(grid);      // more items than CTAs: rotate the assignment
             }
             return tc_launch(map_wh, map_wl, map_xh[b][src], map_xl[b][src], map_xh[b][src ^ 1], map_xl[b][src ^ 1], a,
                              kBoxRows[b], bound, pdl, sm_count, st);
@@ -984,6 +1024,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.M = D; a.K = D; a.tile_rho = c.tile_rho;
         a.b_all = c.b_all; a.bias_cols = with_g ? c.Bias[lcur] : nullptr;
         a.L = c.L; a.U = c.U; a.orig = c.orig[lcur]; a.nx = nx; a.nc = nc; a.D = D;
+        a.kmask = kmask; a.n_rt64 = n_rt64;
         if (use_dmma && nact_host[0] >= dmma_min && DmmaLaunch<T, EPI_ITER>::ok(a)) {
             DmmaLaunch<T, EPI_ITER>::go(a, D, cap, nact_host[0] >= dmma_big, st);
         } else if (nact_host[0] < 2048) {
@@ -1001,6 +1042,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.D = D; a.nx = nx; a.nc = nc; a.ldv = nc + 2 * nx;
         a.raw = 1; a.M = nc + 2 * nx; a.w_row0 = prob->n_rho * D; a.chunk_kb = tc_chunk; a.chunk_rows = 0;
         a.steps = 1; a.done = nullptr; a.Yh_alt = nullptr; a.Yl_alt = nullptr;
+        a.kmask = nullptr; a.n_rt64 = n_rt64; a.rot = 0;
         a.k_blocks = (D + 31) / 32;
         a.n_col_tiles = 0; a.n_row_tiles = (a.M + 127) / 128;
         a.dbg = nullptr;
@@ -1016,6 +1058,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.ldm = 0; a.mat_stride = 0; a.X = c.V[src]; a.ldx = ldv; a.out = c.Tres; a.ldo = nc + 2 * nx;
         a.tile_rho = c.tile_rho; a.b_all = nullptr; a.bias_cols = nullptr; a.L = nullptr; a.U = nullptr;
         a.orig = c.orig[lcur]; a.nx = nx; a.nc = nc; a.D = D;
+        a.kmask = nullptr; a.n_rt64 = n_rt64;
         const bool small = nact_host[0] < 2048;
         auto one = [&](int Mrows) {
             if (use_dmma && nact_host[0] >= dmma_min && DmmaLaunch<T, EPI_RAW>::ok(a))

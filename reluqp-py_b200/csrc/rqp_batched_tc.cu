@@ -260,15 +260,57 @@ __device__ __forceinline__ bool tc_tile_lookup(const int* sb, int t, int n_row_t
     }
     return false;
 }
-// Rows of the W planes and the k-block range a row tile needs.  Iteration tiles (raw == 0): rows of
-// W_rho, all of K.  Residual tiles (raw == 1): rows of the residual operator [A 0 0; H 0 0; 0 0 A'] stored
-// after the n_rho layer matrices; its row blocks only touch the x columns or the lambda columns of the
-// state, so most k-blocks are structurally zero and are skipped.
-__device__ __forceinline__ void tc_tile_rows(const TcArgs& a, int rho, int rt, int& wrow, int& kb_lo, int& kb_hi) {
+// The k-blocks (32 state columns each) a work item runs over, in ascending order: either a plain range
+// [kb, kb_hi) or, when the caller supplied block masks (TcArgs::kmask, at most 64 k-blocks), the set bits of
+// `mask`.  Blocks of W_rho that are entirely zero -- most of the z and lambda columns of the lambda rows
+// [R A, -R, I] -- contribute exact zeros to the accumulator and are skipped: no loads, no MMAs.
+struct KIter {
+    unsigned long long mask;
+    int kb, kb_hi;
+    bool use_mask;
+    __device__ __forceinline__ int count() const { return use_mask ? __popcll(mask) : kb_hi - kb; }
+    __device__ __forceinline__ int next() {           // caller checks count() / loops count() times
+        if (use_mask) {
+            const int b = __ffsll((long long)mask) - 1;
+            mask &= mask - 1ull;
+            return b;
+        }
+        return kb++;
+    }
+    // keep elements [lo, hi) of the sequence
+    __device__ __forceinline__ void slice(int lo, int hi) {
+        if (use_mask) {
+            unsigned long long m = mask, out = 0ull;
+            for (int i = 0; i < hi && m; ++i) {
+                const unsigned long long low = m & (~m + 1ull);
+                if (i >= lo) out |= low;
+                m &= m - 1ull;
+            }
+            mask = out;
+        } else {
+            const int k0 = kb;
+            kb = k0 + lo;
+            kb_hi = k0 + hi;
+        }
+    }
+};
+
+// Rows of the W planes and the k-blocks a row tile needs.  Iteration tiles (raw == 0): rows of W_rho, all
+// k-blocks that hold a nonzero (all of K without masks).  Residual tiles (raw == 1): rows of the residual
+// operator [A 0 0; H 0 0; 0 0 A'] stored after the n_rho layer matrices; its row blocks only touch the x
+// columns or the lambda columns of the state, so most k-blocks are structurally zero and are skipped.
+__device__ __forceinline__ void tc_tile_rows(const TcArgs& a, int rho, int rt, int& wrow, KIter& ki) {
+    ki.mask = 0ull;
+    ki.use_mask = false;
     if (!a.raw) {
         wrow = rho * a.D + rt * TC_BM;
-        kb_lo = 0;
-        kb_hi = a.k_blocks;
+        ki.kb = 0;
+        ki.kb_hi = a.k_blocks;
+        if (a.kmask != nullptr) {
+            const unsigned long long* km = a.kmask + size_t(rho) * a.n_rt64 + 2 * rt;
+            ki.mask = __ldg(km) | ((2 * rt + 1 < a.n_rt64) ? __ldg(km + 1) : 0ull);
+            ki.use_mask = true;
+        }
         return;
     }
     wrow = a.w_row0 + rt * TC_BM;
@@ -277,8 +319,8 @@ __device__ __forceinline__ void tc_tile_rows(const TcArgs& a, int rho, int rt, i
     int k0 = 0, k1 = a.D;
     if (r1 <= split) k1 = a.nx;                    // A x and H x: x columns only
     else if (r0 >= split) k0 = a.nx + a.nc;        // A' lambda: lambda columns only
-    kb_lo = k0 / TC_BK;
-    kb_hi = (k1 + TC_BK - 1) / TC_BK;
+    ki.kb = k0 / TC_BK;
+    ki.kb_hi = (k1 + TC_BK - 1) / TC_BK;
 }
 
 // Residual epilogue: the accumulator goes out as plain fp32, Out[slot][m] (ld = a.ldv).
@@ -307,18 +349,28 @@ __device__ __forceinline__ int tc_tile_count(const int* sb, int n_row_tiles) {
 // scratch buffer, see the epilogue).  Returns false past the last item.
 template <int BN>
 __device__ __forceinline__ bool tc_item(const int* sb, const TcArgs& a, int u, int& t, int& rank, int& rho, int& col0,
-                                        int& rt, int& wrow, int& kb_lo, int& kb_hi) {
+                                        int& rt, int& wrow, KIter& ki) {
     const int ks = a.ksplit;
     t = u / ks;
     rank = u - t * ks;
     if (!tc_tile_lookup<BN>(sb, t, a.n_row_tiles, rho, col0, rt)) return false;
-    tc_tile_rows(a, rho, rt, wrow, kb_lo, kb_hi);
+    tc_tile_rows(a, rho, rt, wrow, ki);
     if (ks > 1) {                                  // balanced slices; empty only if there are fewer k-blocks than ranks
-        const int nk = kb_hi - kb_lo, lo = kb_lo;
-        kb_lo = lo + (nk * rank) / ks;
-        kb_hi = lo + (nk * (rank + 1)) / ks;
+        const int nk = ki.count();
+        ki.slice((nk * rank) / ks, (nk * (rank + 1)) / ks);
     }
     return true;
+}
+
+// First work item of CTA b in iteration `it` of a launch; the CTA then strides by the grid size.  In window
+// mode with more items than CTAs the assignment ROTATES from iteration to iteration (a.rot, coprime with the
+// grid size): 256 tiles on 148 SMs leave 108 CTAs with two tiles and 40 with one in every iteration, and
+// row tiles differ in cost once zero k-blocks are skipped; a CTA that is light in one iteration runs ahead
+// into the next (column tiles drift freely), so over a window every CTA carries the average load instead of
+// every iteration costing the heaviest CTA's.  Dependencies are per column tile and point strictly to the
+// previous iteration, so any assignment that is monotone in the iteration number is deadlock free.
+__device__ __forceinline__ int tc_first_item(const TcArgs& a, int it) {
+    return a.rot > 0 ? int((blockIdx.x + unsigned(it) * unsigned(a.rot)) % gridDim.x) : int(blockIdx.x);
 }
 
 template <int BN>
@@ -388,9 +440,11 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
             for (int it = 0; it < a.steps; ++it) {
                 const CUtensorMap* mxh = (it & 1) ? &map_xh1 : &map_xh;
                 const CUtensorMap* mxl = (it & 1) ? &map_xl1 : &map_xl;
-                for (int u = blockIdx.x; u < n_items; u += gridDim.x) {
-                    int t, rank, rho, xrow, rt, wrow, kb_lo, kb_hi;
-                    if (!tc_item<BN>(sb, a, u, t, rank, rho, xrow, rt, wrow, kb_lo, kb_hi)) break;
+                for (int u = tc_first_item(a, it); u < n_items; u += gridDim.x) {
+                    int t, rank, rho, xrow, rt, wrow;
+                    KIter ki;
+                    if (!tc_item<BN>(sb, a, u, t, rank, rho, xrow, rt, wrow, ki)) break;
+                    int nk = ki.count();
                     // Is there something to wait for before this tile's state planes may be read: the previous
                     // kernel (first tile of a PDL launch) or the previous iteration of this column tile (window
                     // mode)?  Then W, which depends on neither, goes first: up to a ring-full of W planes is
@@ -400,16 +454,18 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                     const bool dep = cnt != nullptr && it > 0 && ld_acquire_u32(cnt) < need;
                     int P = 0;
                     if (first || dep) {
-                        P = (kb_hi - kb_lo) < STAGES ? (kb_hi - kb_lo) : STAGES;
+                        P = nk < STAGES ? nk : STAGES;
                         uint32_t st2 = stage, ph2 = phase;
+                        KIter kw = ki;
                         for (int s = 0; s < P; ++s) {
+                            const int kb = kw.next();
                             const long long tw = clock64();
                             mbar_wait(empty + st2, ph2 ^ 1u);
                             w_empty += clock64() - tw;
                             unsigned char* sp = base + size_t(st2) * STAGE_BYTES;
                             mbar_expect_tx(full + st2, STAGE_BYTES);
-                            tma_load_2d(sp, &map_wh, (kb_lo + s) * TC_BK, wrow, full + st2);
-                            tma_load_2d(sp + TC_TILE_BYTES, &map_wl, (kb_lo + s) * TC_BK, wrow, full + st2);
+                            tma_load_2d(sp, &map_wh, kb * TC_BK, wrow, full + st2);
+                            tma_load_2d(sp + TC_TILE_BYTES, &map_wl, kb * TC_BK, wrow, full + st2);
                             if (++st2 == STAGES) { st2 = 0; ph2 ^= 1u; }
                         }
                         if (first) { grid_dep_wait(); first = false; }
@@ -424,12 +480,14 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                     }
                     if (cnt != nullptr && it > 0) fence_proxy_async_all();   // acquire above -> TMA reads below
                     for (int s = 0; s < P; ++s) {
+                        const int kb = ki.next();
                         unsigned char* sp = base + size_t(stage) * STAGE_BYTES;
-                        tma_load_2d(sp + 2 * TC_TILE_BYTES, mxh, (kb_lo + s) * TC_BK, xrow, full + stage);
-                        tma_load_2d(sp + 2 * TC_TILE_BYTES + XT, mxl, (kb_lo + s) * TC_BK, xrow, full + stage);
+                        tma_load_2d(sp + 2 * TC_TILE_BYTES, mxh, kb * TC_BK, xrow, full + stage);
+                        tma_load_2d(sp + 2 * TC_TILE_BYTES + XT, mxl, kb * TC_BK, xrow, full + stage);
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
-                    for (int kb = kb_lo + P; kb < kb_hi; ++kb) {
+                    for (int i = P; i < nk; ++i) {
+                        const int kb = ki.next();
                         const long long tw = clock64();
                         mbar_wait(empty + stage, phase ^ 1u);
                         w_empty += clock64() - tw;
@@ -454,15 +512,16 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
         long long w_full = 0, w_acc = 0, t_all = clock64(), ntile = 0;
         grid_dep_wait();
         for (int it = 0; it < a.steps; ++it)
-        for (int u = blockIdx.x; u < n_items; u += gridDim.x) {
-            int t, rank, rho, col0, rt, wrow, kb_lo, kb_hi;
-            if (!tc_item<BN>(sb, a, u, t, rank, rho, col0, rt, wrow, kb_lo, kb_hi)) break;
+        for (int u = tc_first_item(a, it); u < n_items; u += gridDim.x) {
+            int t, rank, rho, col0, rt, wrow;
+            KIter ki;
+            if (!tc_item<BN>(sb, a, u, t, rank, rho, col0, rt, wrow, ki)) break;
             ntile++;
-            const int nk = kb_hi - kb_lo;
+            const int nk = ki.count();
             const int chunk = (a.chunk_kb > 0 && a.chunk_kb < nk && (a.chunk_rows <= 0 || rt * TC_BM < a.chunk_rows))
                                   ? a.chunk_kb : nk;
             int in_chunk = 0;
-            for (int kb = kb_lo; kb < kb_hi; ++kb) {
+            for (int i = 0; i < nk; ++i) {
                 long long tw = clock64();
                 if (in_chunk == 0) {
                     mbar_wait(acc_empty + acc, acc_phase ^ 1u);   // epilogue has drained this accumulator stage
@@ -473,7 +532,7 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                 mbar_wait(full + stage, phase);
                 w_full += clock64() - tw;
                 tc_fence_after();
-                const bool last = in_chunk == chunk - 1 || kb == kb_hi - 1;
+                const bool last = in_chunk == chunk - 1 || i == nk - 1;
                 if (elect_one()) {
                     const uint32_t d_tmem = tmem_base + acc * BN;
                     unsigned char* sp = base + size_t(stage) * STAGE_BYTES;
@@ -514,10 +573,11 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
         grid_dep_wait();
         long long t_all = clock64();
         for (int it = 0; it < a.steps; ++it)
-        for (int u = blockIdx.x; u < n_items; u += gridDim.x) {
-            int t, rank, rho, col0, rt, wrow, kb_lo, kb_hi;
-            if (!tc_item<BN>(sb, a, u, t, rank, rho, col0, rt, wrow, kb_lo, kb_hi)) break;
-            const int nk = kb_hi - kb_lo;
+        for (int u = tc_first_item(a, it); u < n_items; u += gridDim.x) {
+            int t, rank, rho, col0, rt, wrow;
+            KIter ki;
+            if (!tc_item<BN>(sb, a, u, t, rank, rho, col0, rt, wrow, ki)) break;
+            const int nk = ki.count();
             const int chunk = (a.chunk_kb > 0 && a.chunk_kb < nk && (a.chunk_rows <= 0 || rt * TC_BM < a.chunk_rows))
                                   ? a.chunk_kb : (nk > 0 ? nk : 1);
             const int nchunks = (nk + chunk - 1) / chunk;

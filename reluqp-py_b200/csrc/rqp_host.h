@@ -9,6 +9,7 @@ namespace rqp {
 
 struct SinglePlan {
     int grid, block, cpt, rpc, rows_smem, rmode, ring;
+    int check_tpw;   // > 0: the residual-check matrix rows of each warp stay in shared memory (tasks per warp)
     size_t smem_bytes;
     size_t vcells_bytes, pcells_bytes, ws_bytes;
 };

@@ -26,14 +26,26 @@
 //    decision from bitwise identical numbers (rho estimate, index move, termination).
 //  * Every wait is bounded by a watchdog; on expiry the kernel exits with result.error set.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "rqp_common.cuh"
 #include "rqp_host.h"
 
 namespace rqp {
 
+#ifndef RQP_V_STAGE
+#define RQP_V_STAGE 0
+#endif
+#ifndef RQP_V_AG
+#define RQP_V_AG 0
+#endif
+#ifndef RQP_V_CHKTIME
+#define RQP_V_CHKTIME 0     // diagnostics: the phase counters time the steps of the residual check instead
+#endif
 constexpr int RM = 8;  // rows per register chunk
 constexpr int RING_STAGES = 4;   // streamed-slab ring: 4 stages of RM rows x (NT * 16) bytes
+constexpr int kMaxReplicas = 8;  // exchange-cell copies the workspace is sized for
+constexpr int kDefaultReplicas = 1;
 
 struct SingleParams {
     const void* W;
@@ -65,6 +77,9 @@ struct SingleParams {
     int prepoll_cycles;   // spin this many SM cycles after the CTA barrier before the first poll
     int exch_flags;       // bit 0: CTA barrier after the publish store (polls queue behind it)
     int ring;             // 1: stream the slab through a shared-memory ring filled by bulk async copies
+    int check_tpw;        // > 0: rows of A / H / A' each warp needs in a check are kept in shared memory
+    int replicas;         // copies of the exchange cells; CTA c reads copy c % replicas (spreads the hot
+                          // lines every CTA polls over more L2 slices), publishers write all copies
 };
 
 template <typename T>
@@ -101,7 +116,8 @@ __device__ __forceinline__ void chunk_dot(const T* __restrict__ wrow0, long long
 // Warp dot product of a global-memory row with a shared-memory vector: up to 8 independent loads per
 // lane are issued before the first use (the rows are read once per check, from L2 or HBM, so the
 // loop is latency bound unless the loads overlap).  Every lane returns the full sum.
-template <typename T>
+// GL: the row is in global memory (read-only path); otherwise a shared-memory copy.
+template <typename T, bool GL>
 __device__ __forceinline__ T warp_row_dot(const T* __restrict__ row, const T* xs, int n, int lane) {
     T s0 = T(0), s1 = T(0);
     for (int j0 = 0; j0 < n; j0 += 256) {
@@ -109,7 +125,7 @@ __device__ __forceinline__ T warp_row_dot(const T* __restrict__ row, const T* xs
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int j = j0 + u * 32 + lane;
-            a[u] = (j < n) ? __ldg(row + j) : T(0);
+            a[u] = (j < n) ? (GL ? __ldg(row + j) : row[j]) : T(0);
         }
 #pragma unroll
         for (int u = 0; u < 8; u += 2) {
@@ -123,7 +139,7 @@ __device__ __forceinline__ T warp_row_dot(const T* __restrict__ row, const T* xs
 
 // Two rows at once (H x and A' lambda of the same index): all loads of both rows are in flight
 // together.  Returns the two sums through references.
-template <typename T>
+template <typename T, bool GL>
 __device__ __forceinline__ void warp_row_dot2(const T* __restrict__ r1, const T* x1, int n1,
                                               const T* __restrict__ r2, const T* x2, int n2, int lane, T& o1, T& o2) {
     T s0 = T(0), s1 = T(0), q0 = T(0), q1 = T(0);
@@ -133,8 +149,8 @@ __device__ __forceinline__ void warp_row_dot2(const T* __restrict__ r1, const T*
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = j0 + u * 32 + lane;
-            a[u] = (j < n1) ? __ldg(r1 + j) : T(0);
-            b[u] = (j < n2) ? __ldg(r2 + j) : T(0);
+            a[u] = (j < n1) ? (GL ? __ldg(r1 + j) : r1[j]) : T(0);
+            b[u] = (j < n2) ? (GL ? __ldg(r2 + j) : r2[j]) : T(0);
         }
 #pragma unroll
         for (int u = 0; u < 4; u += 2) {
@@ -190,9 +206,15 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
     Decision* dec = reinterpret_cast<Decision*>(tot + NW * 8);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(dec + 1);
     uint64_t* rbar = mbar + 1;                                 // [RING_STAGES] ring "full" barriers
+    uint64_t* cbar = rbar + RING_STAGES;                       // check rows landed
+    // check rows: [NW][check_tpw][nx + nc] after the barriers (16-byte aligned)
+    T* crow = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(cbar + 1) + 15) & ~uintptr_t(15));
 
     Watchdog wd{p.watchdog_ns, p.abort_flag, 0, 0};
     const uint32_t epoch = p.epoch;
+    // exchange cells: [replicas][2 buffers][nvec * 4 words]; this CTA polls its own replica
+    const size_t rep_words = size_t(2) * nvec * 4;
+    const uint64_t* my_cells = p.vcells + size_t(blockIdx.x % p.replicas) * rep_words;
 
     // ---- per-thread column ownership (iteration invariant)
     int coff[CPT];        // element offset of the owned vector column inside a W row (clamped)
@@ -218,7 +240,8 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
             my_hi = static_cast<const T*>(p.u)[my_row - nx];
         }
         my_b = ball[size_t(rho_ind) * D + my_row];
-        C::publish(p.vcells, my_row, my_v, epoch);  // v_0 into buffer 0
+        for (int rp = 0; rp < p.replicas; ++rp)
+            C::publish(p.vcells + size_t(rp) * rep_words, my_row, my_v, epoch);  // v_0 into buffer 0
     }
 
     // ---- stage the W slab of the current rho
@@ -226,9 +249,37 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
     if (tid == 0) {
         mbar_init(mbar, 1);
         for (int s = 0; s < RING_STAGES; ++s) mbar_init(rbar + s, 1);
+        mbar_init(cbar, 1);
         fence_mbar_init();
     }
     __syncthreads();
+    // Residual-check rows (rho independent): warp w's task j is row i = (blockIdx.x * NW + w) + j * G * NW of
+    // [A; (H, A')]; bulk copies issued now land long before the first check.
+    bool crow_pending = p.check_tpw > 0;
+    if (p.check_tpw > 0 && tid == 0) {
+        const T* Hm0 = static_cast<const T*>(p.H);
+        const T* Am0 = static_cast<const T*>(p.A);
+        const T* ATm0 = static_cast<const T*>(p.AT);
+        uint32_t bytes = 0;
+        for (int w = 0; w < NW; ++w)
+            for (int j = 0; j < p.check_tpw; ++j) {
+                const int i = blockIdx.x * NW + w + j * G * NW;
+                if (i < nc) bytes += uint32_t(nx * sizeof(T));
+                else if (i < nc + nx) bytes += uint32_t((nx + nc) * sizeof(T));
+            }
+        mbar_expect_tx(cbar, bytes);
+        for (int w = 0; w < NW; ++w)
+            for (int j = 0; j < p.check_tpw; ++j) {
+                const int i = blockIdx.x * NW + w + j * G * NW;
+                T* dst = crow + size_t(w * p.check_tpw + j) * (nx + nc);
+                if (i < nc) {
+                    bulk_g2s(dst, Am0 + size_t(i) * nx, uint32_t(nx * sizeof(T)), cbar);
+                } else if (i < nc + nx) {
+                    bulk_g2s(dst, Hm0 + size_t(i - nc) * nx, uint32_t(nx * sizeof(T)), cbar);
+                    bulk_g2s(dst + nx, ATm0 + size_t(i - nc) * nc, uint32_t(nc * sizeof(T)), cbar);
+                }
+            }
+    }
     // ---- streaming ring (HBM-bound sizes): tiles of RM rows x (NT*VEC) columns of the slab, in the
     // order (row chunk, column chunk), flow through RING_STAGES shared-memory stages filled by 1-D bulk
     // async copies (one per row); the DMA engine keeps ~96 KB in flight per SM independent of registers,
@@ -268,13 +319,17 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
         return good;
     };
     Vec16<T> wreg[RMODE ? RM : 1][RMODE ? CPT : 1];
+    // Per-phase cycle counters of thread 0 / CTA 0 (result.phase_cycles).  Kept only in the register-resident
+    // kernels, where they are free; the shared-memory / streaming kernels sit at 255 registers and the 16
+    // counter registers cost them ~10 % per iteration (C3: 9.7 -> 8.8 us), so there the counters read 0.
+    constexpr bool kTimers = RMODE || RQP_V_CHKTIME;
     long long ph[8] = {0, 0, 0, 0, 0, 0, 0, RMODE ? 1 : 0};
     auto stage_slab = [&](int ri) {
         // caller guarantees every thread is past its last read of Ws (a __syncthreads)
-        const long long ts = clock64();
+        const long long ts = kTimers ? clock64() : 0;
         if (p.ring) {
             ring_start(ri);
-            ph[6] += clock64() - ts;
+            if (kTimers) ph[6] += clock64() - ts;
             return true;
         }
         if (RMODE) {
@@ -288,7 +343,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                         Vec16<T>::ldg(Wg + (long long)min(r, rows - 1) * ldw + coff[i]);
                 }
             }
-            ph[6] += clock64() - ts;
+            if (kTimers) ph[6] += clock64() - ts;
             return true;
         }
         if (rows_s > 0) {
@@ -308,7 +363,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 if (wd.expired()) { ok = false; break; }
             }
             mbar_parity ^= 1u;
-            ph[6] += clock64() - ts;
+            if (kTimers) ph[6] += clock64() - ts;
             return ok;
         }
         return true;
@@ -325,10 +380,17 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
     // Residual evaluation on v_k (flag fk in vcells buffer k&1).  final_pass: no index move, no
     // termination test (reluqpth.py:243).  Returns false on watchdog abort (uniform over the CTA).
     auto residual_pass = [&](int kk, uint32_t pflag, bool final_pass) -> bool {
-        const uint64_t* vslot = p.vcells + size_t(kk & 1) * nvec * 4;
+        const uint64_t* vslot = my_cells + size_t(kk & 1) * nvec * 4;
         const uint32_t fk = epoch + uint32_t(kk);
         bool good = true;
+#if RQP_V_CHKTIME
+        long long ct0 = clock64();
+#define CHK_MARK(i) do { const long long n__ = clock64(); ph[i] += n__ - ct0; ct0 = n__; } while (0)
+#else
+#define CHK_MARK(i) do { } while (0)
+#endif
         // 1. stage v_k into shared memory
+#if RQP_V_STAGE == 0
         wd.arm();
         for (int c = tid; c < nvec; c += NT) {
             const int nval = max(0, min(VEC, D - c * VEC));
@@ -346,7 +408,48 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
 #pragma unroll
             for (int e = 0; e < VEC; ++e) vs[c * VEC + e] = ((nd >> e) & 1u) ? out[e] : T(0);
         }
+#else
+        // the loads of SQ columns a thread stages are issued together (one L2 round trip), columns whose
+        // flags have not arrived yet are polled again
+        constexpr int SQ = RQP_V_STAGE == 1 ? 2 : 4;
+        wd.arm();
+        for (int c0 = tid; c0 < nvec; c0 += SQ * NT) {
+            uint64_t w[SQ][4];
+            uint32_t pend = 0;
+#pragma unroll
+            for (int q = 0; q < SQ; ++q) {
+                const int c = c0 + q * NT;
+                if (c < nvec) {
+                    ld_relaxed_u64x2(vslot + size_t(c) * 4, w[q][0], w[q][1]);
+                    ld_relaxed_u64x2(vslot + size_t(c) * 4 + 2, w[q][2], w[q][3]);
+                    pend |= 1u << q;
+                }
+            }
+            while (pend != 0u && good) {
+#pragma unroll
+                for (int q = 0; q < SQ; ++q) {
+                    if (pend & (1u << q)) {
+                        const int c = c0 + q * NT;
+                        const int nval = max(0, min(VEC, D - c * VEC));
+                        const uint32_t nd = (1u << nval) - 1u;
+                        T out[VEC];
+                        const uint32_t m = C::unpack(w[q], fk, out);
+                        if ((m & nd) == nd) {
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) vs[c * VEC + e] = ((nd >> e) & 1u) ? out[e] : T(0);
+                            pend &= ~(1u << q);
+                        } else {
+                            ld_relaxed_u64x2(vslot + size_t(c) * 4, w[q][0], w[q][1]);
+                            ld_relaxed_u64x2(vslot + size_t(c) * 4 + 2, w[q][2], w[q][3]);
+                        }
+                    }
+                }
+                if (pend != 0u && wd.expired()) good = false;
+            }
+        }
+#endif
         if (__syncthreads_or(!good)) return false;
+        CHK_MARK(0);
 
         // 2. one matrix row per warp-task, grid-strided
         const T* __restrict__ Hm = static_cast<const T*>(p.H);
@@ -358,9 +461,19 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
         const T* ls = vs + nx + nc;
         T m0 = T(0), m1 = T(0), m2 = T(0), m3 = T(0), m4 = T(0), m5 = T(0), m6 = T(0), osum = T(0);
         const int GW = G * NW;
-        for (int i = blockIdx.x * NW + warp; i < nc + nx; i += GW) {
+        if (crow_pending) {     // first check: the rows were requested at kernel start
+            wd.arm();
+            while (!mbar_try_wait(cbar, 0)) {
+                if (wd.expired()) { good = false; break; }
+            }
+            crow_pending = false;
+        }
+        int tj = 0;
+        for (int i = blockIdx.x * NW + warp; i < nc + nx; i += GW, ++tj) {
+            const T* crw = crow + size_t(warp * p.check_tpw + tj) * (nx + nc);
             if (i < nc) {
-                const T t1 = warp_row_dot(Am + size_t(i) * nx, xs, nx, lane);
+                const T t1 = p.check_tpw > 0 ? warp_row_dot<T, false>(crw, xs, nx, lane)
+                                             : warp_row_dot<T, true>(Am + size_t(i) * nx, xs, nx, lane);
                 const T zi = zs[i];
                 m0 = nanmax(m0, absval(t1 - zi));
                 m1 = nanmax(m1, absval(t1));
@@ -368,7 +481,10 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
             } else {
                 const int ii = i - nc;
                 T t2, t3;
-                warp_row_dot2(Hm + size_t(ii) * nx, xs, nx, ATm + size_t(ii) * nc, ls, nc, lane, t2, t3);
+                if (p.check_tpw > 0)
+                    warp_row_dot2<T, false>(crw, xs, nx, crw + nx, ls, nc, lane, t2, t3);
+                else
+                    warp_row_dot2<T, true>(Hm + size_t(ii) * nx, xs, nx, ATm + size_t(ii) * nc, ls, nc, lane, t2, t3);
                 const T gi = __ldg(gv + ii);
                 m3 = nanmax(m3, absval((t2 + t3) + gi));
                 m4 = nanmax(m4, absval(t2));
@@ -377,6 +493,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 osum += xs[ii] * (T(0.5) * t2 + gi);
             }
         }
+        CHK_MARK(1);
         // 3. CTA reduction, publish 8 partials as double cells
         if (lane == 0) {
             double* pw = part + warp * 8;
@@ -393,11 +510,13 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
             }
             Cell<double>::publish(pslot, blockIdx.x * 8 + tid, a, pflag);
         }
+        CHK_MARK(2);
         // 4. all-gather: thread t folds quantity q = t & 7 over CTAs (t >> 3) + m * NT/8
         {
             const int q = tid & 7;
             double a = 0.0;
             wd.arm();
+#if RQP_V_AG == 0
             for (int c = tid >> 3; c < G; c += NT / 8) {
                 double val = 0.0;
                 while (good) {
@@ -411,6 +530,45 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 }
                 a = (q == 7) ? (a + val) : nanmax(a, val);
             }
+#else
+            // the cells of up to AQ CTAs are requested together (one L2 round trip instead of one per CTA),
+            // late ones are polled again; the fold order (ascending CTA index) does not depend on arrival
+            constexpr int AQ = 5;     // G <= 148 CTAs, NT / 8 >= 32 per pass
+            for (int cb = tid >> 3; cb < G; cb += AQ * (NT / 8)) {
+                uint64_t w0[AQ], w1[AQ];
+                uint32_t pend = 0;
+#pragma unroll
+                for (int j = 0; j < AQ; ++j) {
+                    const int c = cb + j * (NT / 8);
+                    if (c < G) {
+                        ld_relaxed_u64x2(pslot + (size_t(c) * 8 + q) * 2, w0[j], w1[j]);
+                        pend |= 1u << j;
+                    }
+                }
+                const uint32_t have = pend;
+                while (pend != 0u && good) {
+#pragma unroll
+                    for (int j = 0; j < AQ; ++j) {
+                        if (pend & (1u << j)) {
+                            if (uint32_t(w0[j] >> 32) == pflag && uint32_t(w1[j] >> 32) == pflag) {
+                                pend &= ~(1u << j);
+                            } else {
+                                const int c = cb + j * (NT / 8);
+                                ld_relaxed_u64x2(pslot + (size_t(c) * 8 + q) * 2, w0[j], w1[j]);
+                            }
+                        }
+                    }
+                    if (pend != 0u && wd.expired()) good = false;
+                }
+#pragma unroll
+                for (int j = 0; j < AQ; ++j) {
+                    if (have & (1u << j)) {
+                        const double val = __longlong_as_double((long long)((w0[j] & 0xffffffffull) | (w1[j] << 32)));
+                        a = (q == 7) ? (a + val) : nanmax(a, val);
+                    }
+                }
+            }
+#endif
             // lanes with equal (lane & 7) hold the same quantity
             double o8 = __shfl_xor_sync(0xffffffffu, a, 8);
             a = (q == 7) ? (a + o8) : nanmax(a, o8);
@@ -419,6 +577,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
             if (lane < 8) tot[warp * 8 + lane] = a;
         }
         if (__syncthreads_or(!good)) return false;
+        CHK_MARK(3);
         // 5. scalar logic, identical in every CTA
         if (tid == 0) {
             double t[8];
@@ -468,6 +627,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
         solved = dec->done != 0;
         n_checks += 1;
         __syncthreads();  // dec / part / tot may be rewritten by the next pass
+        CHK_MARK(5);
         if (new_ri != rho_ind && !solved) {
             rho_ind = new_ri;
             n_switch += 1;
@@ -485,9 +645,9 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
 
     if (!aborted) {
         for (k = 1; k <= p.max_iter; ++k) {
-            const long long tp0 = clock64();
+            const long long tp0 = kTimers ? clock64() : 0;
             // ---- gather the owned columns of v_{k-1}
-            const uint64_t* vslot = p.vcells + size_t((k - 1) & 1) * nvec * 4;
+            const uint64_t* vslot = my_cells + size_t((k - 1) & 1) * nvec * 4;
             const uint32_t fprev = epoch + uint32_t(k - 1);
             T vv[CPT][VEC];
             {
@@ -509,7 +669,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 }
                 wd.arm();
                 while (pending != 0u && ok) {
-                    ph[5] += 1;
+                    if (kTimers) ph[5] += 1;
                     if (p.backoff_ns > 0) __nanosleep(p.backoff_ns);
 #pragma unroll
                     for (int i = 0; i < CPT; ++i) {
@@ -531,7 +691,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 }
             }
 
-            const long long tp1 = clock64();
+            const long long tp1 = kTimers ? clock64() : 0;
             // ---- slab GEMV, 8 rows per chunk
             T* redk = red + size_t(k & 1) * NW * rpc_pad + size_t(warp) * rpc_pad;
             const T* Wg = Wall + (size_t(rho_ind) * D + r0) * ldw;
@@ -591,7 +751,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 warp_multi_reduce8(acc, lane);
                 if ((lane & 3) == 0) redk[rbase + (lane >> 2)] = acc[0];
             }
-            const long long tp2 = clock64();
+            const long long tp2 = kTimers ? clock64() : 0;
             if (__syncthreads_or(!ok)) { aborted = true; break; }
             const long long tp3 = clock64();
 
@@ -603,7 +763,9 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 for (int w = 1; w < NW; ++w) y += rk[size_t(w) * rpc_pad];
                 y += my_b;
                 my_v = clamp_keep_nan(y, my_lo, my_hi);
-                C::publish(p.vcells + size_t(k & 1) * nvec * 4, my_row, my_v, epoch + uint32_t(k));
+                uint64_t* dst = p.vcells + size_t(k & 1) * nvec * 4;
+                for (int rp = 0; rp < p.replicas; ++rp)
+                    C::publish(dst + size_t(rp) * rep_words, my_row, my_v, epoch + uint32_t(k));
             }
             if (p.exch_flags & 1) __syncthreads();
             if (p.prepoll_cycles > 0) {
@@ -612,13 +774,15 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 }
             }
 
-            const long long tp4 = clock64();
-            ph[0] += tp1 - tp0; ph[1] += tp2 - tp1; ph[2] += tp3 - tp2; ph[3] += tp4 - tp3;
+            const long long tp4 = kTimers ? clock64() : 0;
+#if !RQP_V_CHKTIME
+            if (kTimers) { ph[0] += tp1 - tp0; ph[1] += tp2 - tp1; ph[2] += tp3 - tp2; ph[3] += tp4 - tp3; }
+#endif
 
             // ---- residual check (reluqpth.py:218)
             if (p.adaptive && (k % p.check_interval) == 0) {
                 const bool good = residual_pass(k, epoch + uint32_t(k), false);
-                ph[4] += clock64() - tp4;
+                if (kTimers) ph[4] += clock64() - tp4;
                 if (!good) { aborted = true; break; }
                 if (solved) break;
             }
@@ -667,7 +831,7 @@ static size_t smem_fixed_bytes(int elem, long long ldw, int rpc, int block) {
     o += size_t(2) * NW * rpc_pad * elem;          // red
     o = (o + 15) & ~size_t(15);
     o += size_t(2) * NW * 8 * sizeof(double);      // part, tot
-    o += sizeof(Decision) + 16 + 8 * RING_STAGES;  // dec, mbar, ring barriers
+    o += sizeof(Decision) + 16 + 8 * RING_STAGES + 8 + 16;  // dec, mbar, ring barriers, check-row barrier, alignment
     return o;
 }
 
@@ -724,7 +888,21 @@ int plan_single(const rqp_problem* prob, const rqp_settings* stng, const rqp_cap
     plan->rpc = rpc;
     plan->rows_smem = rows_smem;
     plan->smem_bytes = fixed + (plan->ring ? ring_bytes : size_t(rows_smem) * row_bytes) + 128;
-    plan->vcells_bytes = size_t(2) * nvec * 4 * sizeof(uint64_t);
+    // residual-check rows resident in shared memory when they fit beside everything else (small and
+    // medium problems: the checks then never touch L2 for matrix rows); bulk copies need 16-byte rows
+    {
+        const int NW = block / 32;
+        const int tpw = (prob->nx + prob->nc + grid * NW - 1) / (grid * NW);
+        const size_t need = size_t(NW) * tpw * (prob->nx + prob->nc) * elem;
+        const bool aligned = ((size_t(prob->nx) * elem) % 16 == 0) && ((size_t(prob->nc) * elem) % 16 == 0) &&
+                             ((reinterpret_cast<uintptr_t>(prob->H) | reinterpret_cast<uintptr_t>(prob->A) |
+                               reinterpret_cast<uintptr_t>(prob->AT)) & 15) == 0;
+        const bool fits = !plan->ring && aligned && plan->smem_bytes + need <= cap && need < (size_t(1) << 20) &&
+                          getenv("RQP_NO_CHECK_SMEM") == nullptr;
+        plan->check_tpw = fits ? tpw : 0;
+        if (fits) plan->smem_bytes += need;
+    }
+    plan->vcells_bytes = size_t(kMaxReplicas) * 2 * nvec * 4 * sizeof(uint64_t);
     plan->pcells_bytes = size_t(2) * caps.sm_count * 16 * sizeof(uint64_t);
     plan->ws_bytes = 256 + plan->vcells_bytes + plan->pcells_bytes;
     return RQP_OK;
@@ -813,11 +991,23 @@ int launch_single(const rqp_problem* prob, const rqp_settings* stng, rqp_state* 
     prm.rpc = plan.rpc;
     prm.rows_smem = plan.rows_smem;
     prm.backoff_ns = stng->poll_backoff_ns;
-    // 0 = default: 600 SM cycles (measured optimum on B200 for register/shared-resident slabs: the
-    // publish store is not queued behind ~900 early poll requests of the same SM); < 0 = none
-    prm.prepoll_cycles = stng->prepoll_cycles == 0 ? 600 : (stng->prepoll_cycles < 0 ? 0 : stng->prepoll_cycles);
-    prm.exch_flags = stng->exchange_flags;
+    // 0 = default, < 0 = none.  Measured on B200 (tools/prepoll_sweep.py, tools/exch_sweep.sh): polls issued
+    // before the publish stores can have landed only load the L2 -> SM path (every CTA reads all of v: 16 B
+    // per fp64 element), so grids of ~100 CTAs want 600 SM cycles; small grids have little to contend with
+    // and do best with 400 (13..79 CTAs) or 150 (a handful of CTAs).
+    const int prepoll_default = plan.grid >= 80 ? 600 : (plan.grid > 8 ? 400 : 150);
+    prm.prepoll_cycles = stng->prepoll_cycles == 0 ? prepoll_default : (stng->prepoll_cycles < 0 ? 0 : stng->prepoll_cycles);
+    prm.exch_flags = stng->exchange_flags & 0xff;
     prm.ring = plan.ring;
+    prm.check_tpw = plan.check_tpw;
+    // bits 8.. of exchange_flags: number of exchange-cell replicas (0 = default)
+    {
+        int rep = stng->exchange_flags >> 8;
+        if (rep <= 0) rep = kDefaultReplicas;
+        if (rep > kMaxReplicas) rep = kMaxReplicas;
+        if (rep > plan.grid) rep = plan.grid;
+        prm.replicas = rep;
+    }
 
     if (prob->dtype == RQP_F64) {
         rc = plan.block == 256 ? launch_cpt<double, 256>(prm, plan, stream) : launch_cpt<double, 512>(prm, plan, stream);

@@ -30,6 +30,9 @@ struct TcArgs {
     int chunk_rows;         // > 0: only row tiles starting below this row are chunked (the x block)
     int chunk_kb;           // 1-CTA kernels: k-blocks per accumulator chunk (0: one accumulator over all of K)
     int n_col_tiles, n_row_tiles, k_blocks;
+    const unsigned long long* kmask;  // [n_rho][n_rt64] nonzero k-blocks per 64-row tile of W_rho, or null (all dense)
+    int n_rt64;             // 64-row tiles per rho = ceil(D / 64)
+    int rot;                // window mode: rotation of the item -> CTA assignment per iteration (0 = fixed)
     unsigned long long* dbg;  // optional [16] cycle counters written by CTA 0 (diagnostics)
 };
 

@@ -32,6 +32,31 @@ class BatchEngine(object):
         self.ws = None
         self.ws_B = 0
         self.W_hi = self.W_lo = None
+        self.kmask = None
+        self.kmask_min = 0
+
+    def _block_mask(self):
+        """Sparsity map of the layer matrices for the GEMM engines (``rqp_batch.kmask``): one uint64 per
+        (rho, 64-row tile), bit kb set when that tile has a nonzero in columns [32 kb, 32 kb + 32).  The
+        lambda rows of W_rho are ``[R A, -R, I]`` (``reluqpth.py:75``): off the diagonal their z and lambda
+        column blocks are exact zeros, which the engines then skip.  Computed once per setup; None when D
+        has more than 64 column blocks or ``RQP_NO_KMASK`` is set."""
+        if self.kmask is None and os.environ.get("RQP_NO_KMASK") is None:
+            W = self.solver.layers.W_all                      # [n_rho, D, ldw]
+            n_rho, D, _ = W.shape
+            kb, rt = (D + 31) // 32, (D + 63) // 64
+            if kb <= 64:
+                nz = torch.zeros((n_rho, rt * 64, kb * 32), dtype=torch.bool, device=W.device)
+                nz[:, :D, :D] = W[:, :, :D] != 0
+                blocks = nz.view(n_rho, rt, 64, kb, 32).any(dim=4).any(dim=2)          # [n_rho, rt, kb]
+                weights = torch.tensor([1 << b if b < 63 else -(1 << 63) for b in range(kb)], dtype=torch.int64,
+                                       device=W.device)
+                self.kmask = (blocks.to(torch.int64) * weights).sum(dim=2).contiguous()  # bit pattern as int64
+                pairs = torch.zeros((n_rho, (rt + 1) // 2 * 2, kb), dtype=torch.bool, device=W.device)
+                pairs[:, :rt] = blocks
+                per128 = pairs.view(n_rho, -1, 2, kb).any(dim=2).sum(dim=2)
+                self.kmask_min = int(per128.min().item())
+        return self.kmask
 
     def _tf32_planes(self):
         """fp32 only: W ~= W_hi + W_lo with W_hi = rna_tf32(W) (nearest, ties away: add half an ulp of
@@ -125,6 +150,9 @@ class BatchEngine(object):
             wh, wl = self._tf32_planes()
             bt.W_hi, bt.W_lo = wh.data_ptr(), wl.data_ptr()
             bt.res_planes = 1
+        km = self._block_mask()
+        if km is not None:
+            bt.kmask, bt.kmask_min_blocks = km.data_ptr(), self.kmask_min
         self.dbg = None
         if getattr(self, "want_dbg", False):
             self.dbg = torch.zeros(16, dtype=torch.int64, device=dev)

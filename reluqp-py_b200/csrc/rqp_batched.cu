@@ -775,7 +775,7 @@ static BatchLayout batch_layout(const rqp_problem* p, int B, int ldv, bool with_
     l.off_cursor = take(size_t(p->n_rho) * 4);
     l.off_tile = take(size_t(l.n_tiles) * 4);
     l.off_btab = take(64 * 4);
-    l.off_done = take(size_t(l.cap / 32 + 1) * 4);      // window kernel: one completion counter per column tile
+    l.off_done = take(size_t(l.cap / 32 + 2) * 4);      // window kernel: one completion counter per column tile
     // split-K of the tcgen05 kernels (fewer tiles than SMs): one work item per SM at most
     l.off_kcnt = take(planes ? size_t(kMaxSplitItems) * 8 * 4 : 0);
     l.off_scratch = take(planes ? size_t(kMaxSplitItems) * 128 * 128 * 4 : 0);
@@ -885,6 +885,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         return RQP_OK;
     };
     const bool pdl_ok = getenv("RQP_NO_PDL") == nullptr;
+    const bool tc_narrow = getenv("RQP_NO_NARROW") == nullptr;
     const bool tc_ksplit_ok = getenv("RQP_NO_KSPLIT") == nullptr;
     const int tc_ksplit_max = getenv("RQP_KSPLIT_MAX") ? atoi(getenv("RQP_KSPLIT_MAX")) : 8;
     // one launch per check window (1-CTA tcgen05 kernels): 0 never, 1 when CTAs own several tiles, 2 always
@@ -932,7 +933,11 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         if (nact_host[3] * n_row_tiles > sm_count) return 0;              // more than one wave anyway
         if (nact_host[1] * n_row_tiles <= sm_count) return 2;
         if (nact_host[2] * n_row_tiles <= sm_count) return 1;
-        return 0;
+        // 128-column tiles would fit in one wave, 64-column tiles do not: with ONE tile per CTA the chain
+        // mainloop -> epilogue -> next iteration's mainloop is serial (33 us per iteration), with two narrower
+        // tiles per CTA in window mode the epilogue of one overlaps the mainloop of the other (a 64-column
+        // MMA costs ~0.65 of a 128-column one): 2106 active columns 855 -> 712 us per window, 1753: 832 -> 648
+        return tc_narrow ? 1 : 0;
     };
     // pdl: this launch directly follows another 1-CTA tcgen05 iteration kernel of the same window
     // One launch = `steps` iterations starting from buffer `src`.  steps > 1 is the window mode of the 1-CTA
@@ -962,6 +967,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     // window mode: rotate the tile -> CTA assignment by `rot` CTAs per iteration (coprime with the grid, about
     // a quarter of it, odd so that a CTA's row tile changes too); see tc_first_item
     const bool tc_rotate = getenv("RQP_NO_ROTATE") == nullptr;
+    const bool tc_ticket = getenv("RQP_NO_TICKET") == nullptr;
     auto pick_rot = [&](int grid) -> int {
         if (!tc_rotate || grid < 8) return 0;
         auto gcd = [](int x, int y) { while (y) { const int t = x % y; x = y; y = t; } return x; };
@@ -991,7 +997,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.raw = 0; a.M = D; a.w_row0 = 0; a.chunk_kb = tc_chunk; a.chunk_rows = tc_chunk_x ? nx : 0;
         a.k_blocks = (D + 31) / 32;
         a.steps = steps; a.done = nullptr;
-        a.kmask = kmask; a.n_rt64 = n_rt64; a.rot = 0;
+        a.kmask = kmask; a.n_rt64 = n_rt64; a.rot = 0; a.ticket = nullptr;
         a.dbg = static_cast<unsigned long long*>(bt->reserved_dbg);
         if (one_sm_engine()) {
             // 1-CTA tiles of 128 rows x BN columns.  BN is the widest tile that still gives every active
@@ -1006,7 +1012,12 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
                 a.done = reinterpret_cast<unsigned int*>(w8 + lay.off_done);
                 RQP_CUDA_TRY(cudaMemsetAsync(a.done, 0, size_t(cap / 32 + 1) * 4, st));
                 const int grid = bound < sm_count ? bound : sm_count;
-                if (bound > grid) a.rot = pick_rot(grid);      // more items than CTAs: rotate the assignment
+                if (bound > grid) {
+                    // more items than CTAs: hand items out through a ticket counter (the spare last entry of
+                    // the `done` array, zeroed above); RQP_NO_TICKET=1: static assignment rotated per iteration
+                    if (tc_ticket) a.ticket = a.done + cap / 32;
+                    else a.rot = pick_rot(grid);
+                }
             }
             return tc_launch(map_wh, map_wl, map_xh[b][src], map_xl[b][src], map_xh[b][src ^ 1], map_xl[b][src ^ 1], a,
                              kBoxRows[b], bound, pdl, sm_count, st);
@@ -1042,7 +1053,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.D = D; a.nx = nx; a.nc = nc; a.ldv = nc + 2 * nx;
         a.raw = 1; a.M = nc + 2 * nx; a.w_row0 = prob->n_rho * D; a.chunk_kb = tc_chunk; a.chunk_rows = 0;
         a.steps = 1; a.done = nullptr; a.Yh_alt = nullptr; a.Yl_alt = nullptr;
-        a.kmask = nullptr; a.n_rt64 = n_rt64; a.rot = 0;
+        a.kmask = nullptr; a.n_rt64 = n_rt64; a.rot = 0; a.ticket = nullptr;
         a.k_blocks = (D + 31) / 32;
         a.n_col_tiles = 0; a.n_row_tiles = (a.M + 127) / 128;
         a.dbg = nullptr;

@@ -48,7 +48,7 @@ struct TcCfg {
     static constexpr int TMEM_COLS = TC_ACC_STAGES * BN;          // 256 / 128 / 64 (powers of two >= 32)
     static constexpr int EPI_WARPS = BN >= 64 ? 8 : 4;
     static constexpr int COLS_PER_EPI_WARP = BN / (EPI_WARPS / 4);
-    static constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers, bucket table*/;
+    static constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 /*align*/ + 640 /*barriers, bucket table, ticket ring*/;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -373,6 +373,63 @@ __device__ __forceinline__ int tc_first_item(const TcArgs& a, int it) {
     return a.rot > 0 ? int((blockIdx.x + unsigned(it) * unsigned(a.rot)) % gridDim.x) : int(blockIdx.x);
 }
 
+// Walks the work items of one CTA in the order all three roles (producer, MMA issuer, epilogue warps) must
+// agree on.  Static: iteration by iteration, items tc_first_item(it) + j * gridDim.x.  Dynamic (window mode
+// with more items than CTAs, a.ticket != null): items are handed out by a global ticket counter in the
+// order (iteration, item) -- a CTA that finishes early simply takes the next ticket, so the load balances
+// itself and nobody idles on a static schedule's dependency stalls (in-kernel counters, 4096 columns: the
+// rotated static schedule left the producer waiting 24 % of a window for column tiles other CTAs had not
+// finished).  The producer draws the ticket and hands it to the other roles through a two-slot shared-memory
+// ring (sched / sfull / sempty); a ticket >= steps * n_items ends the walk for everybody.  Tickets grow
+// with the iteration number and dependencies point to the previous iteration only, so whoever holds the
+// smallest unfinished ticket can always proceed: no deadlock with all CTAs co-resident.
+struct TcWalk {
+    int it, u;
+    int n_items, steps;
+    bool started;
+    uint32_t ss, sph;
+    __device__ __forceinline__ void init(int n_items_, int steps_) {
+        n_items = n_items_; steps = steps_; started = false; ss = 0; sph = 0; it = 0; u = 0;
+    }
+    __device__ __forceinline__ bool next_static(const TcArgs& a) {
+        if (!started) { started = true; it = 0; u = tc_first_item(a, 0); }
+        else u += int(gridDim.x);
+        while (u >= n_items) {
+            if (++it >= steps) return false;
+            u = tc_first_item(a, it);
+        }
+        return true;
+    }
+    __device__ __forceinline__ bool decode(unsigned int tau) {
+        if (tau >= unsigned(steps) * unsigned(n_items)) return false;
+        it = int(tau / unsigned(n_items));
+        u = int(tau - unsigned(it) * unsigned(n_items));
+        return true;
+    }
+    // producer (one thread): draw a ticket, publish it to the other roles
+    __device__ __forceinline__ bool next_producer(const TcArgs& a, volatile unsigned int* sched, uint64_t* sfull,
+                                                  uint64_t* sempty) {
+        if (a.ticket == nullptr) return next_static(a);
+        const unsigned int tau = atomicAdd(a.ticket, 1u);
+        mbar_wait(sempty + ss, sph ^ 1u);
+        sched[ss] = tau;
+        mbar_arrive(sfull + ss);
+        if (++ss == 2) { ss = 0; sph ^= 1u; }
+        return decode(tau);
+    }
+    // MMA issuer and epilogue warps (whole warp, converged)
+    __device__ __forceinline__ bool next_consumer(const TcArgs& a, volatile unsigned int* sched, uint64_t* sfull,
+                                                  uint64_t* sempty, int lane) {
+        if (a.ticket == nullptr) return next_static(a);
+        mbar_wait(sfull + ss, sph);
+        const unsigned int tau = sched[ss];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sempty + ss);
+        if (++ss == 2) { ss = 0; sph ^= 1u; }
+        return decode(tau);
+    }
+};
+
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
@@ -408,6 +465,9 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
     uint64_t* acc_empty = acc_full + NACC;           // [NACC]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
     int* sb = reinterpret_cast<int*>(tmem_slot + 2);  // [64] bucket table
+    uint64_t* sfull = reinterpret_cast<uint64_t*>(sb + 64);   // [2] ticket ring (dynamic window mode)
+    uint64_t* sempty = sfull + 2;                    // [2]
+    volatile unsigned int* sched = reinterpret_cast<volatile unsigned int*>(sempty + 2);   // [2]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -420,6 +480,7 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
         prefetch_tmap(&map_wh); prefetch_tmap(&map_wl); prefetch_tmap(&map_xh); prefetch_tmap(&map_xl);
         for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         for (int s = 0; s < NACC; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, Cfg::EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(sfull + s, 1); mbar_init(sempty + s, 1 + Cfg::EPI_WARPS); }
         fence_mbar_init();
     }
     constexpr int TMEM_COLS = NACC * BN;             // 512 / 256 / 128
@@ -437,10 +498,13 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
             uint32_t stage = 0, phase = 0;
             bool first = true;
             long long w_empty = 0, w_dep = 0, t_all = clock64();
-            for (int it = 0; it < a.steps; ++it) {
-                const CUtensorMap* mxh = (it & 1) ? &map_xh1 : &map_xh;
-                const CUtensorMap* mxl = (it & 1) ? &map_xl1 : &map_xl;
-                for (int u = tc_first_item(a, it); u < n_items; u += gridDim.x) {
+            TcWalk walk;
+            walk.init(n_items, a.steps);
+            {
+                while (walk.next_producer(a, sched, sfull, sempty)) {
+                    const int it = walk.it, u = walk.u;
+                    const CUtensorMap* mxh = (it & 1) ? &map_xh1 : &map_xh;
+                    const CUtensorMap* mxl = (it & 1) ? &map_xl1 : &map_xl;
                     int t, rank, rho, xrow, rt, wrow;
                     KIter ki;
                     if (!tc_item<BN>(sb, a, u, t, rank, rho, xrow, rt, wrow, ki)) break;
@@ -511,8 +575,10 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
         long long w_full = 0, w_acc = 0, t_all = clock64(), ntile = 0;
         grid_dep_wait();
-        for (int it = 0; it < a.steps; ++it)
-        for (int u = tc_first_item(a, it); u < n_items; u += gridDim.x) {
+        TcWalk walk;
+        walk.init(n_items, a.steps);
+        while (walk.next_consumer(a, sched, sfull, sempty, lane)) {
+            const int u = walk.u;
             int t, rank, rho, col0, rt, wrow;
             KIter ki;
             if (!tc_item<BN>(sb, a, u, t, rank, rho, col0, rt, wrow, ki)) break;
@@ -572,8 +638,10 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
         long long w_accf = 0, t_store = 0;
         grid_dep_wait();
         long long t_all = clock64();
-        for (int it = 0; it < a.steps; ++it)
-        for (int u = tc_first_item(a, it); u < n_items; u += gridDim.x) {
+        TcWalk walk;
+        walk.init(n_items, a.steps);
+        while (walk.next_consumer(a, sched, sfull, sempty, lane)) {
+            const int it = walk.it, u = walk.u;
             int t, rank, rho, col0, rt, wrow;
             KIter ki;
             if (!tc_item<BN>(sb, a, u, t, rank, rho, col0, rt, wrow, ki)) break;

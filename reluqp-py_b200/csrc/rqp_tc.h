@@ -32,6 +32,7 @@ struct TcArgs {
     int n_col_tiles, n_row_tiles, k_blocks;
     const unsigned long long* kmask;  // [n_rho][n_rt64] nonzero k-blocks per 64-row tile of W_rho, or null (all dense)
     int n_rt64;             // 64-row tiles per rho = ceil(D / 64)
+    unsigned int* ticket;   // window mode with more items than CTAs: global ticket counter (zeroed before the launch), else null
     int rot;                // window mode: rotation of the item -> CTA assignment per iteration (0 = fixed)
     unsigned long long* dbg;  // optional [16] cycle counters written by CTA 0 (diagnostics)
 };

@@ -214,6 +214,46 @@ def test_tc_window_kernel_is_bit_identical(monkeypatch):
             assert torch.equal(out["2"][3], out["0"][3]), (B, eng)
 
 
+def test_sparsity_map_and_ticket_scheduling_are_bit_identical(monkeypatch):
+    """The block sparsity map of W_rho (zero k-blocks of the lambda rows [R A, -R, I] are skipped: they only
+    add exact zeros), the ticket scheduling of the window kernel (work items drawn from a global counter
+    instead of a static tile -> CTA assignment) and the 64-column tiles of the single-wave regime change WHO
+    computes a tile and WHICH zero blocks it visits, never what is summed: results must be bit-identical to
+    the dense, statically scheduled kernels in fp32 (tcgen05) and in fp64 (DMMA), fixed-iteration runs and
+    full solves alike."""
+    monkeypatch.setenv("RQP_NO_KSPLIT", "1")     # split-K changes the summation order by design
+    plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+    L, U = plant.bounds(plant.sample_x0(2600))
+    prob = (plant.H, plant.g, plant.A, L[0], U[0])
+    switches = ("RQP_NO_KMASK", "RQP_NO_TICKET", "RQP_NO_ROTATE", "RQP_NO_NARROW")
+    for prec in (torch.float32, torch.float64):
+        mf = gpu_model(prob, precision=prec, adaptive_rho=False, max_iter=60)
+        ms = gpu_model(prob, precision=prec)
+        for B in (300, 1500, 2600):
+            out = {}
+            for mode in ("new", "rotated", "plain"):
+                for sw in switches:
+                    monkeypatch.delenv(sw, raising=False)
+                if mode == "rotated":
+                    monkeypatch.setenv("RQP_NO_TICKET", "1")
+                if mode == "plain":
+                    for sw in switches:
+                        monkeypatch.setenv(sw, "1")
+                mf._batch = None                  # the sparsity map is built once per engine: rebuild it
+                ms._batch = None
+                a = mf.solve_batch(L[:B], U[:B])
+                b = ms.solve_batch(L[:B], U[:B])
+                out[mode] = (torch.cat([a.x, a.z, a.lam], 1).clone(), b.iter.clone(),
+                             torch.cat([b.x, b.z, b.lam], 1).clone(), b.pri_res.clone(), b.dua_res.clone())
+                if mode == "new":       # the map exists and some 128-row tile really has zero blocks to skip
+                    assert mf._batch.kmask is not None
+                    assert 0 < mf._batch.kmask_min < (plant.H.shape[0] + 2 * plant.A.shape[0] + 31) // 32
+            for mode in ("rotated", "plain"):
+                for i in range(5):
+                    assert torch.equal(out["new"][i], out[mode][i]), (prec, B, mode, i)
+            assert bool(b.status_code.eq(0).all())
+
+
 def test_tc_split_k(monkeypatch):
     """Split-K of the tcgen05 kernels (fewer tiles than SMs: 2 / 4 / 8 CTAs share a tile's k-blocks, partial
     sums meet in a scratch buffer and are added in rank order by whichever rank arrives last): run-to-run

@@ -76,7 +76,34 @@ def run_batched(args, rank, world, dev):
     if rank != 0:
         return None
     peaks = measured_peaks()
-    achieved = sum(flops) / total_s / 1e12
+    whole = sum(flops) / total_s / 1e12
+    # The dominant kernel: the iteration GEMM of a FULL check window (every column active: 25 iterations of
+    # B columns; one cooperative launch of rqp_batched_tc_kernel in fp32, 25 launches of bgemm_dmma in fp64).
+    # Its duration is measured live by the library with CUDA events on the launching stream
+    # (rqp_batch.first_window_ms), outside the timed region above (the event wait would add a bubble there).
+    win_ms = []
+    if m._batch is not None:
+        m._batch.time_first_window = True
+        for _ in range(3):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            m.solve_batch(Ld, Ud, engine=args.batch_engine)
+            win_ms.append(m._batch.first_window_ms)
+        m._batch.time_first_window = False
+    ci = int(m.settings.check_interval)
+    win_flops = 2.0 * D * D * B * ci
+    win_s = (sum(win_ms) / len(win_ms)) * 1e-3 if win_ms and min(win_ms) > 0 else None
+    achieved = win_flops / win_s / 1e12 if win_s else whole
+    # share of W_rho's k-blocks the engines actually visit (sparsity map of the layer matrices, starting rho)
+    dense_frac = 1.0
+    km = getattr(m._batch, "kmask", None) if m._batch is not None else None
+    if km is not None:
+        kb = (D + 31) // 32
+        rows = km[m.rho_ind].cpu().numpy().astype(np.uint64)
+        if len(rows) % 2:
+            rows = np.concatenate([rows, np.zeros(1, dtype=np.uint64)])
+        per128 = rows[0::2] | rows[1::2]
+        dense_frac = float(sum(bin(int(v)).count("1") for v in per128)) / (len(per128) * kb)
     if dt == torch.float32:
         peak, peak_note = peaks["bf16_tflops_sustained"] / 2.0, \
             "TF32 dense = half of the measured sustained bf16 cuBLAS rate; 3xTF32 executes 3x the algorithmic flops"
@@ -84,6 +111,7 @@ def run_batched(args, rank, world, dev):
         peak, peak_note = 37.1, ("fp64 DMMA rate measured on a B200 of this pool with tools/ubench/fp64_rate.cu "
                                  "(no fp64 figure in MEASURED_PEAKS.json)")
     iters = res.iter.float()
+    mma_mult = 3.0 if dt == torch.float32 and args.batch_engine != 1 else 1.0
     line = dict(
         metric="qp_solves_per_sec", value=B * args.steps * world / float(tmax.item()), unit="solves/s",
         n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * float(tmax.item()) / args.steps,
@@ -98,12 +126,20 @@ def run_batched(args, rank, world, dev):
         iters_per_solve=float(iters.mean().item()), iters_max=int(iters.max().item()), sweeps=res.sweeps,
         all_solved=bool(res.status_code.eq(0).all().item()),
         roofline=dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
-                      traffic=None, peak_source=peaks["source"],
-                      executed=achieved * (3.0 if dt == torch.float32 and args.batch_engine != 1 else 1.0),
-                      executed_frac=achieved * (3.0 if dt == torch.float32 and args.batch_engine != 1 else 1.0) / peak,
-                      note=peak_note + "; achieved = ALGORITHMIC flops 2*D^2 per column-iteration actually run / "
-                      "time over WHOLE solves (checks, regroups and the straggler tail included); executed = what "
-                      "the tensor pipe runs (3 TF32 MMAs per product)"),
+                      # dram__bytes_read.sum + dram__bytes_write.sum of one window launch, ncu --set full
+                      traffic=(473.8e6 + 679.2e6) if (B == 4096 and dt == torch.float32 and args.batch_engine == 0) else None,
+                      traffic_source="profiles/r01d_batched_window_ncu_full.csv" if (B == 4096 and dt == torch.float32 and args.batch_engine == 0) else None,
+                      peak_source=peaks["source"],
+                      kernel="one full check window ({} iterations x {} columns) of the iteration GEMM".format(ci, B),
+                      launch_ms=1e3 * win_s if win_s else None, flops_per_launch=win_flops,
+                      executed=achieved * mma_mult * dense_frac, executed_frac=achieved * mma_mult * dense_frac / peak,
+                      k_blocks_visited=dense_frac,
+                      whole_solve=whole, whole_solve_frac=whole / peak,
+                      note=peak_note + "; achieved = ALGORITHMIC flops 2*D^2 per column-iteration of one full check "
+                      "window / its launch duration (CUDA events on the launching stream, measured live); executed = "
+                      "what the tensor pipe runs (3 TF32 MMAs per product, all-zero k-blocks of W_rho skipped); "
+                      "whole_solve = algorithmic flops of every column-iteration / time of WHOLE solves (checks, "
+                      "regroups and the straggler tail included)"),
         e2e=dict(value=B * args.steps * world / float(te.item()), unit="solves/s",
                  h2d_bytes_per_step=2 * B * nc * elem, d2h_bytes_per_step=B * nx * elem,
                  ms_per_step=1e3 * float(te.item()) / args.steps,

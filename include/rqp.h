@@ -198,6 +198,10 @@ typedef struct rqp_batch {
      * kmask_min_blocks = the fewest set bits any 128-row tile (two consecutive entries OR-ed) has. */
     const void* kmask;
     int32_t kmask_min_blocks;
+    /* Optional HOST pointer (NULL = off): receives the device time in milliseconds of the iteration GEMM
+     * launch(es) of the FIRST check window (every column still active), taken with CUDA events on the
+     * caller's stream -- the per-launch duration of the dominant kernel for roofline reporting. */
+    float* first_window_ms;
 } rqp_batch;
 
 int rqp_batch_workspace_size(const rqp_problem* prob, const rqp_settings* stng, int32_t B,

@@ -1115,6 +1115,14 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         // over K (short mainloops: the relaunch cost of one kernel per iteration would dominate; B = 32:
         // 5.1 -> 3.2 ms per solve).  With one unsplit tile per CTA the chain mainloop -> epilogue -> next
         // mainloop is serial either way and PDL launches are as fast.
+        // optional: device time of the first window's iteration launches (rqp_batch.first_window_ms)
+        const bool time_window = bt->first_window_ms != nullptr && k == 0;
+        cudaEvent_t ev_w0 = nullptr, ev_w1 = nullptr;
+        if (time_window) {
+            RQP_CUDA_TRY(cudaEventCreate(&ev_w0));
+            RQP_CUDA_TRY(cudaEventCreate(&ev_w1));
+            RQP_CUDA_TRY(cudaEventRecord(ev_w0, st));
+        }
         const int n_rt128 = (D + 127) / 128;
         const int tiles_w = use_tc ? nact_host[3 - pick_bn(n_rt128, bt->engine)] * n_rt128 : 0;
         const bool window_pays = use_tc && (tiles_w > sm_count || pick_ksplit(tiles_w, nk_iter) > 1);
@@ -1137,6 +1145,15 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
             }
         }
         k += steps;
+        if (time_window) {
+            RQP_CUDA_TRY(cudaEventRecord(ev_w1, st));
+            RQP_CUDA_TRY(cudaEventSynchronize(ev_w1));
+            float ms = 0.f;
+            RQP_CUDA_TRY(cudaEventElapsedTime(&ms, ev_w0, ev_w1));
+            *bt->first_window_ms = ms;
+            cudaEventDestroy(ev_w0);
+            cudaEventDestroy(ev_w1);
+        }
         const double tw1 = trace_windows ? now_us() : 0.0;
         if (trace_windows) {
             cudaStreamSynchronize(st);

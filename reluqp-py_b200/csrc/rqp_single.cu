@@ -76,6 +76,7 @@ struct SingleParams {
     int backoff_ns; // sleep between failed exchange polls
     int prepoll_cycles;   // spin this many SM cycles after the CTA barrier before the first poll
     int exch_flags;       // bit 0: CTA barrier after the publish store (polls queue behind it)
+    int prepoll_adapt;    // 1: every warp tunes its own spin (additive increase on a failed first poll, slow decrease)
     int ring;             // 1: stream the slab through a shared-memory ring filled by bulk async copies
     int check_tpw;        // > 0: rows of A / H / A' each warp needs in a check are kept in shared memory
     int replicas;         // copies of the exchange cells; CTA c reads copy c % replicas (spreads the hot
@@ -643,6 +644,11 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
 
     if (__syncthreads_or(!ok)) aborted = true;
 
+    // Pre-poll spin, tuned per warp while the solve runs: a first poll that comes back without the flag costs a
+    // second L2 round trip (~800 cycles) and loads the L2 -> SM path for everybody, one that waits too long is
+    // pure idle time; the arrival time depends on the grid size, on where the CTAs sit and on the box.  Additive
+    // increase on a miss, slow decrease on a hit: settles just above the arrival time with a few per cent of misses.
+    int spin = p.prepoll_cycles;
     if (!aborted) {
         for (k = 1; k <= p.max_iter; ++k) {
             const long long tp0 = kTimers ? clock64() : 0;
@@ -666,6 +672,10 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                     if ((m & need[i]) != need[i]) pending |= 1u << i;
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) vv[i][e] = ((need[i] >> e) & 1u) ? out[e] : T(0);
+                }
+                if (RMODE && p.prepoll_adapt) {     // latency-bound sizes only: the large kernels sit at 255 registers
+                    const bool miss = __any_sync(0xffffffffu, pending != 0u);
+                    spin = miss ? min(spin + 96, 1500) : max(spin - 3, 0);
                 }
                 wd.arm();
                 while (pending != 0u && ok) {
@@ -768,8 +778,8 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                     C::publish(dst + size_t(rp) * rep_words, my_row, my_v, epoch + uint32_t(k));
             }
             if (p.exch_flags & 1) __syncthreads();
-            if (p.prepoll_cycles > 0) {
-                const long long t_until = tp3 + p.prepoll_cycles;
+            if (spin > 0) {
+                const long long t_until = tp3 + spin;
                 while (clock64() < t_until) {
                 }
             }
@@ -997,6 +1007,8 @@ int launch_single(const rqp_problem* prob, const rqp_settings* stng, rqp_state* 
     // and do best with 400 (13..79 CTAs) or 150 (a handful of CTAs).
     const int prepoll_default = plan.grid >= 80 ? 600 : (plan.grid > 8 ? 400 : 150);
     prm.prepoll_cycles = stng->prepoll_cycles == 0 ? prepoll_default : (stng->prepoll_cycles < 0 ? 0 : stng->prepoll_cycles);
+    // an explicit prepoll_cycles (or bit 1 of exchange_flags) pins the spin; the default adapts it per warp
+    prm.prepoll_adapt = (stng->prepoll_cycles == 0 && (stng->exchange_flags & 2) == 0) ? 1 : 0;
     prm.exch_flags = stng->exchange_flags & 0xff;
     prm.ring = plan.ring;
     prm.check_tpw = plan.check_tpw;

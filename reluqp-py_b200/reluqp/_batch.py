@@ -153,6 +153,9 @@ class BatchEngine(object):
         km = self._block_mask()
         if km is not None:
             bt.kmask, bt.kmask_min_blocks = km.data_ptr(), self.kmask_min
+        win_ms = C.c_float(0.0)
+        if getattr(self, "time_first_window", False):     # bench: per-launch time of the dominant kernel
+            bt.first_window_ms = C.pointer(win_ms)
         self.dbg = None
         if getattr(self, "want_dbg", False):
             self.dbg = torch.zeros(16, dtype=torch.int64, device=dev)
@@ -169,6 +172,7 @@ class BatchEngine(object):
             _cabi.check(rc, "rqp_solve_batched")
             end.synchronize()
         self._keep = (L, U, G)
+        self.first_window_ms = float(win_ms.value)
         return BatchResults(x=V[:, :nx], z=V[:, nx:nx + nc], lam=V[:, nx + nc:D], iter=it, status_code=status,
                             pri_res=pri, dua_res=dua, rho_estimate=rho, rho_ind=rho_ind,
                             run_time=start.elapsed_time(end) / 1000.0, sweeps=int(sweeps.value))

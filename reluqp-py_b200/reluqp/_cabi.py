@@ -68,7 +68,8 @@ class rqp_batch(C.Structure):
                 ("rho_ind", C.c_void_p), ("iter", C.c_void_p), ("status", C.c_void_p),
                 ("pri_res", C.c_void_p), ("dua_res", C.c_void_p), ("rho_estimate", C.c_void_p),
                 ("engine", C.c_int32), ("res_planes", C.c_int32), ("W_hi", C.c_void_p), ("W_lo", C.c_void_p),
-                ("reserved_dbg", C.c_void_p), ("kmask", C.c_void_p), ("kmask_min_blocks", C.c_int32)]
+                ("reserved_dbg", C.c_void_p), ("kmask", C.c_void_p), ("kmask_min_blocks", C.c_int32),
+                ("first_window_ms", C.POINTER(C.c_float))]
 
 
 _lib = None

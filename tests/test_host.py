@@ -177,7 +177,7 @@ def test_cabi_exports_match_header():
     assert ctypes.sizeof(_cabi.rqp_settings) == 80
     assert ctypes.sizeof(_cabi.rqp_problem) == 96
     assert ctypes.sizeof(_cabi.rqp_state) == 16
-    assert ctypes.sizeof(_cabi.rqp_batch) == 144
+    assert ctypes.sizeof(_cabi.rqp_batch) == 152
     # bad arguments are reported, not crashed on (no GPU needed: checks come first)
     assert lib.rqp_update_bias(1, 0, 0, 0, None, None, None, None) == -1
     assert lib.rqp_query(0, None) == -1

@@ -251,6 +251,36 @@ def test_launch_geometries_agree(golden):
             assert m.last_launch["phase_cycles"][7] == 1
 
 
+def test_check_rows_and_spin_policy_do_not_change_results(monkeypatch):
+    """Shared-memory residency of the residual-check rows (bulk copies at kernel start, RQP_NO_CHECK_SMEM=1
+    reads them from L2 as before), the per-warp adaptive pre-poll spin (exchange_flags bit 1 pins it) and the
+    number of exchange-cell replicas (exchange_flags >> 8) only change WHERE operands come from and WHEN polls
+    are issued: every variant must return bit-identical iterates, residuals and iteration counts, on a
+    register-resident problem (C2 plant) and on a small dense one with several checks per solve."""
+    plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+    L, U = plant.bounds(plant.sample_x0(3))
+    probs = [((plant.H, plant.g, plant.A, L[2], U[2]), {}),
+             (utils.rand_qp(60, 15, 15, seed=5, compute_sol=False)[:5], dict(eps_abs=1e-6))]
+    for prob, kw in probs:
+        out = []
+        for env, tune in ((None, {}), ("1", {}), (None, dict(exchange_flags=2)), (None, dict(exchange_flags=4 * 256)),
+                          (None, dict(prepoll_cycles=250))):
+            if env is None:
+                monkeypatch.delenv("RQP_NO_CHECK_SMEM", raising=False)
+            else:
+                monkeypatch.setenv("RQP_NO_CHECK_SMEM", env)
+            m = reluqpth.ReLU_QP()
+            m.setup(*prob, device="cuda", warm_starting=False, **kw, **tune)
+            r = m.solve()
+            out.append((r.info.iter, r.info.status, m.rho_ind, r.x.clone(), r.z.clone(), float(r.info.pri_res),
+                        float(r.info.dua_res), float(r.info.obj_val)))
+        for o in out[1:]:
+            assert o[:3] == out[0][:3]
+            assert torch.equal(o[3], out[0][3]) and torch.equal(o[4], out[0][4])
+            assert o[5:] == out[0][5:]
+        assert out[0][1] == "solved"
+
+
 def test_bitwise_reproducible():
     prob = utils.rand_qp(87, 21, 21, seed=2, compute_sol=False)[:5]
     m = gpu_model(prob, eps_abs=1e-6, warm_starting=False)

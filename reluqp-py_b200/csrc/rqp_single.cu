@@ -33,12 +33,6 @@
 
 namespace rqp {
 
-#ifndef RQP_V_STAGE
-#define RQP_V_STAGE 0
-#endif
-#ifndef RQP_V_AG
-#define RQP_V_AG 0
-#endif
 #ifndef RQP_V_CHKTIME
 #define RQP_V_CHKTIME 0     // diagnostics: the phase counters time the steps of the residual check instead
 #endif
@@ -380,20 +374,20 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
 
     // Residual evaluation on v_k (flag fk in vcells buffer k&1).  final_pass: no index move, no
     // termination test (reluqpth.py:243).  Returns false on watchdog abort (uniform over the CTA).
-    auto residual_pass = [&](int kk, uint32_t pflag, bool final_pass) -> bool {
+    auto residual_pass = [&](int kk, uint32_t pflag, bool final_pass, bool staged) -> bool {
         const uint64_t* vslot = my_cells + size_t(kk & 1) * nvec * 4;
         const uint32_t fk = epoch + uint32_t(kk);
-        bool good = true;
+        bool good = ok;
 #if RQP_V_CHKTIME
         long long ct0 = clock64();
 #define CHK_MARK(i) do { const long long n__ = clock64(); ph[i] += n__ - ct0; ct0 = n__; } while (0)
 #else
 #define CHK_MARK(i) do { } while (0)
 #endif
-        // 1. stage v_k into shared memory
-#if RQP_V_STAGE == 0
+        // 1. stage v_k into shared memory (unless the caller already did: the register-resident kernels gather
+        //    their own columns of v_k once, for this check AND for iteration k + 1)
         wd.arm();
-        for (int c = tid; c < nvec; c += NT) {
+        for (int c = tid; c < nvec && !staged; c += NT) {
             const int nval = max(0, min(VEC, D - c * VEC));
             const uint32_t nd = (1u << nval) - 1u;
             T out[VEC];
@@ -409,46 +403,6 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
 #pragma unroll
             for (int e = 0; e < VEC; ++e) vs[c * VEC + e] = ((nd >> e) & 1u) ? out[e] : T(0);
         }
-#else
-        // the loads of SQ columns a thread stages are issued together (one L2 round trip), columns whose
-        // flags have not arrived yet are polled again
-        constexpr int SQ = RQP_V_STAGE == 1 ? 2 : 4;
-        wd.arm();
-        for (int c0 = tid; c0 < nvec; c0 += SQ * NT) {
-            uint64_t w[SQ][4];
-            uint32_t pend = 0;
-#pragma unroll
-            for (int q = 0; q < SQ; ++q) {
-                const int c = c0 + q * NT;
-                if (c < nvec) {
-                    ld_relaxed_u64x2(vslot + size_t(c) * 4, w[q][0], w[q][1]);
-                    ld_relaxed_u64x2(vslot + size_t(c) * 4 + 2, w[q][2], w[q][3]);
-                    pend |= 1u << q;
-                }
-            }
-            while (pend != 0u && good) {
-#pragma unroll
-                for (int q = 0; q < SQ; ++q) {
-                    if (pend & (1u << q)) {
-                        const int c = c0 + q * NT;
-                        const int nval = max(0, min(VEC, D - c * VEC));
-                        const uint32_t nd = (1u << nval) - 1u;
-                        T out[VEC];
-                        const uint32_t m = C::unpack(w[q], fk, out);
-                        if ((m & nd) == nd) {
-#pragma unroll
-                            for (int e = 0; e < VEC; ++e) vs[c * VEC + e] = ((nd >> e) & 1u) ? out[e] : T(0);
-                            pend &= ~(1u << q);
-                        } else {
-                            ld_relaxed_u64x2(vslot + size_t(c) * 4, w[q][0], w[q][1]);
-                            ld_relaxed_u64x2(vslot + size_t(c) * 4 + 2, w[q][2], w[q][3]);
-                        }
-                    }
-                }
-                if (pend != 0u && wd.expired()) good = false;
-            }
-        }
-#endif
         if (__syncthreads_or(!good)) return false;
         CHK_MARK(0);
 
@@ -481,12 +435,12 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 m2 = nanmax(m2, absval(zi));
             } else {
                 const int ii = i - nc;
+                const T gi = __ldg(gv + ii);      // issued before the dot products: its L2 latency hides behind them
                 T t2, t3;
                 if (p.check_tpw > 0)
                     warp_row_dot2<T, false>(crw, xs, nx, crw + nx, ls, nc, lane, t2, t3);
                 else
                     warp_row_dot2<T, true>(Hm + size_t(ii) * nx, xs, nx, ATm + size_t(ii) * nc, ls, nc, lane, t2, t3);
-                const T gi = __ldg(gv + ii);
                 m3 = nanmax(m3, absval((t2 + t3) + gi));
                 m4 = nanmax(m4, absval(t2));
                 m5 = nanmax(m5, absval(t3));
@@ -517,7 +471,6 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
             const int q = tid & 7;
             double a = 0.0;
             wd.arm();
-#if RQP_V_AG == 0
             for (int c = tid >> 3; c < G; c += NT / 8) {
                 double val = 0.0;
                 while (good) {
@@ -531,45 +484,6 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 }
                 a = (q == 7) ? (a + val) : nanmax(a, val);
             }
-#else
-            // the cells of up to AQ CTAs are requested together (one L2 round trip instead of one per CTA),
-            // late ones are polled again; the fold order (ascending CTA index) does not depend on arrival
-            constexpr int AQ = 5;     // G <= 148 CTAs, NT / 8 >= 32 per pass
-            for (int cb = tid >> 3; cb < G; cb += AQ * (NT / 8)) {
-                uint64_t w0[AQ], w1[AQ];
-                uint32_t pend = 0;
-#pragma unroll
-                for (int j = 0; j < AQ; ++j) {
-                    const int c = cb + j * (NT / 8);
-                    if (c < G) {
-                        ld_relaxed_u64x2(pslot + (size_t(c) * 8 + q) * 2, w0[j], w1[j]);
-                        pend |= 1u << j;
-                    }
-                }
-                const uint32_t have = pend;
-                while (pend != 0u && good) {
-#pragma unroll
-                    for (int j = 0; j < AQ; ++j) {
-                        if (pend & (1u << j)) {
-                            if (uint32_t(w0[j] >> 32) == pflag && uint32_t(w1[j] >> 32) == pflag) {
-                                pend &= ~(1u << j);
-                            } else {
-                                const int c = cb + j * (NT / 8);
-                                ld_relaxed_u64x2(pslot + (size_t(c) * 8 + q) * 2, w0[j], w1[j]);
-                            }
-                        }
-                    }
-                    if (pend != 0u && wd.expired()) good = false;
-                }
-#pragma unroll
-                for (int j = 0; j < AQ; ++j) {
-                    if (have & (1u << j)) {
-                        const double val = __longlong_as_double((long long)((w0[j] & 0xffffffffull) | (w1[j] << 32)));
-                        a = (q == 7) ? (a + val) : nanmax(a, val);
-                    }
-                }
-            }
-#endif
             // lanes with equal (lane & 7) hold the same quantity
             double o8 = __shfl_xor_sync(0xffffffffu, a, 8);
             a = (q == 7) ? (a + o8) : nanmax(a, o8);
@@ -649,57 +563,65 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
     // pure idle time; the arrival time depends on the grid size, on where the CTAs sit and on the box.  Additive
     // increase on a miss, slow decrease on a hit: settles just above the arrival time with a few per cent of misses.
     int spin = p.prepoll_cycles;
+    // Gather the owned vector columns of v_kk into registers: all loads are issued together, columns whose
+    // flags have not arrived yet are polled again.
+    T vv[CPT][VEC];
+    bool have_vv = false;
+    auto gather = [&](int kk) {
+        const uint64_t* vslot = my_cells + size_t(kk & 1) * nvec * 4;
+        const uint32_t fprev = epoch + uint32_t(kk);
+        {
+            uint64_t w[CPT][4];
+            uint32_t pending = 0;
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) {
+                const uint64_t* cp = vslot + size_t(coff[i] / VEC) * 4;
+                ld_relaxed_u64x2(cp, w[i][0], w[i][1]);
+                ld_relaxed_u64x2(cp + 2, w[i][2], w[i][3]);
+            }
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) {
+                T out[VEC];
+                const uint32_t m = C::unpack(w[i], fprev, out);
+                if ((m & need[i]) != need[i]) pending |= 1u << i;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) vv[i][e] = ((need[i] >> e) & 1u) ? out[e] : T(0);
+            }
+            if (RMODE && p.prepoll_adapt) {     // latency-bound sizes only: the large kernels sit at 255 registers
+                const bool miss = __any_sync(0xffffffffu, pending != 0u);
+                spin = miss ? min(spin + 96, 1500) : max(spin - 3, 0);
+            }
+            wd.arm();
+            while (pending != 0u && ok) {
+                if (kTimers) ph[5] += 1;
+                if (p.backoff_ns > 0) __nanosleep(p.backoff_ns);
+#pragma unroll
+                for (int i = 0; i < CPT; ++i) {
+                    if (pending & (1u << i)) {
+                        const uint64_t* cp = vslot + size_t(coff[i] / VEC) * 4;
+                        uint64_t ww[4];
+                        ld_relaxed_u64x2(cp, ww[0], ww[1]);
+                        ld_relaxed_u64x2(cp + 2, ww[2], ww[3]);
+                        T out[VEC];
+                        const uint32_t m = C::unpack(ww, fprev, out);
+                        if ((m & need[i]) == need[i]) {
+                            pending &= ~(1u << i);
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) vv[i][e] = ((need[i] >> e) & 1u) ? out[e] : T(0);
+                        }
+                    }
+                }
+                if (pending != 0u && wd.expired()) ok = false;
+            }
+        }
+
+    };
     if (!aborted) {
         for (k = 1; k <= p.max_iter; ++k) {
             const long long tp0 = kTimers ? clock64() : 0;
-            // ---- gather the owned columns of v_{k-1}
-            const uint64_t* vslot = my_cells + size_t((k - 1) & 1) * nvec * 4;
-            const uint32_t fprev = epoch + uint32_t(k - 1);
-            T vv[CPT][VEC];
-            {
-                uint64_t w[CPT][4];
-                uint32_t pending = 0;
-#pragma unroll
-                for (int i = 0; i < CPT; ++i) {
-                    const uint64_t* cp = vslot + size_t(coff[i] / VEC) * 4;
-                    ld_relaxed_u64x2(cp, w[i][0], w[i][1]);
-                    ld_relaxed_u64x2(cp + 2, w[i][2], w[i][3]);
-                }
-#pragma unroll
-                for (int i = 0; i < CPT; ++i) {
-                    T out[VEC];
-                    const uint32_t m = C::unpack(w[i], fprev, out);
-                    if ((m & need[i]) != need[i]) pending |= 1u << i;
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) vv[i][e] = ((need[i] >> e) & 1u) ? out[e] : T(0);
-                }
-                if (RMODE && p.prepoll_adapt) {     // latency-bound sizes only: the large kernels sit at 255 registers
-                    const bool miss = __any_sync(0xffffffffu, pending != 0u);
-                    spin = miss ? min(spin + 96, 1500) : max(spin - 3, 0);
-                }
-                wd.arm();
-                while (pending != 0u && ok) {
-                    if (kTimers) ph[5] += 1;
-                    if (p.backoff_ns > 0) __nanosleep(p.backoff_ns);
-#pragma unroll
-                    for (int i = 0; i < CPT; ++i) {
-                        if (pending & (1u << i)) {
-                            const uint64_t* cp = vslot + size_t(coff[i] / VEC) * 4;
-                            uint64_t ww[4];
-                            ld_relaxed_u64x2(cp, ww[0], ww[1]);
-                            ld_relaxed_u64x2(cp + 2, ww[2], ww[3]);
-                            T out[VEC];
-                            const uint32_t m = C::unpack(ww, fprev, out);
-                            if ((m & need[i]) == need[i]) {
-                                pending &= ~(1u << i);
-#pragma unroll
-                                for (int e = 0; e < VEC; ++e) vv[i][e] = ((need[i] >> e) & 1u) ? out[e] : T(0);
-                            }
-                        }
-                    }
-                    if (pending != 0u && wd.expired()) ok = false;
-                }
-            }
+            // ---- gather the owned columns of v_{k-1} (already in registers right after a check)
+            if (!have_vv) gather(k - 1);
+            have_vv = false;
 
             const long long tp1 = kTimers ? clock64() : 0;
             // ---- slab GEMV, 8 rows per chunk
@@ -791,7 +713,22 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
 
             // ---- residual check (reluqpth.py:218)
             if (p.adaptive && (k % p.check_interval) == 0) {
-                const bool good = residual_pass(k, epoch + uint32_t(k), false);
+                bool staged = false;
+                if (RMODE) {
+                    // one gather of v_k serves the check (through shared memory) and iteration k + 1 (registers)
+                    gather(k);
+                    have_vv = true;
+#pragma unroll
+                    for (int i = 0; i < CPT; ++i) {
+                        const int c = tid + i * NT;
+                        if (c < nvec) {
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) vs[c * VEC + e] = vv[i][e];
+                        }
+                    }
+                    staged = true;     // a watchdog expiry in gather() reaches the pass through `ok` (uniform exit there)
+                }
+                const bool good = residual_pass(k, epoch + uint32_t(k), false, staged);
                 if (kTimers) ph[4] += clock64() - tp4;
                 if (!good) { aborted = true; break; }
                 if (solved) break;
@@ -802,7 +739,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
 
     // ---- max_iter fall-through: residuals of the last iterate, no index move (reluqpth.py:243)
     if (!solved && !aborted) {
-        if (!residual_pass(k, epoch + uint32_t(p.max_iter) + 1u, true)) aborted = true;
+        if (!residual_pass(k, epoch + uint32_t(p.max_iter) + 1u, true, false)) aborted = true;
     }
 
     if (p.ring) ring_drain();   // no bulk copy may still target this CTA's shared memory at exit

@@ -23,6 +23,9 @@ def run_batched(args, rank, world, dev):
     plant.rng = np.random.RandomState(1000 + rank)          # every rank draws its own initial states
     X0 = plant.sample_x0(B)
     L, U = plant.bounds(X0)
+    # the caller's arrays are in the solver's dtype (e2e copies exactly h2d_bytes_per_step below)
+    np_dt = np.float32 if dt == torch.float32 else np.float64
+    L, U = np.ascontiguousarray(L, dtype=np_dt), np.ascontiguousarray(U, dtype=np_dt)
     m = reluqpth.ReLU_QP()
     m.setup(plant.H, plant.g, plant.A, L[0], U[0], device=dev, precision=dt, warm_starting=False)
     nx, nc = m.QP.nx, m.QP.nc

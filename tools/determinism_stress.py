@@ -37,3 +37,9 @@ stress("nx85 per-col g, ksplit nowin ", 150, mk85, lambda m: m.solve_batch(L, U,
 stress("nx85 shared g, default       ", 150, mk85, lambda m: m.solve_batch(L, U))
 stress("mpc 300 default              ", 100, mkmpc, lambda m: m.solve_batch(Lm, Um))
 stress("mpc 300 no ksplit, window 2  ", 100, mkmpc, lambda m: m.solve_batch(Lm, Um), RQP_NO_KSPLIT="1", RQP_WINDOW="2")
+# ticket-scheduled window kernel (work items drawn from a global counter: WHO computes a tile varies from run to
+# run, the sums must not): full batches on 128-column tiles, and the single-wave regime on 64-column tiles
+Lb, Ub = plant.bounds(plant.sample_x0(4096))
+stress("mpc 4096 ticket (128 wide)   ", 40, mkmpc, lambda m: m.solve_batch(Lb, Ub))
+stress("mpc 2000 ticket (64 wide)    ", 40, mkmpc, lambda m: m.solve_batch(Lb[:2000], Ub[:2000]))
+stress("mpc 4096 ticket, no ksplit   ", 40, mkmpc, lambda m: m.solve_batch(Lb, Ub), RQP_NO_KSPLIT="1")

@@ -33,6 +33,9 @@
 
 namespace rqp {
 
+#ifndef RQP_V_HALFPOLL
+#define RQP_V_HALFPOLL 0
+#endif
 #ifndef RQP_V_CHKTIME
 #define RQP_V_CHKTIME 0     // diagnostics: the phase counters time the steps of the residual check instead
 #endif
@@ -577,7 +580,11 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
             for (int i = 0; i < CPT; ++i) {
                 const uint64_t* cp = vslot + size_t(coff[i] / VEC) * 4;
                 ld_relaxed_u64x2(cp, w[i][0], w[i][1]);
+#if RQP_V_HALFPOLL      // timing experiment only (wrong results): fetch half of every column's cells
+                w[i][2] = w[i][0]; w[i][3] = w[i][1];
+#else
                 ld_relaxed_u64x2(cp + 2, w[i][2], w[i][3]);
+#endif
             }
 #pragma unroll
             for (int i = 0; i < CPT; ++i) {

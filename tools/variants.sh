@@ -10,5 +10,5 @@ build() { tag=$1; shift
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/variants/librqp_$tag.so build/variants/single_$tag.o build/rqp_batched.o build/rqp_batched_tc.o build/rqp_abi.o -lcudart_static -lpthread -ldl -lrt
   grep -A2 "IdLi2ELi256ELb1" build/variants/single_$tag.log | grep -o "Used [0-9]* registers\|[0-9]* bytes spill stores" | tr '\n' ' '; echo " <- $tag"; }
 build base &
-build chktime -DRQP_V_CHKTIME=1 &
+build halfpoll -DRQP_V_HALFPOLL=1 &
 wait

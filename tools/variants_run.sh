@@ -10,6 +10,7 @@ for so in reluqp-py_b200/build/variants/librqp_*.so; do
   for nosm in "" 1; do
     RQP_NO_CHECK_SMEM=$nosm
     if [ -n "$nosm" ]; then export RQP_NO_CHECK_SMEM; else unset RQP_NO_CHECK_SMEM; fi
+    if [ -n "$PROBE" ]; then echo "$tag: $(python $PROBE 2>&1 | tr "\n" " ")" >> gpurun_out/variants.txt; continue; fi
     python bench.py --steps 200 --warmup 5 --no-cpu-baseline --no-extras $EXTRA 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])

@@ -473,9 +473,9 @@ def run_single(args, rank, world, dev):
         roofline=dict(bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s",
                       frac=achieved / peaks["hbm_gbs"],
                       # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full,
-                      # profiles/r01_single_mpc_ncu_full.csv (mean of the two captured launches)
+                      # profiles/r01d_single_mpc_ncu_full.csv (mean of the two captured launches)
                       traffic=28.4e6 if args.workload == "mpc_single" else None,
-                      traffic_source="profiles/r01_single_mpc_ncu_full.csv" if args.workload == "mpc_single" else None,
+                      traffic_source="profiles/r01d_single_mpc_ncu_full.csv" if args.workload == "mpc_single" else None,
                       peak_source=peaks["source"],
                       note="HBM-equivalent: W_rho stays in shared memory / L2 across iterations, so achieved "
                            "can exceed the DRAM copy peak; algorithmic bytes = s*(D^2+3D+2nc) per iteration "

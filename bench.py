@@ -295,10 +295,11 @@ def main():
                     others[wname]["roofline"] = {k: v for k, v in d["roofline"].items() if k != "note"}
                 except Exception as exc:  # extras must never break the headline line
                     others[wname] = {"error": repr(exc)}
-            try:
-                others["mpc_closed_loop"] = closed_loop_mpc(dev)
-            except Exception as exc:
-                others["mpc_closed_loop"] = {"error": repr(exc)}
+            for key, fused in (("mpc_closed_loop", False), ("mpc_closed_loop_fused", True)):
+                try:
+                    others[key] = closed_loop_mpc(dev, fused=fused)
+                except Exception as exc:
+                    others[key] = {"error": repr(exc)}
             line["other_workloads"] = others
         print(json.dumps(line))
     if world > 1:
@@ -306,7 +307,7 @@ def main():
         dist2.destroy_process_group()
 
 
-def closed_loop_mpc(dev, n_steps=200):
+def closed_loop_mpc(dev, n_steps=200, fused=False):
     """SURVEY 8(f)-1, the real MPC use: simulate the plant, and at every control step call
     update(l=, u=) with the new initial state and a WARM-started solve (state and rho index carried
     over, reluqpth.py:159-183 + :304-305), apply u_0.  Public API, numpy in, x on the host out."""
@@ -323,13 +324,18 @@ def closed_loop_mpc(dev, n_steps=200):
     t0 = time.perf_counter()
     for k in range(n_steps):
         l, u = plant.bounds(x)
-        m.update(l=l, u=u)
-        res = m.solve()
-        w = res.x.cpu().numpy()
+        if fused:                       # additive API: update + warm solve + x to the host in one library call
+            res = m.resolve(l=l, u=u)
+            w = res.x_host
+        else:
+            m.update(l=l, u=u)
+            res = m.solve()
+            w = res.x.cpu().numpy()
         iters.append(res.info.iter)
         x = plant.Ad @ x + plant.Bd @ w[:plant.nu] + 0.01 * rng.randn(plant.nx)
     dt = time.perf_counter() - t0
     return dict(value=n_steps / dt, unit="control steps/s (update + warm solve + x to host)", steps=n_steps,
+                api="ReLU_QP.resolve(l=, u=)" if fused else "ReLU_QP.update(l=, u=); solve(); x.cpu()",
                 ms_per_step=1e3 * dt / n_steps, iters_per_solve=sum(iters) / len(iters), iters_max=max(iters),
                 dtype="f64", note="closed loop with process noise; warm start carries v and rho index")
 

@@ -219,6 +219,25 @@ int rqp_solve_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_bat
  * binding needs no second CUDA library.
  */
 int rqp_copy_h2d(void* dst_dev, const void* src_host, size_t bytes, void* stream);
+
+/*
+ * MPC re-solve in ONE call (the loop around reluqpth.py:159-183 + :201-249 that a controller runs at
+ * every control step: update(g, l, u) then a warm-started solve(), then the solution to the host):
+ *   1. copy `vec_bytes` bytes of staged problem vectors from (pinned) host memory `vec_host` to the device
+ *      buffer `vec_dev` (the caller keeps g, l, u contiguous, so any sub-span of them is one copy; 0 = none);
+ *   2. if `g_changed`, refresh all biases b_rho = B_rho g (Bmat = [n_rho][D][nx], as rqp_update_bias);
+ *   3. solve as rqp_solve does (state / result / workspace / trace as there);
+ *   4. copy the first `out_bytes` bytes of the state vector to (pinned) host memory `out_host` (0 = none);
+ *   5. wait for the stream.
+ * Same results as the separate calls; saves their per-call host overhead (4 library calls and a framework
+ * device->host copy become one call).
+ */
+int rqp_resolve(const rqp_problem* prob, const rqp_settings* stng, rqp_state* state,
+                rqp_result* result, double* trace_dev, int32_t trace_cap,
+                void* workspace, size_t workspace_bytes,
+                void* vec_dev, const void* vec_host, size_t vec_bytes,
+                int32_t g_changed, const void* Bmat,
+                void* out_host, size_t out_bytes, void* stream);
 int rqp_stream_sync(void* stream);
 
 /*

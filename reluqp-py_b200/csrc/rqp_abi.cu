@@ -162,6 +162,33 @@ int rqp_copy_h2d(void* dst_dev, const void* src_host, size_t bytes, void* stream
     return RQP_OK;
 }
 
+int rqp_resolve(const rqp_problem* prob, const rqp_settings* stng, rqp_state* state, rqp_result* result,
+                double* trace_dev, int32_t trace_cap, void* workspace, size_t workspace_bytes, void* vec_dev,
+                const void* vec_host, size_t vec_bytes, int32_t g_changed, const void* Bmat, void* out_host,
+                size_t out_bytes, void* stream) {
+    if (!prob || !stng || !state || !state->v) return RQP_ERR_BAD_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (vec_bytes > 0) {
+        if (!vec_dev || !vec_host) return RQP_ERR_BAD_ARG;
+        RQP_CUDA_TRY(cudaMemcpyAsync(vec_dev, vec_host, vec_bytes, cudaMemcpyHostToDevice, st));
+    }
+    if (g_changed) {
+        const int rc = rqp_update_bias(prob->dtype, prob->n_rho, prob->nx + 2 * prob->nc, prob->nx, Bmat, prob->g,
+                                       const_cast<void*>(prob->b), stream);
+        if (rc != RQP_OK) return rc;
+    }
+    const int rc = rqp_solve(prob, stng, state, result, trace_dev, trace_cap, workspace, workspace_bytes, stream);
+    if (rc != RQP_OK) return rc;
+    if (out_bytes > 0) {
+        if (!out_host) return RQP_ERR_BAD_ARG;
+        const size_t elem = prob->dtype == RQP_F64 ? 8 : 4;
+        if (out_bytes > elem * size_t(prob->nx + 2 * prob->nc)) return RQP_ERR_BAD_ARG;
+        RQP_CUDA_TRY(cudaMemcpyAsync(out_host, state->v, out_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    RQP_CUDA_TRY(cudaStreamSynchronize(st));
+    return RQP_OK;
+}
+
 int rqp_stream_sync(void* stream) {
     RQP_CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     return RQP_OK;

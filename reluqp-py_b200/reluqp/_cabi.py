@@ -17,7 +17,7 @@ RQP_ERR_WATCHDOG = -6
 RQP_TRACE_STRIDE = 5
 EPOCH_LIMIT = 0x70000000
 
-EXPORTS = ("rqp_query", "rqp_workspace_size", "rqp_solve", "rqp_update_bias",
+EXPORTS = ("rqp_query", "rqp_workspace_size", "rqp_solve", "rqp_update_bias", "rqp_resolve",
            "rqp_batch_workspace_size", "rqp_solve_batched", "rqp_copy_h2d", "rqp_stream_sync",
            "rqp_probe_bandwidth",
            "rqp_strerror", "rqp_last_cuda_error")
@@ -91,6 +91,8 @@ def load():
     lib.rqp_solve.argtypes = [C.POINTER(rqp_problem), C.POINTER(rqp_settings), C.POINTER(rqp_state),
                               vp, vp, i32, vp, sz, vp]
     lib.rqp_update_bias.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.rqp_resolve.argtypes = [C.POINTER(rqp_problem), C.POINTER(rqp_settings), C.POINTER(rqp_state),
+                                vp, vp, i32, vp, sz, vp, vp, sz, i32, vp, vp, sz, vp]
     lib.rqp_batch_workspace_size.argtypes = [C.POINTER(rqp_problem), C.POINTER(rqp_settings), i32, C.POINTER(sz)]
     lib.rqp_solve_batched.argtypes = [C.POINTER(rqp_problem), C.POINTER(rqp_settings), C.POINTER(rqp_batch),
                                       vp, sz, C.POINTER(i32), vp]

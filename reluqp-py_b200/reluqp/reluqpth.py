@@ -497,6 +497,65 @@ class ReLU_QP(object):
                                 phase_cycles=[int(c) for c in r.phase_cycles])
         return self.results
 
+    def resolve(self, g=None, l=None, u=None):
+        """MPC re-solve: ``update(g, l, u)`` + ``solve()`` + the primal solution on the host, in ONE library
+        call (``rqp_resolve``: staged vectors host -> device, bias refresh when g changed, the solve kernel,
+        x device -> host, one stream wait).  Additive API for the loop a controller runs at every step
+        (the reference has only the separate calls, ``reluqpth.py:159-183`` and ``:201-249``); results are
+        identical to those calls.  Host (numpy / CPU tensor / sequence) vectors only.  Returns the usual
+        ``Results``; ``results.x_host`` is a numpy view of a pinned buffer holding x, valid until the next
+        ``resolve``."""
+        eng = self._engine
+        if eng is None:
+            raise RuntimeError("ReLU_QP.resolve needs a CUDA device; there is no CPU fallback")
+        st = self.settings
+        nx, nc = self.QP.nx, self.QP.nc
+        if any(torch.is_tensor(v) and v.device.type != "cpu" for v in (g, l, u)):
+            raise ValueError("resolve() takes host vectors; use update() + solve() for device tensors")
+        self._timer.tic_host()
+        spans = [sp for sp in (self._stage(0, nx, g) if g is not None else None,
+                               self._stage(nx, nx + nc, l) if l is not None else None,
+                               self._stage(nx + nc, nx + 2 * nc, u) if u is not None else None) if sp]
+        if len(spans) == 2 and spans[0][1] != spans[1][0]:      # g and u only: not one span, copy l along (unchanged)
+            self._glu_host[nx:nx + nc].copy_(self.QP.l)
+            spans = [(0, nx + 2 * nc)]
+        lo, hi = (min(a for a, _ in spans), max(b for _, b in spans)) if spans else (0, 0)
+        xh = getattr(self, "_x_host", None)
+        if xh is None or xh.numel() != nx or xh.dtype != st.precision:
+            xh = self._x_host = torch.zeros(nx, dtype=st.precision).pin_memory()
+            self._x_host_np = xh.numpy()
+        es = self._glu_es
+        eng._fill_settings()
+        if eng.epoch + eng.stng.max_iter + 2 > _cabi.EPOCH_LIMIT:
+            eng.ws.zero_()
+            eng.epoch = 1
+        eng.state.v = self.output.data_ptr()
+        eng.state.rho_ind = int(self.rho_ind)
+        eng.state.epoch = eng.epoch
+        if not eng.mapped:
+            raise RuntimeError("resolve() needs the mapped result record (RQP_RESULT_MAPPED=1)")
+        with torch.cuda.device(st.device):
+            rc = eng.lib.rqp_resolve(C.byref(eng.prob), C.byref(eng.stng), C.byref(eng.state),
+                                     eng.res_host.data_ptr(), None, 0, eng.ws.data_ptr(), eng.ws.numel(),
+                                     self._glu_ptr + lo * es, self._glu_host_ptr + lo * es, (hi - lo) * es,
+                                     1 if g is not None else 0, self.layers.B_all.data_ptr(),
+                                     xh.data_ptr(), nx * es, _cabi.raw_stream(st.device.index))
+        _cabi.check(rc, "rqp_resolve")
+        eng.epoch = int(eng.state.epoch)
+        self._glu_pending = False
+        r = eng.res_view
+        if r.error != 0:
+            eng.ws.zero_()
+            eng.epoch = 1
+            raise RuntimeError("rqp_resolve: {} (iter {})".format(eng.lib.rqp_strerror(r.error).decode(), r.iter))
+        self.results.info.update_time = 0.0          # folded into run_time: one call does both
+        self.rho_ind = int(r.rho_ind)
+        self.x, self.z, self.lam = self.output[:nx], self.output[nx:nx + nc], self.output[nx + nc:nx + 2 * nc]
+        self.results.x_host = self._x_host_np
+        self.update_results(iter=int(r.iter), status=STATUS_NAMES[int(r.status)], pri_res=r.pri_res,
+                            dua_res=r.dua_res, rho_estimate=r.rho_estimate, obj_val=r.obj_val)
+        return self.results
+
     def warm_start(self, x=None, z=None, lam=None, rho=None):
         """Warm start primal / dual variables and rho.  Unlike the reference (where x, z, lam are
         stored but never reach the state vector) the state IS seeded here."""

@@ -281,6 +281,39 @@ def test_check_rows_and_spin_policy_do_not_change_results(monkeypatch):
         assert out[0][1] == "solved"
 
 
+def test_resolve_equals_update_plus_solve():
+    """The fused MPC re-solve (one library call: staged vectors host -> device, bias refresh, solve, x to the
+    host) must return exactly what update() + solve() + x.cpu() return, step after step of a warm-started
+    closed loop, including steps that change g and cold-started solvers."""
+    plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+    rng = np.random.RandomState(3)
+    for warm in (True, False):
+        x0 = plant.sample_x0()
+        l, u = plant.bounds(x0)
+        ma, mb = reluqpth.ReLU_QP(), reluqpth.ReLU_QP()
+        for m in (ma, mb):
+            m.setup(plant.H, plant.g, plant.A, l, u, device="cuda", warm_starting=warm)
+        xa = xb = x0
+        for k in range(12):
+            la, ua = plant.bounds(xa)
+            g = plant.g + (0.01 * rng.randn(plant.g.shape[0]) if k in (3, 7) else 0.0)
+            kw = dict(l=la, u=ua)
+            if k in (3, 4, 7):          # change g (k = 3, 7), put it back (k = 4)
+                kw["g"] = g if k != 4 else plant.g
+            ma.update(**kw)
+            ra = ma.solve()
+            wa = ra.x.cpu().numpy()
+            ia, sa, pa = ra.info.iter, ra.info.status, float(ra.info.pri_res)
+            rb = mb.resolve(**kw)
+            wb = np.array(rb.x_host)
+            assert (rb.info.iter, rb.info.status, float(rb.info.pri_res)) == (ia, sa, pa), (warm, k)
+            assert np.array_equal(wa, wb), (warm, k)
+            assert torch.equal(ra.z, rb.z) and ma.rho_ind == mb.rho_ind
+            xa = plant.Ad @ xa + plant.Bd @ wa[:plant.nu]
+    with pytest.raises(ValueError):
+        mb.resolve(l=torch.zeros(plant.A.shape[0], device="cuda"))
+
+
 def test_bitwise_reproducible():
     prob = utils.rand_qp(87, 21, 21, seed=2, compute_sol=False)[:5]
     m = gpu_model(prob, eps_abs=1e-6, warm_starting=False)

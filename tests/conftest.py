@@ -18,6 +18,13 @@ GOLDEN = os.path.join(REPO, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the C-ABI library is built in-tree (git-ignored); a fresh checkout with nvcc builds it once here
+    lib = os.path.join(PKG, "lib", "librqp.so")
+    if not os.path.exists(lib):
+        import shutil
+        import subprocess
+        if shutil.which("nvcc") and shutil.which("make"):
+            subprocess.run(["make", "-C", PKG, "-j4"], check=False, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
 def pytest_collection_modifyitems(config, items):

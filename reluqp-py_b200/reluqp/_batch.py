@@ -16,6 +16,29 @@ from . import _cabi
 from .classes import BatchResults, to_tensor
 
 
+def layer_block_mask(W_all):
+    """Block sparsity map of the layer matrices ``W_all [n_rho, D, ld]``: one int64 (read as uint64 by the
+    library) per (rho, 64-row tile), bit kb set when that tile has a nonzero in columns [32 kb, 32 kb + 32).
+    The lambda rows of W_rho are ``[R A, -R, I]`` (``reluqpth.py:75``): off the diagonal their z and lambda
+    column blocks are exact zeros, which the engines then skip.  Returns ``(mask [n_rho, ceil(D/64)],
+    fewest set bits of any 128-row tile)`` or ``(None, 0)`` when D has more than 64 column blocks."""
+    n_rho, D, _ = W_all.shape
+    kb, rt = (D + 31) // 32, (D + 63) // 64
+    if kb > 64:
+        return None, 0
+    dev = W_all.device
+    nz = torch.zeros((n_rho, rt * 64, kb * 32), dtype=torch.bool, device=dev)
+    nz[:, :D, :D] = W_all[:, :, :D] != 0
+    blocks = nz.view(n_rho, rt, 64, kb, 32).any(dim=4).any(dim=2)          # [n_rho, rt, kb]
+    # bit 63 as the sign bit: the int64 sum is then the two's-complement image of the uint64 mask
+    weights = torch.tensor([1 << b if b < 63 else -(1 << 63) for b in range(kb)], dtype=torch.int64, device=dev)
+    mask = (blocks.to(torch.int64) * weights).sum(dim=2).contiguous()
+    pairs = torch.zeros((n_rho, (rt + 1) // 2 * 2, kb), dtype=torch.bool, device=dev)
+    pairs[:, :rt] = blocks
+    per128 = pairs.view(n_rho, -1, 2, kb).any(dim=2).sum(dim=2)
+    return mask, int(per128.min().item())
+
+
 class BatchEngine(object):
     """Per-solver batched engine: owns the workspace and output buffers for the largest batch seen."""
 
@@ -36,26 +59,10 @@ class BatchEngine(object):
         self.kmask_min = 0
 
     def _block_mask(self):
-        """Sparsity map of the layer matrices for the GEMM engines (``rqp_batch.kmask``): one uint64 per
-        (rho, 64-row tile), bit kb set when that tile has a nonzero in columns [32 kb, 32 kb + 32).  The
-        lambda rows of W_rho are ``[R A, -R, I]`` (``reluqpth.py:75``): off the diagonal their z and lambda
-        column blocks are exact zeros, which the engines then skip.  Computed once per setup; None when D
-        has more than 64 column blocks or ``RQP_NO_KMASK`` is set."""
+        """Sparsity map of the layer matrices for the GEMM engines (``rqp_batch.kmask``), computed once per
+        setup by ``layer_block_mask``; None when D has more than 64 column blocks or ``RQP_NO_KMASK`` is set."""
         if self.kmask is None and os.environ.get("RQP_NO_KMASK") is None:
-            W = self.solver.layers.W_all                      # [n_rho, D, ldw]
-            n_rho, D, _ = W.shape
-            kb, rt = (D + 31) // 32, (D + 63) // 64
-            if kb <= 64:
-                nz = torch.zeros((n_rho, rt * 64, kb * 32), dtype=torch.bool, device=W.device)
-                nz[:, :D, :D] = W[:, :, :D] != 0
-                blocks = nz.view(n_rho, rt, 64, kb, 32).any(dim=4).any(dim=2)          # [n_rho, rt, kb]
-                weights = torch.tensor([1 << b if b < 63 else -(1 << 63) for b in range(kb)], dtype=torch.int64,
-                                       device=W.device)
-                self.kmask = (blocks.to(torch.int64) * weights).sum(dim=2).contiguous()  # bit pattern as int64
-                pairs = torch.zeros((n_rho, (rt + 1) // 2 * 2, kb), dtype=torch.bool, device=W.device)
-                pairs[:, :rt] = blocks
-                per128 = pairs.view(n_rho, -1, 2, kb).any(dim=2).sum(dim=2)
-                self.kmask_min = int(per128.min().item())
+            self.kmask, self.kmask_min = layer_block_mask(self.solver.layers.W_all)
         return self.kmask
 
     def _tf32_planes(self):

@@ -254,6 +254,38 @@ def test_sparsity_map_and_ticket_scheduling_are_bit_identical(monkeypatch):
             assert bool(b.status_code.eq(0).all())
 
 
+def test_sparsity_map_at_64_column_blocks(monkeypatch):
+    """D = 2048 is the largest size the sparsity map covers: 64 column blocks, so bit 63 of the mask words is
+    live (the lambda rows' identity block sits in the last columns).  Fixed-iteration batched runs with and
+    without the map must agree bit for bit in fp32 (tcgen05) and fp64 (DMMA), and the map must really skip
+    blocks."""
+    monkeypatch.setenv("RQP_NO_KSPLIT", "1")
+    nx, ne, ni = 1024, 256, 256                      # nc = 512, D = 2048
+    H, g, A, l, u, _ = utils.rand_qp(nx, ne, ni, seed=11, compute_sol=False)
+    rng = np.random.RandomState(5)
+    B = 200
+    L = l[None, :] + 0.05 * rng.randn(B, l.shape[0])
+    U = np.where(np.isfinite(u)[None, :], L + (u - l)[None, :], np.inf)
+    for prec in (torch.float32, torch.float64):
+        m = gpu_model((H, g, A, l, u), precision=prec, adaptive_rho=False, max_iter=30)
+        out = {}
+        for mode in ("map", "dense"):
+            if mode == "dense":
+                monkeypatch.setenv("RQP_NO_KMASK", "1")
+            else:
+                monkeypatch.delenv("RQP_NO_KMASK", raising=False)
+            m._batch = None
+            r = m.solve_batch(L, U)
+            assert r.sweeps >= 0
+            out[mode] = torch.cat([r.x, r.z, r.lam], 1).clone()
+            if mode == "map":
+                assert m._batch.kmask is not None and 0 < m._batch.kmask_min < 64
+                assert bool((m._batch.kmask < 0).any())          # bit 63 set somewhere (int64 sign bit)
+        assert torch.isfinite(out["map"]).all()
+        assert torch.equal(out["map"], out["dense"]), prec
+    monkeypatch.delenv("RQP_NO_KMASK", raising=False)
+
+
 def test_tc_split_k(monkeypatch):
     """Split-K of the tcgen05 kernels (fewer tiles than SMs: 2 / 4 / 8 CTAs share a tile's k-blocks, partial
     sums meet in a scratch buffer and are added in rank order by whichever rank arrives last): run-to-run

@@ -181,3 +181,31 @@ def test_cabi_exports_match_header():
     # bad arguments are reported, not crashed on (no GPU needed: checks come first)
     assert lib.rqp_update_bias(1, 0, 0, 0, None, None, None, None) == -1
     assert lib.rqp_query(0, None) == -1
+
+
+def test_layer_block_mask_matches_brute_force():
+    """The sparsity map handed to the GEMM engines (rqp_batch.kmask): bit kb of entry (rho, t) <=> rows
+    [64 t, 64 t + 64) x columns [32 kb, 32 kb + 32) of W_rho hold a nonzero.  Checked against a plain loop,
+    including D = 2048 where bit 63 (the int64 sign bit) is in use, ragged D, and D > 2048 (no map)."""
+    from reluqp._batch import layer_block_mask
+    rng = np.random.RandomState(0)
+    for D, ld in ((2048, 2048), (2016, 2016), (130, 132), (30, 32)):
+        n_rho = 2
+        W = np.zeros((n_rho, D, ld))
+        kb, rt = (D + 31) // 32, (D + 63) // 64
+        want = np.zeros((n_rho, rt), dtype=np.uint64)
+        for r in range(n_rho):
+            for t in range(rt):
+                for b in rng.choice(kb, size=min(kb, 3), replace=False).tolist() + ([kb - 1] if t == 0 else []):
+                    i = min(64 * t + int(rng.randint(64)), D - 1)
+                    j = min(32 * b + int(rng.randint(32)), D - 1)
+                    W[r, i, j] = -0.5 if (i + j) % 2 else 3.0
+                    want[r, i // 64] |= np.uint64(1) << np.uint64(j // 32)
+        W[:, :, D:] = 7.0                                   # padding columns beyond D never count
+        mask, fewest = layer_block_mask(torch.as_tensor(W))
+        got = mask.numpy().view(np.uint64)
+        np.testing.assert_array_equal(got, want)
+        per128 = [bin(int(want[r, 2 * p]) | (int(want[r, 2 * p + 1]) if 2 * p + 1 < rt else 0)).count("1")
+                  for r in range(n_rho) for p in range((rt + 1) // 2)]
+        assert fewest == min(per128)
+    assert layer_block_mask(torch.zeros((1, 2080, 2080))) == (None, 0)

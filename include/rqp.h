@@ -93,7 +93,9 @@ typedef struct rqp_settings {
     int32_t block;              /* threads per CTA: 256 or 512                          */
     int32_t w_residency;        /* 0 auto, 1 force shared-memory resident, 2 force streamed
                                    with register loads, 3 force register resident, 4 force
-                                   streamed through the bulk-copy shared-memory ring     */
+                                   streamed through the bulk-copy shared-memory ring, 5 force
+                                   the single-CTA kernel (auto picks it for D <= 112 when
+                                   grid and block are 0)                                  */
     int32_t watchdog_ms;        /* 0 = 4000 ms per in-kernel wait                       */
     int32_t prepoll_cycles;     /* tuning: SM cycles to spin after the CTA barrier before the
                                    first exchange poll (0 = default 600, < 0 = none)      */

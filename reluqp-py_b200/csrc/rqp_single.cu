@@ -775,6 +775,233 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
     }
 }
 
+
+// =============================================================================================
+// Single-CTA kernel for small problems (D <= 16 * TR, TR <= 7: D <= 112).
+// A flagged-cell handoff between CTAs costs ~850 cycles on this chip whatever the problem size
+// (tools/ubench/pingpong.cu), so below D ~ 160 one CTA that keeps everything on chip beats any grid: the 256
+// threads form a 16 x 16 grid, thread (ty, tx) keeps the TR x TR register tile W_rho[ty + 16 i][tx + 16 j],
+// multiplies it into its TR entries of the state (shared memory), the 16 threads of a row group add their
+// partial sums with a 4-level butterfly inside a half warp, and iterations are ordered by __syncthreads.
+// Same semantics as the grid kernel (jit_forward :84-89 de-aliased, checks :218-241 with compute_residuals
+// :307-318, fall-through :243); only the summation order differs (fixed -> bit-reproducible).
+// =============================================================================================
+constexpr int TINY_NT = 256;
+
+template <typename T, int TR>
+__global__ void __launch_bounds__(TINY_NT, 1) rqp_tiny_kernel(const SingleParams p) {
+    constexpr int NW = TINY_NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ty = tid >> 4, tx = tid & 15;
+    const int D = p.D, nx = p.nx, nc = p.nc;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* vs = reinterpret_cast<T*>(smem_raw);                  // [2][D]
+    double* part = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(vs + 2 * D) + 15) & ~uintptr_t(15));  // [NW][8]
+    Decision* dec = reinterpret_cast<Decision*>(part + NW * 8);
+
+    const T* __restrict__ Wall = static_cast<const T*>(p.W);
+    const T* __restrict__ ball = static_cast<const T*>(p.b);
+    const T* __restrict__ rhos = static_cast<const T*>(p.rhos);
+    const T* __restrict__ Hm = static_cast<const T*>(p.H);
+    const T* __restrict__ Am = static_cast<const T*>(p.A);
+    const T* __restrict__ ATm = static_cast<const T*>(p.AT);
+    const T* __restrict__ gv = static_cast<const T*>(p.g);
+
+    int rho_ind = p.rho_ind0;
+    T rho = rhos[rho_ind];
+    // thread (ty, tx < TR) finalizes row ty + 16 tx (bias, clamp of the z rows, store)
+    const int fin_row = ty + 16 * tx;
+    const bool is_fin = tx < TR && fin_row < D;
+    T my_b = T(0), my_lo = -CUDART_INF, my_hi = CUDART_INF;
+    if (is_fin && fin_row >= nx && fin_row < nx + nc) {
+        my_lo = static_cast<const T*>(p.l)[fin_row - nx];
+        my_hi = static_cast<const T*>(p.u)[fin_row - nx];
+    }
+    for (int r = tid; r < D; r += TINY_NT) vs[r] = static_cast<const T*>(p.v)[r];      // v_0 in buffer 0
+    T w[TR][TR];
+    auto stage = [&](int ri) {
+        const T* Wg = Wall + size_t(ri) * D * p.ldw;
+#pragma unroll
+        for (int i = 0; i < TR; ++i)
+#pragma unroll
+            for (int j = 0; j < TR; ++j) {
+                const int r = ty + 16 * i, c = tx + 16 * j;
+                w[i][j] = (r < D && c < D) ? __ldg(Wg + size_t(r) * p.ldw + c) : T(0);
+            }
+        if (is_fin) my_b = ball[size_t(ri) * D + fin_row];
+    };
+    stage(rho_ind);
+    __syncthreads();
+
+    int k = 0, n_checks = 0, n_switch = 0;
+    bool solved = false;
+    T pri = CUDART_NAN, dua = CUDART_NAN, obj = CUDART_NAN;
+    uint64_t t_begin = 0;
+    if (tid == 0) t_begin = globaltimer_ns();
+
+    // residuals of the iterate in vs[buf] (reluqpth.py:307-318), rho step and termination test (:223-233)
+    auto residual_pass = [&](int kk, int buf, bool final_pass) {
+        const T* xs = vs + size_t(buf) * D;
+        const T* zs = xs + nx;
+        const T* ls = xs + nx + nc;
+        T m0 = T(0), m1 = T(0), m2 = T(0), m3 = T(0), m4 = T(0), m5 = T(0), m6 = T(0), osum = T(0);
+        for (int i = tid; i < nc + nx; i += TINY_NT) {
+            if (i < nc) {
+                const T* row = Am + size_t(i) * nx;
+                T a0 = T(0), a1 = T(0);
+                int j = 0;
+                for (; j + 1 < nx; j += 2) { a0 = fma(__ldg(row + j), xs[j], a0); a1 = fma(__ldg(row + j + 1), xs[j + 1], a1); }
+                if (j < nx) a0 = fma(__ldg(row + j), xs[j], a0);
+                const T t1 = a0 + a1, zi = zs[i];
+                m0 = nanmax(m0, absval(t1 - zi));
+                m1 = nanmax(m1, absval(t1));
+                m2 = nanmax(m2, absval(zi));
+            } else {
+                const int ii = i - nc;
+                const T* hr = Hm + size_t(ii) * nx;
+                const T* ar = ATm + size_t(ii) * nc;
+                const T gi = __ldg(gv + ii);
+                T a0 = T(0), a1 = T(0), c0 = T(0), c1 = T(0);
+                int j = 0;
+                for (; j + 1 < nx; j += 2) { a0 = fma(__ldg(hr + j), xs[j], a0); a1 = fma(__ldg(hr + j + 1), xs[j + 1], a1); }
+                if (j < nx) a0 = fma(__ldg(hr + j), xs[j], a0);
+                for (j = 0; j + 1 < nc; j += 2) { c0 = fma(__ldg(ar + j), ls[j], c0); c1 = fma(__ldg(ar + j + 1), ls[j + 1], c1); }
+                if (j < nc) c0 = fma(__ldg(ar + j), ls[j], c0);
+                const T t2 = a0 + a1, t3 = c0 + c1;
+                m3 = nanmax(m3, absval((t2 + t3) + gi));
+                m4 = nanmax(m4, absval(t2));
+                m5 = nanmax(m5, absval(t3));
+                m6 = nanmax(m6, absval(gi));
+                osum += xs[ii] * (T(0.5) * t2 + gi);
+            }
+        }
+        m0 = warp_nanmax(m0); m1 = warp_nanmax(m1); m2 = warp_nanmax(m2); m3 = warp_nanmax(m3);
+        m4 = warp_nanmax(m4); m5 = warp_nanmax(m5); m6 = warp_nanmax(m6); osum = warp_sum(osum);
+        if (lane == 0) {
+            double* pw = part + warp * 8;
+            pw[0] = double(m0); pw[1] = double(m1); pw[2] = double(m2); pw[3] = double(m3);
+            pw[4] = double(m4); pw[5] = double(m5); pw[6] = double(m6); pw[7] = double(osum);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double t[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                double a = part[q];
+                for (int ww = 1; ww < NW; ++ww) a = (q == 7) ? (a + part[ww * 8 + q]) : nanmax(a, part[ww * 8 + q]);
+                t[q] = a;
+            }
+            const T pr = T(t[0]), du = T(t[3]);
+            const T nprim = nanmax(T(t[1]), T(t[2]));
+            const T ndual = nanmax(nanmax(T(t[4]), T(t[5])), T(t[6]));
+            const T num = pr / nprim;
+            const T den = du / ndual;
+            const T rho_new = clamp_keep_nan(T(rho * t_sqrt(num / den)), T(p.rho_min), T(p.rho_max));
+            int ri = rho_ind, dn = 0;
+            if (!final_pass) {
+                const T cur = rhos[ri];
+                if (rho_new > cur * T(p.tol) && ri < p.n_rho - 1) ri += 1;
+                else if (rho_new < cur / T(p.tol) && ri > 0) ri -= 1;
+                T tp = T(p.thr_p), td = T(p.thr_d);
+                if (p.eps_rel != 0.0) {
+                    tp = tp + T(p.eps_rel) * nprim;
+                    td = td + T(p.eps_rel) * ndual;
+                }
+                dn = (pr < tp && du < td) ? 1 : 0;
+            }
+            dec->rho_ind = ri; dec->done = dn; dec->rho = double(rho_new);
+            dec->pri = double(pr); dec->dua = double(du); dec->obj = t[7];
+            if (p.trace != nullptr && n_checks < p.trace_cap) {
+                double* tr = p.trace + size_t(n_checks) * RQP_TRACE_STRIDE;
+                tr[0] = double(kk); tr[1] = double(ri); tr[2] = double(pr); tr[3] = double(du); tr[4] = double(rho_new);
+            }
+        }
+        __syncthreads();
+        rho = T(dec->rho); pri = T(dec->pri); dua = T(dec->dua); obj = T(dec->obj);
+        const int new_ri = dec->rho_ind;
+        solved = dec->done != 0;
+        n_checks += 1;
+        __syncthreads();                                     // dec / part may be rewritten by the next pass
+        if (new_ri != rho_ind && !solved) {
+            n_switch += 1;
+            stage(new_ri);
+        }
+        rho_ind = new_ri;
+    };
+
+    for (k = 1; k <= p.max_iter; ++k) {
+        const T* vo = vs + size_t((k - 1) & 1) * D;
+        T vc[TR], acc[TR];
+#pragma unroll
+        for (int j = 0; j < TR; ++j) {
+            const int c = tx + 16 * j;
+            vc[j] = c < D ? vo[c] : T(0);
+        }
+#pragma unroll
+        for (int i = 0; i < TR; ++i) {
+            T a = T(0);
+#pragma unroll
+            for (int j = 0; j < TR; ++j) a = fma(w[i][j], vc[j], a);
+            acc[i] = a;
+        }
+        // butterfly over the 16 threads of a row group (one half warp): every lane ends with the full sums
+#pragma unroll
+        for (int m = 8; m >= 1; m >>= 1) {
+#pragma unroll
+            for (int i = 0; i < TR; ++i) acc[i] += shfl_xor(acc[i], m);
+        }
+        T y = T(0);
+#pragma unroll
+        for (int i = 0; i < TR; ++i) y = (i == tx) ? acc[i] : y;
+        if (is_fin) vs[size_t(k & 1) * D + fin_row] = clamp_keep_nan(y + my_b, my_lo, my_hi);
+        __syncthreads();
+        if (p.adaptive && (k % p.check_interval) == 0) {
+            residual_pass(k, k & 1, false);
+            if (solved) break;
+        }
+    }
+    if (k > p.max_iter) k = p.max_iter;
+    if (!solved) residual_pass(k, k & 1, true);              // fall-through: no index move (reluqpth.py:243)
+
+    for (int r = tid; r < D; r += TINY_NT) static_cast<T*>(p.v)[r] = vs[size_t(k & 1) * D + r];
+    if (tid == 0) {
+        rqp_result r;
+        r.iter = k;
+        r.status = solved ? RQP_STATUS_SOLVED : RQP_STATUS_MAX_ITER;
+        r.rho_ind = rho_ind;
+        r.error = 0;
+        r.pri_res = double(pri); r.dua_res = double(dua); r.rho_estimate = double(rho); r.obj_val = double(obj);
+        r.n_checks = n_checks;
+        r.n_rho_switches = n_switch;
+        r.t_begin_ns = t_begin;
+        r.t_end_ns = globaltimer_ns();
+        r.grid = 1; r.block = TINY_NT; r.rows_per_cta = D; r.rows_in_smem = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.phase_cycles[i] = 0;
+        r.phase_cycles[7] = 1;                               // W lives in registers
+        *p.result = r;
+    }
+}
+
+constexpr int kTinyMaxD = 112;     // TR = 10 (D <= 160) spills at 255 registers and loses to the grid kernel
+// does the problem qualify for the single-CTA kernel?  (auto: no explicit grid / block / residency)
+static bool tiny_ok(const rqp_problem* prob, const rqp_settings* stng) {
+    const int D = prob->nx + 2 * prob->nc;
+    if (stng->grid != 0 || stng->block != 0 || (stng->w_residency != 0 && stng->w_residency != 5)) return false;
+    if (stng->w_residency != 5 && getenv("RQP_NO_TINY") != nullptr) return false;
+    return D <= kTinyMaxD;
+}
+template <typename T>
+static int launch_tiny(const SingleParams& prm, cudaStream_t stream) {
+    const size_t smem = size_t(2) * prm.D * sizeof(T) + 16 + (TINY_NT / 32) * 8 * sizeof(double) + sizeof(Decision) + 64;
+    if (prm.D <= 32) rqp_tiny_kernel<T, 2><<<1, TINY_NT, smem, stream>>>(prm);
+    else if (prm.D <= 64) rqp_tiny_kernel<T, 4><<<1, TINY_NT, smem, stream>>>(prm);
+    else if (prm.D <= 112) rqp_tiny_kernel<T, 7><<<1, TINY_NT, smem, stream>>>(prm);
+    else rqp_tiny_kernel<T, 10><<<1, TINY_NT, smem, stream>>>(prm);
+    RQP_CUDA_TRY(cudaGetLastError());
+    return RQP_OK;
+}
+
 // -------------------------------------------------------------------------------------------
 // Host side: launch geometry + dispatch.
 // -------------------------------------------------------------------------------------------
@@ -818,6 +1045,7 @@ int plan_single(const rqp_problem* prob, const rqp_settings* stng, const rqp_cap
     if (fixed + 1024 > cap) return RQP_ERR_UNSUPPORTED;
     long long fit = (long long)((cap - fixed - 256) / row_bytes);
     int rows_smem = int(fit < rpc ? fit : rpc);
+    if (stng->w_residency == 5 && !tiny_ok(prob, stng)) return RQP_ERR_UNSUPPORTED;
     if (stng->w_residency == 2) rows_smem = 0;
     if (rows_smem < rpc) rows_smem = rows_smem / RM * RM;
     if (stng->w_residency == 1 && rows_smem < rpc) return RQP_ERR_UNSUPPORTED;
@@ -918,6 +1146,7 @@ int launch_single(const rqp_problem* prob, const rqp_settings* stng, rqp_state* 
     if (state->epoch == 0 || state->epoch > 0x70000000u) return RQP_ERR_BAD_ARG;
     if ((reinterpret_cast<uintptr_t>(prob->W) & 15) || (reinterpret_cast<uintptr_t>(ws) & 255)) return RQP_ERR_BAD_ARG;
 
+    const bool tiny = tiny_ok(prob, stng);
     SingleParams prm;
     prm.W = prob->W; prm.b = prob->b; prm.H = prob->H; prm.A = prob->A; prm.AT = prob->AT;
     prm.g = prob->g; prm.l = prob->l; prm.u = prob->u; prm.rhos = prob->rhos;
@@ -965,6 +1194,12 @@ int launch_single(const rqp_problem* prob, const rqp_settings* stng, rqp_state* 
         prm.replicas = rep;
     }
 
+    if (tiny) {
+        // small problems: one CTA, everything on chip, no exchange (a plain launch: nothing to co-schedule)
+        rc = prob->dtype == RQP_F64 ? launch_tiny<double>(prm, stream) : launch_tiny<float>(prm, stream);
+        if (rc == RQP_OK) state->epoch += uint32_t(stng->max_iter) + 2u;
+        return rc;
+    }
     if (prob->dtype == RQP_F64) {
         rc = plan.block == 256 ? launch_cpt<double, 256>(prm, plan, stream) : launch_cpt<double, 512>(prm, plan, stream);
     } else {

@@ -76,7 +76,14 @@ def test_known_answer_settings(golden, name):
     m = gpu_model(known_answer_problem(), **gold["settings"])
     res = m.solve()
     check(m, res, gold)
-    assert m.rho_ind == gold["rho_ind_after"]
+    if gold["pri"] > 1e-12 or gold["dua"] > 1e-12:
+        assert m.rho_ind == gold["rho_ind_after"]
+    else:
+        # residuals at machine precision (ka_maxiter50_nosolve: pri 9e-16, dua 4e-14 at the second check): the rho
+        # estimate sqrt((pri/..)/(dua/..)) is rounding noise in the reference too, and whether it crosses the
+        # index threshold depends on the summation order of the kernel that ran (grid kernel: 5, single-CTA
+        # kernel: 6, reference: 5)
+        assert abs(m.rho_ind - gold["rho_ind_after"]) <= 1
 
 
 def test_cold_start_resets(golden):
@@ -312,6 +319,43 @@ def test_resolve_equals_update_plus_solve():
             xa = plant.Ad @ xa + plant.Bd @ wa[:plant.nu]
     with pytest.raises(ValueError):
         mb.resolve(l=torch.zeros(plant.A.shape[0], device="cuda"))
+
+
+def test_single_cta_kernel_matches_grid_kernel(monkeypatch):
+    """Problems with D <= 112 run in ONE CTA (register tiles of W_rho, no exchange); an explicit grid or
+    RQP_NO_TINY=1 sends them through the cooperative grid kernel.  Both must give the same iteration count,
+    status and rho index, and iterates that agree to summation-order rounding, at every tile size
+    (D <= 32 / 64 / 112), in fp64 and fp32, warm and cold."""
+    cases = [(known_answer_problem(), {}),
+             (utils.rand_qp(10, 5, 5, seed=1, compute_sol=False)[:5], dict(eps_abs=1e-6)),
+             (utils.rand_qp(30, 7, 8, seed=2, compute_sol=False)[:5], dict(eps_abs=1e-6)),
+             (utils.rand_qp(56, 14, 14, seed=3, compute_sol=False)[:5], dict(eps_abs=1e-6)),
+             (utils.rand_qp(57, 14, 14, seed=3, compute_sol=False)[:5], dict(eps_abs=1e-6))]   # D = 113: grid kernel
+    for prob, kw in cases:
+        D = prob[0].shape[0] + 2 * prob[2].shape[0]
+        for prec, tol in ((torch.float64, 1e-10), (torch.float32, 2e-3)):
+            a = gpu_model(prob, precision=prec, **kw)
+            ra = a.solve()
+            ia, sa, ka = ra.info.iter, ra.info.status, a.rho_ind
+            xa = ra.x.double().cpu().numpy()
+            assert (a.last_launch["grid"] == 1) == (D <= 112), D
+            b = gpu_model(prob, precision=prec, grid=max(2, (D + 7) // 8), **kw)
+            rb = b.solve()
+            assert b.last_launch["grid"] > 1
+            if prec == torch.float64:
+                assert (rb.info.iter, rb.info.status, b.rho_ind) == (ia, sa, ka), (D, prec)
+            assert rel_err(rb.x.double().cpu().numpy(), xa) < tol, (D, prec)
+            # warm re-solve from the solution: same one-window result on both paths
+            if kw.get("eps_abs") and prec == torch.float64:
+                a2, b2 = a.solve(), b.solve()
+                assert a2.info.iter == b2.info.iter
+    monkeypatch.setenv("RQP_NO_TINY", "1")
+    c = gpu_model(cases[1][0], **cases[1][1])
+    c.solve()
+    assert c.last_launch["grid"] > 1
+    monkeypatch.delenv("RQP_NO_TINY")
+    with pytest.raises(RuntimeError):                           # D = 113 cannot be forced into one CTA
+        gpu_model(cases[4][0], w_residency=5).solve()
 
 
 def test_bitwise_reproducible():

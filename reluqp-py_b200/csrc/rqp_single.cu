@@ -796,7 +796,12 @@ __global__ void __launch_bounds__(TINY_NT, 1) rqp_tiny_kernel(const SingleParams
     const int D = p.D, nx = p.nx, nc = p.nc;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* vs = reinterpret_cast<T*>(smem_raw);                  // [2][D]
-    double* part = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(vs + 2 * D) + 15) & ~uintptr_t(15));  // [NW][8]
+    // the matrices of the residual check, staged once (odd row strides: thread i walks row i, conflict free)
+    const int lda = nx | 1, ldt = nc | 1;
+    T* As = vs + 2 * D;                                      // [nc][lda]
+    T* Hs = As + size_t(nc) * lda;                           // [nx][lda]
+    T* ATs = Hs + size_t(nx) * lda;                          // [nx][ldt]
+    double* part = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ATs + size_t(nx) * ldt) + 15) & ~uintptr_t(15));  // [NW][8]
     Decision* dec = reinterpret_cast<Decision*>(part + NW * 8);
 
     const T* __restrict__ Wall = static_cast<const T*>(p.W);
@@ -818,6 +823,9 @@ __global__ void __launch_bounds__(TINY_NT, 1) rqp_tiny_kernel(const SingleParams
         my_hi = static_cast<const T*>(p.u)[fin_row - nx];
     }
     for (int r = tid; r < D; r += TINY_NT) vs[r] = static_cast<const T*>(p.v)[r];      // v_0 in buffer 0
+    for (int idx = tid; idx < nc * nx; idx += TINY_NT) As[size_t(idx / nx) * lda + idx % nx] = __ldg(Am + idx);
+    for (int idx = tid; idx < nx * nx; idx += TINY_NT) Hs[size_t(idx / nx) * lda + idx % nx] = __ldg(Hm + idx);
+    for (int idx = tid; idx < nx * nc; idx += TINY_NT) ATs[size_t(idx / nc) * ldt + idx % nc] = __ldg(ATm + idx);
     T w[TR][TR];
     auto stage = [&](int ri) {
         const T* Wg = Wall + size_t(ri) * D * p.ldw;
@@ -839,6 +847,18 @@ __global__ void __launch_bounds__(TINY_NT, 1) rqp_tiny_kernel(const SingleParams
     uint64_t t_begin = 0;
     if (tid == 0) t_begin = globaltimer_ns();
 
+    auto row_dot = [](const T* row, const T* x, int n) -> T {      // 4 interleaved partial sums, fixed order
+        T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+        int j = 0;
+        for (; j + 3 < n; j += 4) {
+            a0 = fma(row[j], x[j], a0);
+            a1 = fma(row[j + 1], x[j + 1], a1);
+            a2 = fma(row[j + 2], x[j + 2], a2);
+            a3 = fma(row[j + 3], x[j + 3], a3);
+        }
+        for (; j < n; ++j) a0 = fma(row[j], x[j], a0);
+        return (a0 + a1) + (a2 + a3);
+    };
     // residuals of the iterate in vs[buf] (reluqpth.py:307-318), rho step and termination test (:223-233)
     auto residual_pass = [&](int kk, int buf, bool final_pass) {
         const T* xs = vs + size_t(buf) * D;
@@ -847,27 +867,15 @@ __global__ void __launch_bounds__(TINY_NT, 1) rqp_tiny_kernel(const SingleParams
         T m0 = T(0), m1 = T(0), m2 = T(0), m3 = T(0), m4 = T(0), m5 = T(0), m6 = T(0), osum = T(0);
         for (int i = tid; i < nc + nx; i += TINY_NT) {
             if (i < nc) {
-                const T* row = Am + size_t(i) * nx;
-                T a0 = T(0), a1 = T(0);
-                int j = 0;
-                for (; j + 1 < nx; j += 2) { a0 = fma(__ldg(row + j), xs[j], a0); a1 = fma(__ldg(row + j + 1), xs[j + 1], a1); }
-                if (j < nx) a0 = fma(__ldg(row + j), xs[j], a0);
-                const T t1 = a0 + a1, zi = zs[i];
+                const T t1 = row_dot(As + size_t(i) * lda, xs, nx), zi = zs[i];
                 m0 = nanmax(m0, absval(t1 - zi));
                 m1 = nanmax(m1, absval(t1));
                 m2 = nanmax(m2, absval(zi));
             } else {
                 const int ii = i - nc;
-                const T* hr = Hm + size_t(ii) * nx;
-                const T* ar = ATm + size_t(ii) * nc;
                 const T gi = __ldg(gv + ii);
-                T a0 = T(0), a1 = T(0), c0 = T(0), c1 = T(0);
-                int j = 0;
-                for (; j + 1 < nx; j += 2) { a0 = fma(__ldg(hr + j), xs[j], a0); a1 = fma(__ldg(hr + j + 1), xs[j + 1], a1); }
-                if (j < nx) a0 = fma(__ldg(hr + j), xs[j], a0);
-                for (j = 0; j + 1 < nc; j += 2) { c0 = fma(__ldg(ar + j), ls[j], c0); c1 = fma(__ldg(ar + j + 1), ls[j + 1], c1); }
-                if (j < nc) c0 = fma(__ldg(ar + j), ls[j], c0);
-                const T t2 = a0 + a1, t3 = c0 + c1;
+                const T t2 = row_dot(Hs + size_t(ii) * lda, xs, nx);
+                const T t3 = row_dot(ATs + size_t(ii) * ldt, ls, nc);
                 m3 = nanmax(m3, absval((t2 + t3) + gi));
                 m4 = nanmax(m4, absval(t2));
                 m5 = nanmax(m5, absval(t3));
@@ -991,15 +999,26 @@ static bool tiny_ok(const rqp_problem* prob, const rqp_settings* stng) {
     if (stng->w_residency != 5 && getenv("RQP_NO_TINY") != nullptr) return false;
     return D <= kTinyMaxD;
 }
-template <typename T>
-static int launch_tiny(const SingleParams& prm, cudaStream_t stream) {
-    const size_t smem = size_t(2) * prm.D * sizeof(T) + 16 + (TINY_NT / 32) * 8 * sizeof(double) + sizeof(Decision) + 64;
-    if (prm.D <= 32) rqp_tiny_kernel<T, 2><<<1, TINY_NT, smem, stream>>>(prm);
-    else if (prm.D <= 64) rqp_tiny_kernel<T, 4><<<1, TINY_NT, smem, stream>>>(prm);
-    else if (prm.D <= 112) rqp_tiny_kernel<T, 7><<<1, TINY_NT, smem, stream>>>(prm);
-    else rqp_tiny_kernel<T, 10><<<1, TINY_NT, smem, stream>>>(prm);
+template <typename T, int TR>
+static int launch_tiny_tr(const SingleParams& prm, size_t smem, cudaStream_t stream) {
+    static size_t ok_dev[kMaxDevices] = {};
+    size_t& okb = ok_dev[current_device_slot()];
+    if (smem > okb) {       // more than 48 KB of dynamic shared memory needs the opt-in, once per device
+        RQP_CUDA_TRY(cudaFuncSetAttribute(rqp_tiny_kernel<T, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        okb = smem;
+    }
+    rqp_tiny_kernel<T, TR><<<1, TINY_NT, smem, stream>>>(prm);
     RQP_CUDA_TRY(cudaGetLastError());
     return RQP_OK;
+}
+template <typename T>
+static int launch_tiny(const SingleParams& prm, cudaStream_t stream) {
+    const size_t nx = size_t(prm.nx), nc = size_t(prm.nc);
+    const size_t elems = 2 * size_t(prm.D) + nc * (nx | 1) + nx * (nx | 1) + nx * (nc | 1);
+    const size_t smem = elems * sizeof(T) + 16 + (TINY_NT / 32) * 8 * sizeof(double) + sizeof(Decision) + 64;
+    if (prm.D <= 32) return launch_tiny_tr<T, 2>(prm, smem, stream);
+    if (prm.D <= 64) return launch_tiny_tr<T, 4>(prm, smem, stream);
+    return launch_tiny_tr<T, 7>(prm, smem, stream);
 }
 
 // -------------------------------------------------------------------------------------------

@@ -25,6 +25,8 @@
 //    reduced per CTA, all-gathered through flagged cells, and every CTA then takes the SAME
 //    decision from bitwise identical numbers (rho estimate, index move, termination).
 //  * Every wait is bounded by a watchdog; on expiry the kernel exits with result.error set.
+//  * Problems with D <= 112 skip the grid altogether: rqp_tiny_kernel keeps W_rho in the registers of ONE CTA
+//    (16 x 16 thread grid, TR x TR tiles) and orders iterations with __syncthreads (see there).
 #include <math_constants.h>
 #include <stdlib.h>
 

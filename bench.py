@@ -483,9 +483,16 @@ def run_single(args, rank, world, dev):
                       traffic=28.4e6 if args.workload == "mpc_single" else None,
                       traffic_source="profiles/r01d_single_mpc_ncu_full.csv" if args.workload == "mpc_single" else None,
                       peak_source=peaks["source"],
-                      note="HBM-equivalent: W_rho stays in shared memory / L2 across iterations, so achieved "
-                           "can exceed the DRAM copy peak; algorithmic bytes = s*(D^2+3D+2nc) per iteration "
+                      note="HBM-equivalent: W_rho stays in registers / shared memory / L2 across iterations, so "
+                           "achieved can exceed the DRAM copy peak; algorithmic bytes = s*(D^2+3D+2nc) per iteration "
                            "+ s*(nx^2+2*nc*nx) per check", **probe),
+        # the physical bound of the on-chip-resident sizes is the inter-CTA handoff, not memory bandwidth:
+        # store -> seen by a poller is ~850 SM cycles one way on this B200 (tools/ubench/pingpong.cu), plus ~600
+        # cycles of GEMV / reduction / finalize per iteration
+        latency_bound=(dict(floor_us_per_iter=(850 + 600) / 1965.0, achieved_us_per_iter=sum(loop_us) / sum(iters),
+                            frac=((850 + 600) / 1965.0) / (sum(loop_us) / sum(iters)),
+                            source="tools/ubench/pingpong.cu (handoff 850 cycles) + in-kernel phase counters")
+                       if args.workload == "mpc_single" else None),
         e2e=dict(value=solves / e2e_s_max, unit="solves/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                  ms_per_step=1e3 * e2e_s_max / args.steps,
                  api="ReLU_QP.update(l=numpy, u=numpy); ReLU_QP.solve(); results.x.cpu()"),

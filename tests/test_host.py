@@ -136,6 +136,8 @@ def test_solve_refuses_without_cuda():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.solve()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.resolve(l=l, u=u)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.solve_batch(np.stack([l, l]), np.stack([u, u]))
 
 

@@ -50,16 +50,18 @@ __global__ void update_bias_kernel(const T* __restrict__ Bm, const T* __restrict
     const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long r = wid; r < nrows; r += nwarps) {
+        // summed in double for both element types (exact products in fp32): b_rho feeds every iteration and its
+        // rounding noise reaches the dual residual multiplied by K^-1
         const T* __restrict__ row = Bm + r * nx;
-        T s0 = T(0), s1 = T(0);
+        double s0 = 0.0, s1 = 0.0;
         int j = lane;
         for (; j + 32 < nx; j += 64) {
-            s0 = fma(__ldg(row + j), __ldg(g + j), s0);
-            s1 = fma(__ldg(row + j + 32), __ldg(g + j + 32), s1);
+            s0 = fma(double(__ldg(row + j)), double(__ldg(g + j)), s0);
+            s1 = fma(double(__ldg(row + j + 32)), double(__ldg(g + j + 32)), s1);
         }
-        if (j < nx) s0 = fma(__ldg(row + j), __ldg(g + j), s0);
-        const T s = warp_sum(s0 + s1);
-        if (lane == 0) out[r] = s;
+        if (j < nx) s0 = fma(double(__ldg(row + j)), double(__ldg(g + j)), s0);
+        const double s = warp_sum(s0 + s1);
+        if (lane == 0) out[r] = T(s);
     }
 }
 

@@ -207,6 +207,24 @@ struct Vec16<float> {
         acc = fmaf(q.w, v[3], acc);
         return acc;
     }
+    // fp32 data, fp64 running sum: the four products of one 16-byte piece are summed in fp32 (FFMA chain from
+    // zero: error <= ~3 ulp of a 4-term partial), the partial is widened and added to a DOUBLE accumulator.  The
+    // long part of the summation -- D/4 partials, the warp tree, the cross-warp sum -- is then exact to 2^-53,
+    // so the rounding noise of a row is ~sqrt(D/4) * 2^-24 * |term| instead of plain fp32's ~(D/32) * sqrt(256)
+    // * 2^-24 * |term| (sequential chains then a tree): 6-9x less at D = 4000..8000, within 2-3x of full fp64
+    // accumulation, for one cvt.f64.f32 + one DADD per FOUR matrix elements (full fp64 accumulation -- a
+    // conversion and a DFMA per element -- cost the latency-bound kernels +25 % and the L2-resident ones +45 %
+    // per iteration, tools/ubench/cvt_rate.cu and profiles/r02a_sweep.json).
+    // Why it matters: rounding noise in the x rows acts like a perturbation of b_rho and reaches the dual
+    // residual multiplied by K^-1 = H + sigma I + A' R A; with plain fp32 sums the dual residual of
+    // rand_qp(nx >= 3200) floors just above eps_abs * sqrt(nx) and the solve never terminates.
+    __device__ __forceinline__ double dot(const float (&v)[4], double acc) const {
+        float p = q.x * v[0];
+        p = fmaf(q.y, v[1], p);
+        p = fmaf(q.z, v[2], p);
+        p = fmaf(q.w, v[3], p);
+        return acc + double(p);
+    }
     static __device__ __forceinline__ Vec16 ldg(const float* p) {
         Vec16 r;
         r.q = __ldg(reinterpret_cast<const float4*>(p));

@@ -90,12 +90,14 @@ template <>
 __device__ __forceinline__ double t_sqrt<double>(double x) { return sqrt(x); }
 
 // 8 rows x CPT vector columns of the slab against the thread's v registers.
+// Partial sums are DOUBLE for both element types: with fp32 data every 16-byte piece contributes a 4-term fp32
+// partial that is widened before it is added (see Vec16<float>::dot), so the long summation is exact.
 template <typename T, int CPT, bool SMEM, bool FULL>
 __device__ __forceinline__ void chunk_dot(const T* __restrict__ wrow0, long long ldw, int nrows,
                                           const int (&coff)[CPT], const T (&vv)[CPT][Cell<T>::kVec],
-                                          T (&acc)[RM]) {
+                                          double (&acc)[RM]) {
 #pragma unroll
-    for (int r = 0; r < RM; ++r) acc[r] = T(0);
+    for (int r = 0; r < RM; ++r) acc[r] = 0.0;
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
         Vec16<T> w[RM];
@@ -117,9 +119,16 @@ __device__ __forceinline__ void chunk_dot(const T* __restrict__ wrow0, long long
 // lane are issued before the first use (the rows are read once per check, from L2 or HBM, so the
 // loop is latency bound unless the loads overlap).  Every lane returns the full sum.
 // GL: the row is in global memory (read-only path); otherwise a shared-memory copy.
+// The sum is accumulated in DOUBLE for both element types (a product of two floats is exact in double).
+// Why: the dual residual H x + A' lambda + g is a difference of terms of size |H||x|; evaluated in fp32 it
+// has a noise floor of ~|H||x| 2^-24 sqrt(n), which from nx ~ 3000 on straddles the termination threshold
+// eps_abs sqrt(nx) (rand_qp(3200,...): terms ~1.6e4, computed dua stuck at 0.058..0.066 vs threshold
+// 0.0566 while the iterate itself was converged; the CPU reference's MKL summation happened to land on
+// 0.040).  The checks run once per check_interval and are memory bound, so the wider sum is free; fp64
+// results are unchanged.
 template <typename T, bool GL>
-__device__ __forceinline__ T warp_row_dot(const T* __restrict__ row, const T* xs, int n, int lane) {
-    T s0 = T(0), s1 = T(0);
+__device__ __forceinline__ double warp_row_dot(const T* __restrict__ row, const T* xs, int n, int lane) {
+    double s0 = 0.0, s1 = 0.0;
     for (int j0 = 0; j0 < n; j0 += 256) {
         T a[8];
 #pragma unroll
@@ -130,8 +139,8 @@ __device__ __forceinline__ T warp_row_dot(const T* __restrict__ row, const T* xs
 #pragma unroll
         for (int u = 0; u < 8; u += 2) {
             const int j = j0 + u * 32 + lane;
-            s0 = fma(a[u], (j < n) ? xs[j] : T(0), s0);
-            s1 = fma(a[u + 1], (j + 32 < n) ? xs[j + 32] : T(0), s1);
+            s0 = fma(double(a[u]), double((j < n) ? xs[j] : T(0)), s0);
+            s1 = fma(double(a[u + 1]), double((j + 32 < n) ? xs[j + 32] : T(0)), s1);
         }
     }
     return warp_sum(s0 + s1);
@@ -141,8 +150,9 @@ __device__ __forceinline__ T warp_row_dot(const T* __restrict__ row, const T* xs
 // together.  Returns the two sums through references.
 template <typename T, bool GL>
 __device__ __forceinline__ void warp_row_dot2(const T* __restrict__ r1, const T* x1, int n1,
-                                              const T* __restrict__ r2, const T* x2, int n2, int lane, T& o1, T& o2) {
-    T s0 = T(0), s1 = T(0), q0 = T(0), q1 = T(0);
+                                              const T* __restrict__ r2, const T* x2, int n2, int lane, double& o1,
+                                              double& o2) {
+    double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
     const int nmax = n1 > n2 ? n1 : n2;
     for (int j0 = 0; j0 < nmax; j0 += 128) {
         T a[4], b[4];
@@ -155,10 +165,10 @@ __device__ __forceinline__ void warp_row_dot2(const T* __restrict__ r1, const T*
 #pragma unroll
         for (int u = 0; u < 4; u += 2) {
             const int j = j0 + u * 32 + lane;
-            s0 = fma(a[u], (j < n1) ? x1[j] : T(0), s0);
-            s1 = fma(a[u + 1], (j + 32 < n1) ? x1[j + 32] : T(0), s1);
-            q0 = fma(b[u], (j < n2) ? x2[j] : T(0), q0);
-            q1 = fma(b[u + 1], (j + 32 < n2) ? x2[j + 32] : T(0), q1);
+            s0 = fma(double(a[u]), double((j < n1) ? x1[j] : T(0)), s0);
+            s1 = fma(double(a[u + 1]), double((j + 32 < n1) ? x1[j + 32] : T(0)), s1);
+            q0 = fma(double(b[u]), double((j < n2) ? x2[j] : T(0)), q0);
+            q1 = fma(double(b[u + 1]), double((j + 32 < n2) ? x2[j + 32] : T(0)), q1);
         }
     }
     o1 = warp_sum(s0 + s1);
@@ -199,9 +209,9 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
     T* Ws = reinterpret_cast<T*>(smem_raw);                    // [rows_smem][ldw], or the streaming ring
     const size_t ws_elems = p.ring ? size_t(RING_STAGES) * RM * NT * VEC : size_t(p.rows_smem) * ldw;
     T* vs = Ws + ws_elems;                                     // [ldw]   (check phase only)
-    T* red = vs + ldw;                                         // [2][NW][rpc_pad]
-    size_t off = (reinterpret_cast<unsigned char*>(red + 2 * NW * rpc_pad) - smem_raw + 15) & ~size_t(15);
-    double* part = reinterpret_cast<double*>(smem_raw + off);  // [NW][8]
+    // cross-warp partial sums, double for both element types: [2][NW][rpc_pad]
+    double* red = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(vs + ldw) + 15) & ~uintptr_t(15));
+    double* part = red + 2 * NW * rpc_pad;                     // [NW][8]
     double* tot = part + NW * 8;                               // [NW][8]
     Decision* dec = reinterpret_cast<Decision*>(tot + NW * 8);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(dec + 1);
@@ -419,7 +429,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
         const T* xs = vs;
         const T* zs = vs + nx;
         const T* ls = vs + nx + nc;
-        T m0 = T(0), m1 = T(0), m2 = T(0), m3 = T(0), m4 = T(0), m5 = T(0), m6 = T(0), osum = T(0);
+        double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0, m4 = 0.0, m5 = 0.0, m6 = 0.0, osum = 0.0;
         const int GW = G * NW;
         if (crow_pending) {     // first check: the rows were requested at kernel start
             wd.arm();
@@ -432,16 +442,16 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
         for (int i = blockIdx.x * NW + warp; i < nc + nx; i += GW, ++tj) {
             const T* crw = crow + size_t(warp * p.check_tpw + tj) * (nx + nc);
             if (i < nc) {
-                const T t1 = p.check_tpw > 0 ? warp_row_dot<T, false>(crw, xs, nx, lane)
-                                             : warp_row_dot<T, true>(Am + size_t(i) * nx, xs, nx, lane);
-                const T zi = zs[i];
+                const double t1 = p.check_tpw > 0 ? warp_row_dot<T, false>(crw, xs, nx, lane)
+                                                  : warp_row_dot<T, true>(Am + size_t(i) * nx, xs, nx, lane);
+                const double zi = double(zs[i]);
                 m0 = nanmax(m0, absval(t1 - zi));
                 m1 = nanmax(m1, absval(t1));
                 m2 = nanmax(m2, absval(zi));
             } else {
                 const int ii = i - nc;
-                const T gi = __ldg(gv + ii);      // issued before the dot products: its L2 latency hides behind them
-                T t2, t3;
+                const double gi = double(__ldg(gv + ii));      // issued before the dot products: its L2 latency hides behind them
+                double t2, t3;
                 if (p.check_tpw > 0)
                     warp_row_dot2<T, false>(crw, xs, nx, crw + nx, ls, nc, lane, t2, t3);
                 else
@@ -450,15 +460,15 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 m4 = nanmax(m4, absval(t2));
                 m5 = nanmax(m5, absval(t3));
                 m6 = nanmax(m6, absval(gi));
-                osum += xs[ii] * (T(0.5) * t2 + gi);
+                osum += double(xs[ii]) * (0.5 * t2 + gi);
             }
         }
         CHK_MARK(1);
         // 3. CTA reduction, publish 8 partials as double cells
         if (lane == 0) {
             double* pw = part + warp * 8;
-            pw[0] = double(m0); pw[1] = double(m1); pw[2] = double(m2); pw[3] = double(m3);
-            pw[4] = double(m4); pw[5] = double(m5); pw[6] = double(m6); pw[7] = double(osum);
+            pw[0] = m0; pw[1] = m1; pw[2] = m2; pw[3] = m3;
+            pw[4] = m4; pw[5] = m5; pw[6] = m6; pw[7] = osum;
         }
         __syncthreads();
         uint64_t* pslot = p.pcells + size_t(n_checks & 1) * size_t(G) * 16;
@@ -634,12 +644,12 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
 
             const long long tp1 = kTimers ? clock64() : 0;
             // ---- slab GEMV, 8 rows per chunk
-            T* redk = red + size_t(k & 1) * NW * rpc_pad + size_t(warp) * rpc_pad;
+            double* redk = red + size_t(k & 1) * NW * rpc_pad + size_t(warp) * rpc_pad;
             const T* Wg = Wall + (size_t(rho_ind) * D + r0) * ldw;
             if (RMODE) {
-                T acc[RM];
+                double acc[RM];
 #pragma unroll
-                for (int r = 0; r < RM; ++r) acc[r] = T(0);
+                for (int r = 0; r < RM; ++r) acc[r] = 0.0;
 #pragma unroll
                 for (int i = 0; i < CPT; ++i) {
 #pragma unroll
@@ -652,9 +662,9 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 for (int ch = 0; ch < nchunks; ++ch) {
                     const int rbase = ch * RM;
                     const int nr = min(RM, rows - rbase);
-                    T acc[RM];
+                    double acc[RM];
 #pragma unroll
-                    for (int r = 0; r < RM; ++r) acc[r] = T(0);
+                    for (int r = 0; r < RM; ++r) acc[r] = 0.0;
 #pragma unroll
                     for (int i = 0; i < CPT; ++i) {
                         if (i < cpt_rt) {                       // uniform
@@ -679,7 +689,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
             for (int ch = 0; ch < nchunks; ++ch) {
                 const int rbase = ch * RM;
                 const int nr = min(RM, rows - rbase);
-                T acc[RM];
+                double acc[RM];
                 if (rbase < rows_s) {  // rows_s is a multiple of RM unless it equals rows
                     const T* w0 = Ws + size_t(rbase) * ldw;
                     if (nr == RM) chunk_dot<T, CPT, true, true>(w0, ldw, nr, coff, vv, acc);
@@ -698,11 +708,11 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
 
             // ---- finalize own rows: cross-warp sum (fixed order), bias, clamp, publish v_k
             if (is_fin) {
-                const T* rk = red + size_t(k & 1) * NW * rpc_pad + tid;
-                T y = rk[0];
+                const double* rk = red + size_t(k & 1) * NW * rpc_pad + tid;
+                double ys = rk[0];
 #pragma unroll
-                for (int w = 1; w < NW; ++w) y += rk[size_t(w) * rpc_pad];
-                y += my_b;
+                for (int w = 1; w < NW; ++w) ys += rk[size_t(w) * rpc_pad];
+                const T y = T(ys + double(my_b));        // fp32: the one rounding of this row's W v + b
                 my_v = clamp_keep_nan(y, my_lo, my_hi);
                 uint64_t* dst = p.vcells + size_t(k & 1) * nvec * 4;
                 for (int rp = 0; rp < p.replicas; ++rp)
@@ -849,16 +859,18 @@ __global__ void __launch_bounds__(TINY_NT, 1) rqp_tiny_kernel(const SingleParams
     uint64_t t_begin = 0;
     if (tid == 0) t_begin = globaltimer_ns();
 
-    auto row_dot = [](const T* row, const T* x, int n) -> T {      // 4 interleaved partial sums, fixed order
-        T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+    // sums in double for both element types (see warp_row_dot): the fp32 residuals are then the true residuals of
+    // the fp32 iterate, not an fp32 evaluation with its own noise floor
+    auto row_dot = [](const T* row, const T* x, int n) -> double {      // 4 interleaved partial sums, fixed order
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int j = 0;
         for (; j + 3 < n; j += 4) {
-            a0 = fma(row[j], x[j], a0);
-            a1 = fma(row[j + 1], x[j + 1], a1);
-            a2 = fma(row[j + 2], x[j + 2], a2);
-            a3 = fma(row[j + 3], x[j + 3], a3);
+            a0 = fma(double(row[j]), double(x[j]), a0);
+            a1 = fma(double(row[j + 1]), double(x[j + 1]), a1);
+            a2 = fma(double(row[j + 2]), double(x[j + 2]), a2);
+            a3 = fma(double(row[j + 3]), double(x[j + 3]), a3);
         }
-        for (; j < n; ++j) a0 = fma(row[j], x[j], a0);
+        for (; j < n; ++j) a0 = fma(double(row[j]), double(x[j]), a0);
         return (a0 + a1) + (a2 + a3);
     };
     // residuals of the iterate in vs[buf] (reluqpth.py:307-318), rho step and termination test (:223-233)
@@ -866,31 +878,31 @@ __global__ void __launch_bounds__(TINY_NT, 1) rqp_tiny_kernel(const SingleParams
         const T* xs = vs + size_t(buf) * D;
         const T* zs = xs + nx;
         const T* ls = xs + nx + nc;
-        T m0 = T(0), m1 = T(0), m2 = T(0), m3 = T(0), m4 = T(0), m5 = T(0), m6 = T(0), osum = T(0);
+        double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0, m4 = 0.0, m5 = 0.0, m6 = 0.0, osum = 0.0;
         for (int i = tid; i < nc + nx; i += TINY_NT) {
             if (i < nc) {
-                const T t1 = row_dot(As + size_t(i) * lda, xs, nx), zi = zs[i];
+                const double t1 = row_dot(As + size_t(i) * lda, xs, nx), zi = double(zs[i]);
                 m0 = nanmax(m0, absval(t1 - zi));
                 m1 = nanmax(m1, absval(t1));
                 m2 = nanmax(m2, absval(zi));
             } else {
                 const int ii = i - nc;
-                const T gi = __ldg(gv + ii);
-                const T t2 = row_dot(Hs + size_t(ii) * lda, xs, nx);
-                const T t3 = row_dot(ATs + size_t(ii) * ldt, ls, nc);
+                const double gi = double(__ldg(gv + ii));
+                const double t2 = row_dot(Hs + size_t(ii) * lda, xs, nx);
+                const double t3 = row_dot(ATs + size_t(ii) * ldt, ls, nc);
                 m3 = nanmax(m3, absval((t2 + t3) + gi));
                 m4 = nanmax(m4, absval(t2));
                 m5 = nanmax(m5, absval(t3));
                 m6 = nanmax(m6, absval(gi));
-                osum += xs[ii] * (T(0.5) * t2 + gi);
+                osum += double(xs[ii]) * (0.5 * t2 + gi);
             }
         }
         m0 = warp_nanmax(m0); m1 = warp_nanmax(m1); m2 = warp_nanmax(m2); m3 = warp_nanmax(m3);
         m4 = warp_nanmax(m4); m5 = warp_nanmax(m5); m6 = warp_nanmax(m6); osum = warp_sum(osum);
         if (lane == 0) {
             double* pw = part + warp * 8;
-            pw[0] = double(m0); pw[1] = double(m1); pw[2] = double(m2); pw[3] = double(m3);
-            pw[4] = double(m4); pw[5] = double(m5); pw[6] = double(m6); pw[7] = double(osum);
+            pw[0] = m0; pw[1] = m1; pw[2] = m2; pw[3] = m3;
+            pw[4] = m4; pw[5] = m5; pw[6] = m6; pw[7] = osum;
         }
         __syncthreads();
         if (tid == 0) {
@@ -941,7 +953,8 @@ __global__ void __launch_bounds__(TINY_NT, 1) rqp_tiny_kernel(const SingleParams
 
     for (k = 1; k <= p.max_iter; ++k) {
         const T* vo = vs + size_t((k - 1) & 1) * D;
-        T vc[TR], acc[TR];
+        T vc[TR];
+        double acc[TR];      // double partial sums for both element types (exact products in fp32)
 #pragma unroll
         for (int j = 0; j < TR; ++j) {
             const int c = tx + 16 * j;
@@ -949,10 +962,11 @@ __global__ void __launch_bounds__(TINY_NT, 1) rqp_tiny_kernel(const SingleParams
         }
 #pragma unroll
         for (int i = 0; i < TR; ++i) {
-            T a = T(0);
+            // the thread's TR (<= 7) products of a row in the element type, the cross-thread sum in double
+            T a = w[i][0] * vc[0];
 #pragma unroll
-            for (int j = 0; j < TR; ++j) a = fma(w[i][j], vc[j], a);
-            acc[i] = a;
+            for (int j = 1; j < TR; ++j) a = fma(w[i][j], vc[j], a);
+            acc[i] = double(a);
         }
         // butterfly over the 16 threads of a row group (one half warp): every lane ends with the full sums
 #pragma unroll
@@ -960,10 +974,10 @@ __global__ void __launch_bounds__(TINY_NT, 1) rqp_tiny_kernel(const SingleParams
 #pragma unroll
             for (int i = 0; i < TR; ++i) acc[i] += shfl_xor(acc[i], m);
         }
-        T y = T(0);
+        double y = 0.0;
 #pragma unroll
         for (int i = 0; i < TR; ++i) y = (i == tx) ? acc[i] : y;
-        if (is_fin) vs[size_t(k & 1) * D + fin_row] = clamp_keep_nan(y + my_b, my_lo, my_hi);
+        if (is_fin) vs[size_t(k & 1) * D + fin_row] = clamp_keep_nan(T(y + double(my_b)), my_lo, my_hi);
         __syncthreads();
         if (p.adaptive && (k % p.check_interval) == 0) {
             residual_pass(k, k & 1, false);
@@ -1030,8 +1044,8 @@ static size_t smem_fixed_bytes(int elem, long long ldw, int rpc, int block) {
     const int NW = block / 32;
     const int rpc_pad = (rpc + RM - 1) / RM * RM;
     size_t o = size_t(ldw) * elem;                 // vs
-    o += size_t(2) * NW * rpc_pad * elem;          // red
     o = (o + 15) & ~size_t(15);
+    o += size_t(2) * NW * rpc_pad * sizeof(double);  // red (double for both element types)
     o += size_t(2) * NW * 8 * sizeof(double);      // part, tot
     o += sizeof(Decision) + 16 + 8 * RING_STAGES + 8 + 16;  // dec, mbar, ring barriers, check-row barrier, alignment
     return o;

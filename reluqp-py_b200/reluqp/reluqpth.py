@@ -132,6 +132,7 @@ class ReLU_Layer(object):
         n = len(self.rho_list)
         W_all = torch.zeros((n, D, ldw), device=dev, dtype=st.precision)
         B_all = torch.zeros((n, D, nx), device=dev, dtype=st.precision)
+        b_all = torch.zeros((n, D), device=dev, dtype=st.precision)
         eq = (u - l) <= st.eq_tol
         Ix = torch.eye(nx, device=dev, dtype=sdt)
         Ic = torch.eye(nc, device=dev, dtype=sdt)
@@ -165,7 +166,12 @@ class ReLU_Layer(object):
             W[:, nx + nc:, nx + nc:D] = Ic
             B_all[c0:c0 + m, :nx] = -K
             B_all[c0:c0 + m, nx:nx + nc] = -AK
-        b_all = torch.matmul(B_all, self.QP.g).contiguous()
+            # b_rho = B_rho g (:77) in the SETUP dtype, rounded once: with precision=float32 on fp64-formed
+            # matrices this is what "formed in float64 and rounded" means for b as well.  (b from the already
+            # rounded B in fp32 carries ~sqrt(nx) 2^-24 |K||g| of noise, which reaches the dual residual
+            # multiplied by K^-1 and kept rand_qp(nx >= 3200) in fp32 from ever terminating.)
+            b_all[c0:c0 + m, :nx] = -(K @ q.g)
+            b_all[c0:c0 + m, nx:nx + nc] = -(AK @ q.g)
         return W_all, B_all, b_all
 
     def forward(self, input, idx):

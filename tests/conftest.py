@@ -56,6 +56,8 @@ class Golden(object):
             m = dict(self.meta["mpc"][name])
         elif group == "large":
             m = dict(self.meta["large"][name])
+        elif group == "xl":
+            m = dict(self.meta["xl"][name])
         else:
             m = dict(self.meta[name])
         a = self.arrays(group)

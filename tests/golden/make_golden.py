@@ -17,7 +17,7 @@ three shims of SURVEY.md §8c at run time (nothing is copied into this repo):
 (the reference's is broken) but are SOLVED by the reference.
 
 Outputs (all committed): golden_small.npz, golden_sweep.npz, golden_mpc.npz,
-golden_large.npz, golden_meta.json.
+golden_large.npz, golden_xl.npz, golden_meta.json.
 """
 import hashlib
 import importlib.util
@@ -280,10 +280,43 @@ def main():
     np.savez_compressed(os.path.join(HERE, "golden_large.npz"),
                         **{k: (v.astype(np.float64)) for k, v in LG.items()})
 
+    meta["xl"] = xl_cases()
     with open(os.path.join(HERE, "golden_meta.json"), "w") as f:
         json.dump(meta, f, indent=1, sort_keys=True)
     print("done")
 
 
+def xl_cases():
+    """Round 2 additions (golden_xl.npz): the rest of BASELINE config 5's size sweep and config 3's seeds, in fp64
+    and fp32-hybrid -- nx = 1000 (seeds 0-3), C3 seeds 1-4, nx = 3200 and nx = 4000 (seed 0; the sizes
+    whose W_rho does not fit L2 and streams from HBM).  Same reference loop (reluqpth.py:201-249 via the shims)."""
+    XL, xl = {}, {}
+    cases = [(1000, s) for s in range(4)] + [(2000, s) for s in range(1, 5)] + [(3200, 0), (4000, 0)]
+    for nx, seed in cases:
+        H, g, A, l, u, _ = RU.rand_qp(nx, nx // 4, nx // 4, seed=seed, compute_sol=False)
+        t0 = time.time()
+        m = ref_model(H, g, A, l, u)
+        tag = "nx{}_s{}".format(nx, seed)
+        put(XL, xl, tag + "_fp64", run(m), nx=nx, seed=seed, sha256=sha(H, g, A, l, u)[:16])
+        cast_model_fp32(m)
+        m.clear_primal_dual()
+        m.output = m.output.to(torch.float32)
+        put(XL, xl, tag + "_fp32hybrid", run(m), nx=nx, seed=seed, settings=dict(precision="float32"))
+        print(tag, xl[tag + "_fp64"]["iter"], xl[tag + "_fp32hybrid"]["iter"], xl[tag + "_fp32hybrid"]["status"],
+              round(time.time() - t0, 1), flush=True)
+        del m
+    # x, z, lam in float32 are enough for the 1e-4 / 1e-6 comparisons?  No: fp64 cases are compared at 1e-6
+    # relative, keep doubles (10 problems x 3 vectors x <= 8000 doubles: < 1 MB compressed)
+    np.savez_compressed(os.path.join(HERE, "golden_xl.npz"), **{k: v.astype(np.float64) for k, v in XL.items()})
+    return xl
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-xl":      # regenerate golden_xl.npz and its meta entry only
+        with open(os.path.join(HERE, "golden_meta.json")) as f:
+            meta_ = json.load(f)
+        meta_["xl"] = xl_cases()
+        with open(os.path.join(HERE, "golden_meta.json"), "w") as f:
+            json.dump(meta_, f, indent=1, sort_keys=True)
+    else:
+        main()

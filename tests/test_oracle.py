@@ -170,3 +170,24 @@ def test_mpc_c2_first_columns(golden):
         gold = golden.case("mpc", "mpc_col{}".format(j))
         gold = dict(gold, rho_ind_after=r.rho_ind)
         check(r, gold, tol=1e-7)
+
+
+@pytest.mark.parametrize("nx,seed", [(1000, 0), (1000, 2), (2000, 3)])
+def test_xl_cases(golden, nx, seed):
+    """Round-2 goldens (golden_xl.npz: nx = 1000 seeds 0-3, C3 seeds 1-4, nx = 3200 / 4000) -- the oracle is
+    checked here on the three cheapest to set up on CPU (the GPU tests run all ten): fp64 and fp32-hybrid."""
+    prob = utils.rand_qp(nx, nx // 4, nx // 4, seed=seed, compute_sol=False)[:5]
+    tag = "nx{}_s{}".format(nx, seed)
+    g64 = golden.case("xl", tag + "_fp64")
+    import hashlib
+    h = hashlib.sha256()
+    for a in prob:
+        h.update(np.ascontiguousarray(a).tobytes())
+    assert g64["sha256"] == h.hexdigest()[:16]       # same problem bits as the reference run
+    r = O.OracleSolver(*prob).solve()
+    assert (r.iter, r.status) == (g64["iter"], g64["status"])
+    assert rel_err(r.x.numpy(), g64["x"]) < 1e-9
+    g32 = golden.case("xl", tag + "_fp32hybrid")
+    r = O.OracleSolver(*prob, precision=torch.float32, setup_precision=torch.float64).solve()
+    assert (r.iter, r.status) == (g32["iter"], g32["status"])
+    assert rel_err(r.x.double().numpy(), g32["x"]) < 1e-6

@@ -4,7 +4,11 @@ D = 2 nx) and batch sweep (1 ... 65536 MPC QPs sharing W) against the CPU oracle
 
     python tools/bench_sweep.py [--sizes 50,100,...] [--batches 1,4,...] [--dtype f64|f32] [--out file.json]
 
-Not the driver's bench (that is bench.py); this writes a JSON table for profiles/ and DESIGN.md.
+Not the driver's bench (that is bench.py); this writes a JSON table for profiles/ and DESIGN.md, and -- like the
+reference's benchmarks/random_qps.py:23 (assert status == 'solved') and :68 (solution cross-check, there against
+OSQP, here against the CPU oracle because OSQP is absent) -- it ASSERTS: every row must be `solved`, agree with the
+oracle's status and, when the oracle ran, with its x (1e-6 relative in fp64, 1e-4 in fp32; fp64 also the same
+iteration count).  Violations are listed under "failures" in the JSON and the exit status is 1.
 Single-QP rows: device-timed microseconds per ADMM iteration (in-kernel %globaltimer and CUDA events
 around the launch), HBM-equivalent GB/s = s*(D^2+3D+2nc)*iters / time, the slab residency the planner
 chose, and the CPU oracle's microseconds per iteration (best of 1/4/8/all threads)."""
@@ -52,6 +56,7 @@ def single_row(nx, dtype, seed, cpu):
         status = int(r.status)
     ms = [a.elapsed_time(b) for a, b in ev]
     res = m.solve()
+    x_gpu = res.x.detach().double().cpu().numpy()
     ll = m.last_launch
     row = dict(nx=nx, nc=nc, D=D, dtype=dtype, iters=its[0], status="solved" if status == 0 else "max_iters_reached",
                us_per_iter_kernel=min(loops) / its[0], us_per_iter_events=1e3 * min(ms) / its[0],
@@ -73,9 +78,28 @@ def single_row(nx, dtype, seed, cpu):
         for _ in range(reps):
             rr = s.solve()
         dtc = (time.perf_counter() - t0) / reps
-        row.update(cpu_us_per_iter=1e6 * dtc / rr.iter, cpu_iters=rr.iter, cpu_threads=nthr,
+        xo = rr.x.double().numpy()
+        row.update(cpu_us_per_iter=1e6 * dtc / rr.iter, cpu_iters=rr.iter, cpu_threads=nthr, cpu_status=rr.status,
+                   x_rel_err_vs_oracle=float(np.max(np.abs(x_gpu - xo)) / max(1e-300, np.max(np.abs(xo)))),
                    speedup_per_iter=(1e6 * dtc / rr.iter) / row["us_per_iter_kernel"])
     return row
+
+
+def row_failures(row):
+    """random_qps.py:23 / :68 for one row of the size sweep."""
+    tag = "single nx={} {}".format(row["nx"], row["dtype"])
+    bad = []
+    if row["status"] != "solved":
+        bad.append(tag + ": status " + row["status"])
+    if "cpu_status" in row:
+        if row["cpu_status"] != row["status"]:
+            bad.append(tag + ": oracle status {} != {}".format(row["cpu_status"], row["status"]))
+        tol = 1e-6 if row["dtype"] == "f64" else 1e-4
+        if row["x_rel_err_vs_oracle"] > tol:
+            bad.append(tag + ": x differs from the oracle by {:.2e} (> {:g})".format(row["x_rel_err_vs_oracle"], tol))
+        if row["dtype"] == "f64" and row["cpu_iters"] != row["iters"]:
+            bad.append(tag + ": {} iterations, oracle {}".format(row["iters"], row["cpu_iters"]))
+    return bad
 
 
 def batch_rows(batches, dtype, cpu_sps):
@@ -110,13 +134,16 @@ def main():
     ap.add_argument("--batches", default="1,4,16,64,256,1024,4096,16384,65536")
     ap.add_argument("--dtypes", default="f64,f32")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-max-nx", type=int, default=4000,
+                    help="largest nx the CPU oracle is run on (its fp64 setup takes minutes from nx ~ 3000)")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
-    out = dict(gpu=torch.cuda.get_device_name(0), host_cpus=os.cpu_count(), single=[], batched=[])
+    out = dict(gpu=torch.cuda.get_device_name(0), host_cpus=os.cpu_count(), single=[], batched=[], failures=[])
     for dtype in args.dtypes.split(","):
         for nx in [int(x) for x in args.sizes.split(",") if x]:
-            row = single_row(nx, dtype, 0, not args.no_cpu)
+            row = single_row(nx, dtype, 0, not args.no_cpu and nx <= args.cpu_max_nx)
             out["single"].append(row)
+            out["failures"] += row_failures(row)
             print(json.dumps(row), flush=True)
     cpu_sps = None
     if not args.no_cpu and args.batches:
@@ -129,10 +156,16 @@ def main():
             rows = batch_rows([int(b) for b in args.batches.split(",")], dtype, cpu_sps)
             out["batched"] += rows
             for r in rows:
+                if not r["all_solved"]:
+                    out["failures"].append("batched B={} {}: not every column solved".format(r["B"], r["dtype"]))
                 print(json.dumps(r), flush=True)
     if args.out:
         with open(args.out, "w") as f:
             json.dump(out, f, indent=1)
+    if out["failures"]:
+        print("FAILURES:\n  " + "\n  ".join(out["failures"]), file=sys.stderr)
+        sys.exit(1)
+    print("all rows solved and consistent with the oracle", file=sys.stderr)
 
 
 if __name__ == "__main__":

@@ -2,26 +2,30 @@
 """Benchmark of the ReLU-QP solve path on B200 (the contract the driver depends on).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload mpc_single|large_qp|mpc_batched]
+                    [--workload mpc_batched|mpc_single|large_qp]
 
 One "step" = one pass of the hot path over one batch of synthetic input:
-  mpc_single  (default; BASELINE.json configs[1]) one cold solve of a random linear-MPC QP
-              (nx=12 nu=4 horizon 20 -> 320 variables, 320 constraints, D=960, fp64); the QP
-              instance (initial state x0 -> l, u) changes every step.  N>1: N independent
-              replicas, one per GPU ("replicas only": a single QP does not shard).
+  mpc_batched (default; BASELINE.json configs[3]: the path that shards) `--batch` (4096) random linear-MPC QPs
+              (nx=12 nu=4 horizon 20 -> D=960) sharing W_rho PER GPU in one batched solve through the
+              NCCL-sharded public path; N>1 shards columns across GPUs with no data-path collective and one
+              final all-gather of (iter, status).  `value` is weak scaling (4096 QPs per GPU at every N, so
+              v_N / (N v_1) is meaningful); `strong_scaling` carries the same 4096 QPs split over the N GPUs.
+  mpc_single  (configs[1]) one cold solve of one such QP in fp64; the instance (x0 -> l, u) changes every
+              step.  A single QP does not shard: N>1 = N independent replicas ("replicas only").
   large_qp    (configs[2]) one cold solve of rand_qp(2000, 500, 500) (D=4000) in fp32.
-  mpc_batched (configs[3]) 4096 MPC QPs sharing W per GPU in one batched solve; N>1 shards
-              columns across GPUs (weak scaling), no data-path collective.
+At N=1 the line of the default workload carries full-step runs of the other two under `other_workloads`.
 
-Printed JSON (one line, rank 0): metric qp_solves_per_sec, value = whole-job solves/s with all
-inputs resident in HBM when the timed region starts (CUDA events around each launch, L2 flushed
-between steps), e2e = the same through the public Python API with HOST inputs (numpy l, u in,
-x out; wall clock incl. H2D/D2H), roofline for the dominant kernel, cpu_baseline = the CPU
-oracle (torch-CPU restatement of the reference, de-aliased) on this box's host cores.
+Printed JSON (one line, rank 0): metric qp_solves_per_sec, value = whole-job solves/s with all inputs resident
+in HBM when the timed region starts (CUDA events around each launch, L2 flushed between steps), e2e = the same
+through the public Python API with PINNED HOST inputs (l, u in; x and (iter, status) out; wall clock incl.
+H2D / D2H), roofline for the dominant kernel, cpu_baseline = the CPU oracle (torch-CPU restatement of the
+reference, de-aliased) on this box's host cores, gpu_launches = kernels the library launched in the timed
+region (counted by the library, rqp_kernel_launches()).
 
---impl reference times that CPU oracle alone on the same workload (the reference itself is
-Python + torch on CPU; /root/reference does not exist on the GPU box, so its restatement in
-oracle/ is what runs; kind "port").
+--impl reference times that CPU oracle alone on the same workload and `config` (the reference is Python + torch;
+/root/reference does not exist on the GPU box, so its restatement in oracle/ is what runs; kind "port").  For the
+batched workload the columns are independent, so the CPU arm may use every host core: it runs P worker
+processes x T torch threads (best of a few splits), each solving its share of a bounded sample of columns.
 """
 import argparse
 import json
@@ -204,24 +208,124 @@ def cpu_oracle_run(wl, n_solves, n_warm, threads=None):
     return len(times) / sum(times), times, iters, setup_s
 
 
+def _cpu_batch_worker(q_in, q_out, threads):
+    """Worker of cpu_oracle_batch_parallel: own oracle solver (shared W), solves the column blocks it is sent."""
+    import torch as _t
+    _t.set_num_threads(threads)
+    from oracle import reluqp_oracle as O
+    from reluqp.mpc import RandomLinMPC
+    plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+    s = None
+    while True:
+        job = q_in.get()
+        if job is None:
+            return
+        L, U = job
+        if s is None:
+            s = O.OracleSolver(plant.H, plant.g, plant.A, L[0], U[0], warm_starting=False)
+            s.update(l=L[0], u=U[0]); s.solve()                       # warm-up (first-call overheads)
+            q_out.put(("ready", 0, 0))
+            continue
+        iters = 0
+        for j in range(L.shape[0]):
+            s.update(l=L[j], u=U[j])
+            iters += s.solve().iter
+        q_out.put(("done", L.shape[0], iters))
+
+
+def cpu_oracle_batch_parallel(n_cols, n_steps, n_warm, seed=1000):
+    """The reference's CPU path on a batch of independent QPs with every host core it can use: P processes x T
+    torch threads, each process solving its share of `n_cols` columns per step with sequential
+    update(l, u) + solve() (reluqpth.py:159-183, 201-249).  A few (P, T) splits are tried on one step each and
+    the fastest runs the timed steps.  Returns (solves/s, per-step seconds, iterations, P, T)."""
+    import multiprocessing as mp
+    from reluqp.mpc import RandomLinMPC
+    ncpu = os.cpu_count() or 1
+    plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+    plant.rng = np.random.RandomState(seed)
+    L, U = plant.bounds(plant.sample_x0(n_cols))
+    ctx = mp.get_context("spawn")
+
+    def run_split(P, T, steps):
+        qi = [ctx.Queue() for _ in range(P)]
+        qo = ctx.Queue()
+        procs = [ctx.Process(target=_cpu_batch_worker, args=(qi[p], qo, T), daemon=True) for p in range(P)]
+        for pr in procs:
+            pr.start()
+        bounds = [(n_cols * p // P, n_cols * (p + 1) // P) for p in range(P)]
+        for p in range(P):                                   # setup + warm-up, untimed
+            qi[p].put((L[:1], U[:1]))
+        for _ in range(P):
+            qo.get()
+        times, iters = [], 0
+        for s in range(steps):
+            t0 = time.perf_counter()
+            for p, (a, b) in enumerate(bounds):
+                qi[p].put((L[a:b], U[a:b]))
+            for _ in range(P):
+                _, n, it = qo.get()
+                iters += it
+            times.append(time.perf_counter() - t0)
+        for p in range(P):
+            qi[p].put(None)
+        for pr in procs:
+            pr.join(timeout=5)
+        return times, iters
+
+    splits = sorted({(1, ncpu), (max(1, ncpu // 4), min(4, ncpu)), (max(1, ncpu // 2), min(2, ncpu)), (ncpu, 1)})
+    splits = [(P, T) for P, T in splits if P <= n_cols]
+    best, best_t = splits[0], None
+    for P, T in splits:
+        t, _ = run_split(P, T, 1)
+        if best_t is None or t[0] < best_t:
+            best, best_t = (P, T), t[0]
+    times, iters = run_split(best[0], best[1], n_warm + n_steps)
+    times = times[n_warm:]
+    return n_cols * len(times) / sum(times), times, iters * len(times) / (n_warm + n_steps), best[0], best[1]
+
+
+def single_config(args, wl, ninst, world):
+    """`config` of the single-QP workloads -- identical in both arms."""
+    return dict(workload=args.workload, description=wl["label"], instances=ninst,
+                multi_gpu="replicas only (a single QP does not shard)" if world > 1 else "single GPU",
+                l2="flushed between steps (512 MiB fill)",
+                timing="ours: CUDA events around each solve launch, summed; reference: host wall clock")
+
+
 def run_reference_arm(args, rank, world):
-    """--impl reference: the reference's CPU path (oracle port) on this box's host cores."""
+    """--impl reference: the reference's CPU path (oracle port) on this box's host cores, same `config`."""
     if rank != 0:
         return
-    wl = make_workload(args.workload if args.workload != "mpc_batched" else "mpc_batched")
-    per_step = 1 if args.workload != "mpc_batched" else 8     # bounded sample of the 4096-QP batch
-    n = max(1, args.steps) * per_step
-    nw = max(1, args.warmup) * per_step
+    if args.workload == "mpc_batched":
+        from bench_batched import batched_config
+        n_cols = min(args.batch, 256)                       # bounded sample of the batch per step
+        sps, times, iters, P, T = cpu_oracle_batch_parallel(n_cols, max(1, args.steps), max(0, min(args.warmup, 2)))
+        sample = ("{} of the {} columns per step, {} steps: {} worker processes x {} torch threads, each with its own "
+                  "oracle solver (shared W), sequential update(l,u)+solve() per column; extrapolates linearly to the "
+                  "batch".format(n_cols, args.batch, len(times), P, T))
+        line = dict(metric="qp_solves_per_sec", value=sps, unit="solves/s", n_gpus=args.gpus, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=1e3 * args.batch / sps, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
+                    config=batched_config(args, world),
+                    cpu_baseline=dict(value=sps, unit="solves/s", cores=P * T, processes=P, threads_per_process=T,
+                                      kind="port", sample=sample, host_cpus=os.cpu_count(),
+                                      us_per_admm_iter_per_core=1e6 * sum(times) * P / max(1.0, iters)),
+                    e2e=dict(value=sps, unit="solves/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    gpu_launches=0)
+        print(json.dumps(line))
+        return
+    wl = make_workload(args.workload)
+    n = max(1, args.steps)
+    nw = max(1, args.warmup)
     if args.workload == "large_qp":
         n, nw = min(n, 5), min(nw, 2)
     sps, times, iters, setup_s = cpu_oracle_run(wl, n, nw)
     cores = torch.get_num_threads()
     sample = "{} cold solves ({} warm-up) of: {}".format(len(times), nw, wl["label"])
     line = dict(metric="qp_solves_per_sec", value=sps, unit="solves/s", n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=1e3 * per_step / sps if args.workload != "mpc_batched" else
-                1e3 * 4096 / sps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                warmup=args.warmup, ms_per_step=1e3 / sps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f64" if wl["dtype"] == torch.float64 else "f32", data="synthetic", impl="reference",
-                config=dict(workload=args.workload, description=wl["label"]),
+                config=single_config(args, wl, wl["L"].shape[0], world),
                 cpu_baseline=dict(value=sps, unit="solves/s", cores=cores, kind="port", sample=sample,
                                   us_per_admm_iter=1e6 * sum(times) / max(1, sum(iters)),
                                   setup_s=setup_s, host_cpus=os.cpu_count()),
@@ -233,10 +337,10 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=0, help="0 = 20 (mpc_batched, large_qp) / 200 (mpc_single)")
+    ap.add_argument("--warmup", type=int, default=0, help="0 = 3 (mpc_batched, large_qp) / 10 (mpc_single)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mpc_single", choices=["mpc_single", "large_qp", "mpc_batched"])
+    ap.add_argument("--workload", default="mpc_batched", choices=["mpc_single", "large_qp", "mpc_batched"])
     ap.add_argument("--grid", type=int, default=0)
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--w-residency", type=int, default=0)
@@ -249,6 +353,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other workloads")
     args = ap.parse_args()
+    if args.steps <= 0:
+        args.steps = 200 if args.workload == "mpc_single" else 20
+    if args.warmup <= 0:
+        args.warmup = 10 if args.workload == "mpc_single" else 3
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -275,21 +383,22 @@ def main():
         line = run_single(args, rank, world, dev)
     if rank == 0 and line is not None:
         if world == 1 and not args.no_extras:
-            # the other BASELINE.json configs, short runs, for context (not the headline)
+            # the other BASELINE.json configs as full-step runs of their own (not the headline)
             import copy
             others = {}
             for wname in ("mpc_single", "large_qp", "mpc_batched"):
                 if wname == args.workload:
                     continue
                 a2 = copy.copy(args)
-                a2.workload, a2.no_cpu_baseline = wname, True
-                a2.steps, a2.warmup = (3, 3) if wname != "mpc_single" else (20, 3)
+                a2.workload, a2.no_cpu_baseline = wname, wname == "mpc_batched"
+                a2.steps, a2.warmup = (200, 10) if wname == "mpc_single" else (20, 3)
                 a2.grid = a2.block = a2.w_residency = a2.backoff = a2.prepoll = a2.exch_flags = 0
                 try:
                     d = run_batched(a2, 0, 1, dev) if wname == "mpc_batched" else run_single(a2, 0, 1, dev)
-                    others[wname] = {k: d[k] for k in ("value", "unit", "ms_per_step", "dtype", "iters_per_solve",
-                                                       "roofline", "e2e", "all_solved") if k in d}
-                    for k in ("us_per_admm_iter_in_kernel", "engine", "iters_max"):
+                    others[wname] = {k: d[k] for k in ("value", "unit", "steps", "warmup", "ms_per_step", "dtype",
+                                                       "iters_per_solve", "roofline", "e2e", "all_solved",
+                                                       "cpu_baseline", "gpu_launches", "latency_bound") if k in d}
+                    for k in ("us_per_admm_iter_in_kernel", "engine", "iters_max", "config"):
                         if k in d:
                             others[wname][k] = d[k]
                     others[wname]["roofline"] = {k: v for k, v in d["roofline"].items() if k != "note"}
@@ -390,12 +499,14 @@ def run_single(args, rank, world, dev):
     torch.cuda.synchronize()
     iters, checks, statuses, loop_us = [], [], [], []
     phases.clear()
+    launches0 = int(_cabi.load().rqp_kernel_launches())
     t_wall0 = time.perf_counter()
     for s in range(args.steps):
         it, ck, stt, lus = resident_step((args.warmup + s) % ninst, *evs[s])
         iters.append(it); checks.append(ck); statuses.append(stt); loop_us.append(lus)
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
+    n_launches = int(_cabi.load().rqp_kernel_launches()) - launches0
     if world > 1:
         dist.barrier()
     step_ms = [a.elapsed_time(b) for a, b in evs]
@@ -461,11 +572,9 @@ def run_single(args, rank, world, dev):
         metric="qp_solves_per_sec", value=value, unit="solves/s", n_gpus=world, steps=args.steps,
         warmup=args.warmup, ms_per_step=total_ms_max / args.steps, higher_is_better=True, scaling="weak",
         vs_baseline=None, dtype="f64" if elem == 8 else "f32", data="synthetic",
-        config=dict(workload=args.workload, description=wl["label"], instances=ninst,
-                    multi_gpu="replicas only" if world > 1 else "single GPU",
-                    l2="flushed between steps (512 MiB fill)", timing="CUDA events around each solve launch, summed",
-                    launch=dict(grid=launch["grid"], block=launch["block"], rows_per_cta=launch["rows_per_cta"],
-                                rows_in_smem=launch["rows_in_smem"])),
+        config=single_config(args, wl, ninst, world),
+        launch=dict(grid=launch["grid"], block=launch["block"], rows_per_cta=launch["rows_per_cta"],
+                    rows_in_smem=launch["rows_in_smem"]),
         us_per_admm_iter=1e3 * total_ms / sum(iters),
         us_per_admm_iter_in_kernel=sum(loop_us) / sum(iters),
         iters_per_solve=sum(iters) / len(iters),
@@ -496,7 +605,7 @@ def run_single(args, rank, world, dev):
         e2e=dict(value=solves / e2e_s_max, unit="solves/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                  ms_per_step=1e3 * e2e_s_max / args.steps,
                  api="ReLU_QP.update(l=numpy, u=numpy); ReLU_QP.solve(); results.x.cpu()"),
-        gpu_launches=args.steps,
+        gpu_launches=n_launches,
         clocks=clocks,
     )
     if not args.no_cpu_baseline:

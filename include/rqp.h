@@ -36,7 +36,8 @@ typedef enum rqp_status {
     RQP_ERR_CUDA = -3,          /* a CUDA runtime call failed (see rqp_last_cuda_error)     */
     RQP_ERR_WORKSPACE = -4,     /* workspace too small                                      */
     RQP_ERR_LAUNCH_TOO_LARGE = -5, /* cooperative grid does not fit on the device          */
-    RQP_ERR_WATCHDOG = -6       /* in-kernel wait exceeded the watchdog (reported in result.error) */
+    RQP_ERR_WATCHDOG = -6,      /* in-kernel wait exceeded the watchdog (reported in result.error) */
+    RQP_ERR_TOO_LARGE = -7      /* D = nx + 2 nc above the single-QP kernels' ceiling (rqp_size_limit)   */
 } rqp_status;
 
 /* result.status values; the Python layer maps them to the reference's strings
@@ -135,6 +136,11 @@ typedef struct rqp_result {
 #define RQP_TRACE_STRIDE 5
 
 int rqp_query(int device, rqp_caps* caps);
+
+/* Largest state dimension D = nx + 2 nc rqp_solve accepts for a dtype: a thread keeps its share of v in
+ * registers (at most 16 x 16 bytes with 512 threads), so D <= 16384 in fp64 and <= 32768 in fp32 (W_rho alone is
+ * then 2 / 4 GiB).  Larger problems get RQP_ERR_TOO_LARGE from rqp_workspace_size / rqp_solve. */
+int rqp_size_limit(int32_t dtype, int32_t* max_D);
 
 /* Bytes of workspace rqp_solve needs for this problem (exchange cells + reduction slots). */
 int rqp_workspace_size(const rqp_problem* prob, const rqp_settings* stng, size_t* bytes);
@@ -249,6 +255,10 @@ int rqp_stream_sync(void* stream);
  */
 int rqp_probe_bandwidth(const void* buf, size_t bytes, int32_t reps, float* ms_per_pass,
                         void* stream);
+
+/* Number of CUDA kernels this library has launched in this process so far (all entry points, all threads):
+ * the difference across a timed region is what bench.py reports as gpu_launches. */
+unsigned long long rqp_kernel_launches(void);
 
 const char* rqp_strerror(int code);
 /* cudaGetErrorString of the last CUDA failure seen by this library on this thread. */

@@ -1,5 +1,6 @@
 // extern "C" entry points of librqp.so (declared in include/rqp.h) and the small kernels that
 // sit beside the solve path: the bias refresh of ReLU_QP.update and a bandwidth probe.
+#include <atomic>
 #include <mutex>
 
 #include "rqp_common.cuh"
@@ -9,6 +10,9 @@ namespace rqp {
 
 static thread_local cudaError_t g_last_cuda = cudaSuccess;
 void set_last_cuda_error(cudaError_t e) { g_last_cuda = e; }
+
+static std::atomic<unsigned long long> g_kernel_launches{0};
+void note_launch(int n) { g_kernel_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 static int query_device(int device, rqp_caps* caps) {
     cudaDeviceProp prop;
@@ -92,6 +96,12 @@ int rqp_query(int device, rqp_caps* caps) {
     return query_device(device, caps);
 }
 
+int rqp_size_limit(int32_t dtype, int32_t* max_D) {
+    if (!max_D || (dtype != RQP_F32 && dtype != RQP_F64)) return RQP_ERR_BAD_ARG;
+    *max_D = 16 * 512 * (dtype == RQP_F64 ? 2 : 4);
+    return RQP_OK;
+}
+
 int rqp_workspace_size(const rqp_problem* prob, const rqp_settings* stng, size_t* bytes) {
     if (!bytes) return RQP_ERR_BAD_ARG;
     rqp_caps caps;
@@ -136,6 +146,7 @@ int rqp_update_bias(int32_t dtype, int32_t n_rho, int32_t D, int32_t nx, const v
                                                           nrows, nx);
     else
         return RQP_ERR_UNSUPPORTED;
+    note_launch();
     RQP_CUDA_TRY(cudaGetLastError());
     return RQP_OK;
 }
@@ -215,6 +226,7 @@ int rqp_probe_bandwidth(const void* buf, size_t bytes, int32_t reps, float* ms_p
     for (int r = 0; r < reps; ++r)
         probe_read_kernel<<<grid, block, 0, st>>>(static_cast<const float4*>(buf), n16, sink);
     RQP_CUDA_TRY(cudaEventRecord(e1, st));
+    note_launch(3 + reps);
     RQP_CUDA_TRY(cudaEventSynchronize(e1));
     float ms = 0.f;
     RQP_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
@@ -234,10 +246,13 @@ const char* rqp_strerror(int code) {
         case RQP_ERR_WORKSPACE: return "workspace too small";
         case RQP_ERR_LAUNCH_TOO_LARGE: return "cooperative launch does not fit on the device";
         case RQP_ERR_WATCHDOG: return "in-kernel wait exceeded the watchdog";
+        case RQP_ERR_TOO_LARGE: return "problem too large for the single-QP kernels (D = nx + 2 nc above rqp_size_limit)";
     }
     return "unknown rqp status";
 }
 
 const char* rqp_last_cuda_error(void) { return cudaGetErrorString(g_last_cuda); }
+
+unsigned long long rqp_kernel_launches(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
 
 }  // extern "C"

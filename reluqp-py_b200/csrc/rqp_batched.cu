@@ -875,10 +875,12 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
             RQP_CUDA_TRY(cudaMemsetAsync(c.counts, 0, size_t(c.n_rho) * 4, st));
             RQP_CUDA_TRY(cudaMemsetAsync(c.orig[lcur ^ 1], 0xff, size_t(cap) * 4, st));
             batch_hist<<<(cap + thr - 1) / thr, thr, 0, st>>>(c.key, cap, c.counts);
+            note_launch();
         }
         batch_scan<<<1, 32, 0, st>>>(c.counts, c.starts, c.cursor, c.tile_rho, c.btab, c.n_rho, lay.n_tiles,
                                      c.n_active, c.n_active_host);
         batch_scatter<T><<<warp_blocks, thr, 0, st>>>(c, cur, lcur, iter_now, status_out, copy_state);
+        note_launch(2);
         RQP_CUDA_TRY(cudaGetLastError());
         cur ^= 1;
         lcur ^= 1;
@@ -1036,6 +1038,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.b_all = c.b_all; a.bias_cols = with_g ? c.Bias[lcur] : nullptr;
         a.L = c.L; a.U = c.U; a.orig = c.orig[lcur]; a.nx = nx; a.nc = nc; a.D = D;
         a.kmask = kmask; a.n_rt64 = n_rt64;
+        note_launch();
         if (use_dmma && nact_host[0] >= dmma_min && DmmaLaunch<T, EPI_ITER>::ok(a)) {
             DmmaLaunch<T, EPI_ITER>::go(a, D, cap, nact_host[0] >= dmma_big, st);
         } else if (nact_host[0] < 2048) {
@@ -1072,6 +1075,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.kmask = nullptr; a.n_rt64 = n_rt64;
         const bool small = nact_host[0] < 2048;
         auto one = [&](int Mrows) {
+            note_launch();
             if (use_dmma && nact_host[0] >= dmma_min && DmmaLaunch<T, EPI_RAW>::ok(a))
                 DmmaLaunch<T, EPI_RAW>::go(a, Mrows, cap, nact_host[0] >= dmma_big, st);
             else if (small)
@@ -1092,6 +1096,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
 
     // ---- start: v = 0, rho index from the caller, first grouping into buffer 0
     batch_init_keys<T><<<(cap + thr - 1) / thr, thr, 0, st>>>(c);
+    note_launch();
     int rc = regroup(0, RQP_STATUS_MAX_ITER, 0, false);
     if (rc != RQP_OK) return rc;
     if (use_tc) {   // the kernel choice of the first window reads the tile counts written by the scan
@@ -1170,6 +1175,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
                 gemm_res(cur);
             }
             batch_check<T><<<warp_blocks, thr, 0, st>>>(c, cur, lcur, 0);
+            note_launch();
             rc = regroup(k, RQP_STATUS_SOLVED, 1, true);
             if (rc != RQP_OK) return rc;
             sweeps += 1;
@@ -1187,6 +1193,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
             gemm_res(cur);
         }
         batch_check<T><<<warp_blocks, thr, 0, st>>>(c, cur, lcur, 1);
+        note_launch();
         rc = regroup(stng->max_iter, RQP_STATUS_MAX_ITER, 1, true);
         if (rc != RQP_OK) return rc;
         RQP_CUDA_TRY(cudaStreamSynchronize(st));

@@ -982,6 +982,7 @@ int tc2_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& 
     int pairs = sm_count / 2;
     if (n_tiles < pairs) pairs = n_tiles;
     rqp_batched_tc2_kernel<<<2 * pairs, TC_THREADS, TC_SMEM_BYTES, st>>>(wh, wl, xh, xl, args);
+    note_launch();
     RQP_CUDA_TRY(cudaGetLastError());
     return RQP_OK;
 }
@@ -1016,6 +1017,7 @@ static int tc_launch_bn(const CUtensorMap& wh, const CUtensorMap& wl, const CUte
         cfg.numAttrs = 1;
     }
     RQP_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, wh, wl, xh, xl, xh1, xl1, args));
+    note_launch();
     return RQP_OK;
 }
 

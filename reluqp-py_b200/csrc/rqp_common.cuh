@@ -20,6 +20,10 @@ void set_last_cuda_error(cudaError_t e);
         }                                          \
     } while (0)
 
+// Process-wide count of the kernels this library has launched (rqp_kernel_launches() in the ABI): what
+// bench.py reports as gpu_launches instead of a formula.
+void note_launch(int n = 1);
+
 // Function attributes (dynamic shared memory opt-in) are per device: a process that drives several
 // GPUs must set them once on each, so the "already done" caches are indexed by the current device.
 constexpr int kMaxDevices = 64;

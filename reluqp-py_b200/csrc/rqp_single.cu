@@ -1024,6 +1024,7 @@ static int launch_tiny_tr(const SingleParams& prm, size_t smem, cudaStream_t str
         okb = smem;
     }
     rqp_tiny_kernel<T, TR><<<1, TINY_NT, smem, stream>>>(prm);
+    note_launch();
     RQP_CUDA_TRY(cudaGetLastError());
     return RQP_OK;
 }
@@ -1060,14 +1061,16 @@ int plan_single(const rqp_problem* prob, const rqp_settings* stng, const rqp_cap
     const int elem = prob->dtype == RQP_F64 ? 8 : 4;
     const int vec = 16 / elem;
     const int nvec = int(prob->ldw / vec);
+    // Size ceiling of the single-QP kernels: a thread keeps its columns of v in registers, at most 16 vector
+    // columns (16 bytes each) per thread, so ldw <= 16 * 512 * (16 / sizeof(T)): D <= 16384 in fp64, <= 32768 in
+    // fp32 (W_rho = 2 / 4 GiB, the 18-rho set 36 / 72 GiB).  Beyond that: RQP_ERR_TOO_LARGE (rqp_size_limit()).
     int block = stng->block;
     if (block == 0) block = (nvec > 16 * 256) ? 512 : 256;
     if (block != 256 && block != 512) return RQP_ERR_UNSUPPORTED;
     int cpt_rt = (nvec + block - 1) / block;
     int cpt = 1;
     while (cpt < cpt_rt) cpt *= 2;
-    if (cpt > 16) return RQP_ERR_UNSUPPORTED;
-    if (block == 512 && cpt > 8) return RQP_ERR_UNSUPPORTED;
+    if (cpt > 16) return stng->block == 0 ? RQP_ERR_TOO_LARGE : RQP_ERR_UNSUPPORTED;
     int grid = stng->grid > 0 ? stng->grid : caps.sm_count;
     if (grid > caps.sm_count) return RQP_ERR_LAUNCH_TOO_LARGE;
     int rpc = (D + grid - 1) / grid;
@@ -1142,6 +1145,7 @@ static int launch_one(const SingleParams& prm, const SinglePlan& plan, cudaStrea
     void* args[] = {const_cast<SingleParams*>(&prm)};
     RQP_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(plan.grid), dim3(NT), args,
                                              plan.smem_bytes, stream));
+    note_launch();
     return RQP_OK;
 }
 
@@ -1161,9 +1165,7 @@ static int launch_cpt(const SingleParams& prm, const SinglePlan& plan, cudaStrea
         case 2: return launch_one<T, 2, NT>(prm, plan, stream);
         case 4: return launch_one<T, 4, NT>(prm, plan, stream);
         case 8: return launch_one<T, 8, NT>(prm, plan, stream);
-        case 16:
-            if (NT == 256) return launch_one<T, 16, 256>(prm, plan, stream);
-            return RQP_ERR_UNSUPPORTED;
+        case 16: return launch_one<T, 16, NT>(prm, plan, stream);
     }
     return RQP_ERR_UNSUPPORTED;
 }

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .classes import BatchResults, to_tensor
+from .classes import BatchResults
 
 
 def layer_block_mask(W_all):
@@ -57,6 +57,50 @@ class BatchEngine(object):
         self.W_hi = self.W_lo = None
         self.kmask = None
         self.kmask_min = 0
+        self._stage = {}         # name -> (pinned host tensor, device tensor) for host inputs, largest batch seen
+        self._x_host = None
+
+    def pinned_inputs(self, B, with_g=False):
+        """Pinned host arrays ``(l [B, nc], u [B, nc][, g [B, nx]])`` in the solver dtype, as numpy views.  A
+        caller that fills these and passes them to ``solve`` skips the host-side staging copy: the arrays
+        go to the device with one asynchronous copy each."""
+        qp = self.solver.QP
+        out = []
+        for name, n in (("l", qp.nc), ("u", qp.nc)) + ((("g", qp.nx),) if with_g else ()):
+            out.append(torch.empty((int(B), n), dtype=self.dtype).pin_memory().numpy())
+        return tuple(out)
+
+    def pinned_output(self, B):
+        """Pinned host array ``x [B, nx]`` for ``solve(..., x_out=)``."""
+        return torch.empty((int(B), self.solver.QP.nx), dtype=self.dtype).pin_memory().numpy()
+
+    def _to_device(self, name, a, width):
+        """Host array (numpy / CPU tensor / sequence) or device tensor -> contiguous ``[B, width]`` device
+        tensor of the solver dtype.  Host data travel through ONE asynchronous copy from pinned memory: either
+        the caller's own pinned array or a persistent pinned staging buffer (pageable memory would make the
+        driver stage the copy itself, chunk by chunk and synchronously)."""
+        dev, dt = self.device, self.dtype
+        if torch.is_tensor(a) and a.device.type != "cpu":
+            return a.detach().to(device=dev, dtype=dt).contiguous()
+        t = torch.from_numpy(a) if isinstance(a, np.ndarray) else torch.as_tensor(a)
+        if t.dim() != 2 or t.shape[1] != width:
+            raise ValueError("{} must have shape [B, {}]".format(name, width))
+        B = int(t.shape[0])
+        ent = self._stage.get(name)
+        if ent is None or ent[1].shape[0] < B:
+            ent = [torch.empty((B, width), dtype=dt).pin_memory(), torch.empty((B, width), dtype=dt, device=dev), None]
+            self._stage[name] = ent
+        host, devbuf, ev = ent
+        src = t
+        if not (t.dtype == dt and t.is_contiguous() and t.is_pinned()):
+            if ev is not None:                 # the previous asynchronous copy may still be reading the buffer
+                ev.synchronize()
+            host[:B].copy_(t)
+            src = host[:B]
+        devbuf[:B].copy_(src, non_blocking=True)
+        ent[2] = torch.cuda.Event()
+        ent[2].record()
+        return devbuf[:B]
 
     def _block_mask(self):
         """Sparsity map of the layer matrices for the GEMM engines (``rqp_batch.kmask``), computed once per
@@ -116,30 +160,36 @@ class BatchEngine(object):
             self.ws.fill_(int(poison))
         return self.ws
 
-    def solve(self, l, u, g=None, engine=0):
-        """engine: 0 auto (fp32 -> tcgen05 3xTF32, fp64 -> tiled SIMT), 1 SIMT, 2 tcgen05."""
+    def solve(self, l, u, g=None, engine=0, x_out=None):
+        """engine: 0 auto (fp32 -> tcgen05 3xTF32 with chunked accumulation, fp64 -> DMMA tensor-core tiles;
+        few columns -> the single-QP kernel per column), 1 SIMT tiles, 2 tcgen05 (fp32), 4 / 5 / 6 tcgen05
+        with 128 / 64 / 32-column tiles.  ``x_out``: optional pinned host array / tensor ``[B, nx]`` that
+        receives the primal solutions (one asynchronous device -> host copy, waited for before returning)."""
         sv = self.solver
         qp = sv.QP
         nx, nc = qp.nx, qp.nc
         D = nx + 2 * nc
         dev, dt = self.device, self.dtype
-        L = to_tensor(l, dev, dt)
-        U = to_tensor(u, dev, dt)
-        if L.dim() != 2 or L.shape[1] != nc or U.shape != L.shape:
-            raise ValueError("l and u must both have shape [B, {}]".format(nc))
-        B = int(L.shape[0])
-        G = None
-        if g is not None:
-            G = to_tensor(g, dev, dt)
-            if G.shape != (B, nx):
-                raise ValueError("g must have shape [B, {}]".format(nx))
+        with torch.cuda.device(dev):
+            L = self._to_device("l", l, nc)
+            U = self._to_device("u", u, nc)
+            if L.dim() != 2 or L.shape[1] != nc or U.shape != L.shape:
+                raise ValueError("l and u must both have shape [B, {}]".format(nc))
+            B = int(L.shape[0])
+            G = None
+            if g is not None:
+                G = self._to_device("g", g, nx)
+                if G.shape != (B, nx):
+                    raise ValueError("g must have shape [B, {}]".format(nx))
         self._settings()
         ldv = (D + 3) // 4 * 4
         V = torch.zeros((B, ldv), dtype=dt, device=dev)
         rho_ind0 = int(np.argmin(np.abs(np.asarray(sv.layers.rho_list) - sv.settings.rho)))
         small = 40 if dt == torch.float64 else 12
         if engine == 0 and G is None and B <= small:
-            return self._solve_small(L, U, V, rho_ind0, nx, nc, D)
+            res = self._solve_small(L, U, V, rho_ind0, nx, nc, D)
+            self._copy_out(res, x_out)
+            return res
         ws = self._workspace(B)
         rho_ind = torch.full((B,), rho_ind0, dtype=torch.int32, device=dev)
         it = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -180,42 +230,85 @@ class BatchEngine(object):
             end.synchronize()
         self._keep = (L, U, G)
         self.first_window_ms = float(win_ms.value)
-        return BatchResults(x=V[:, :nx], z=V[:, nx:nx + nc], lam=V[:, nx + nc:D], iter=it, status_code=status,
-                            pri_res=pri, dua_res=dua, rho_estimate=rho, rho_ind=rho_ind,
-                            run_time=start.elapsed_time(end) / 1000.0, sweeps=int(sweeps.value))
+        res = BatchResults(x=V[:, :nx], z=V[:, nx:nx + nc], lam=V[:, nx + nc:D], iter=it, status_code=status,
+                           pri_res=pri, dua_res=dua, rho_estimate=rho, rho_ind=rho_ind,
+                           run_time=start.elapsed_time(end) / 1000.0, sweeps=int(sweeps.value))
+        self._copy_out(res, x_out)
+        return res
+
+    def _copy_out(self, res, x_out):
+        """x -> the caller's (pinned) host array: one strided device -> host copy, then a stream wait."""
+        if x_out is None:
+            return
+        dst = torch.from_numpy(x_out) if isinstance(x_out, np.ndarray) else x_out
+        if tuple(dst.shape) != tuple(res.x.shape) or dst.dtype != res.x.dtype or dst.device.type != "cpu":
+            raise ValueError("x_out must be a host array of shape {} and dtype {}".format(tuple(res.x.shape), res.x.dtype))
+        with torch.cuda.device(self.device):
+            dst.copy_(res.x, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        res.x_host = x_out
 
 
     def _solve_small(self, L, U, V, rho_ind0, nx, nc, D):
         """Few columns: the batched GEMM engines sit at their per-iteration latency floor (tens of
         microseconds) while the persistent single-QP kernel iterates in ~1.5 us, so column j is
-        solved by that kernel directly (same semantics by construction: it IS the single solve)."""
+        solved by that kernel directly (same semantics by construction: it IS the single solve).
+        Nothing of the single-QP solver's state is touched: the launches read l, u straight from rows of the
+        caller's arrays through a private copy of the problem struct, and use a private exchange workspace,
+        epoch counter and result records; all B launches are enqueued back to back and waited for once."""
         sv = self.solver
-        eng, qp = sv._engine, sv.QP
+        eng = sv._engine
         dev, dt = self.device, self.dtype
         B = L.shape[0]
-        keep_l, keep_u = qp.l.clone(), qp.u.clone()
-        it, status, rho_ind, pri, dua, rho = [], [], [], [], [], []
+        if getattr(self, "_small", None) is None:
+            prob = _cabi.rqp_problem.from_buffer_copy(eng.prob)
+            ws = torch.zeros(eng.ws.numel(), dtype=torch.uint8, device=dev)
+            self._small = dict(prob=prob, ws=ws, epoch=1, state=_cabi.rqp_state(), res=None)
+        sm = self._small
+        nbytes = C.sizeof(_cabi.rqp_result)
+        if sm["res"] is None or sm["res"].numel() < B * nbytes:
+            sm["res"] = torch.zeros(B * nbytes, dtype=torch.uint8).pin_memory()
+        eng._fill_settings()
+        stng = eng.stng
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        try:
+        with torch.cuda.device(dev):
+            stream = _cabi.raw_stream(dev.index)
+            t0.record()
             for j in range(B):
-                qp.l.copy_(L[j])
-                qp.u.copy_(U[j])
-                r = eng.run(V[j, :D], rho_ind0)
-                it.append(int(r.iter)); status.append(int(r.status)); rho_ind.append(int(r.rho_ind))
-                pri.append(float(r.pri_res)); dua.append(float(r.dua_res)); rho.append(float(r.rho_estimate))
-        finally:
-            qp.l.copy_(keep_l)
-            qp.u.copy_(keep_u)
-        t1.record()
-        t1.synchronize()
+                if sm["epoch"] + stng.max_iter + 2 > _cabi.EPOCH_LIMIT:
+                    sm["ws"].zero_()
+                    sm["epoch"] = 1
+                sm["prob"].l = L[j].data_ptr()
+                sm["prob"].u = U[j].data_ptr()
+                st = sm["state"]
+                st.v, st.rho_ind, st.epoch = V[j].data_ptr(), int(rho_ind0), sm["epoch"]
+                rc = self.lib.rqp_solve(C.byref(sm["prob"]), C.byref(stng), C.byref(st),
+                                        sm["res"].data_ptr() + j * nbytes, None, 0, sm["ws"].data_ptr(),
+                                        sm["ws"].numel(), stream)
+                _cabi.check(rc, "rqp_solve")
+                sm["epoch"] = int(st.epoch)
+            t1.record()
+            t1.synchronize()
+        recs = [_cabi.rqp_result.from_address(sm["res"].data_ptr() + j * nbytes) for j in range(B)]
+        for r in recs:
+            if r.error != 0:
+                sm["ws"].zero_()
+                sm["epoch"] = 1
+                raise RuntimeError("rqp_solve: {} (iter {})".format(self.lib.rqp_strerror(r.error).decode(), r.iter))
+        if sv.settings.verbose:
+            for j, r in enumerate(recs):
+                print("column {}: iter {}, status {}, res_p: {:.2e}, res_d: {:.2e}".format(
+                    j, int(r.iter), int(r.status), r.pri_res, r.dua_res))
         i32 = dict(dtype=torch.int32, device=dev)
-        return BatchResults(x=V[:, :nx], z=V[:, nx:nx + nc], lam=V[:, nx + nc:D], iter=torch.tensor(it, **i32),
-                            status_code=torch.tensor(status, **i32), pri_res=torch.tensor(pri, dtype=dt, device=dev),
-                            dua_res=torch.tensor(dua, dtype=dt, device=dev),
-                            rho_estimate=torch.tensor(rho, dtype=dt, device=dev),
-                            rho_ind=torch.tensor(rho_ind, **i32), run_time=t0.elapsed_time(t1) / 1000.0, sweeps=0)
+        return BatchResults(x=V[:, :nx], z=V[:, nx:nx + nc], lam=V[:, nx + nc:D],
+                            iter=torch.tensor([int(r.iter) for r in recs], **i32),
+                            status_code=torch.tensor([int(r.status) for r in recs], **i32),
+                            pri_res=torch.tensor([r.pri_res for r in recs], dtype=dt, device=dev),
+                            dua_res=torch.tensor([r.dua_res for r in recs], dtype=dt, device=dev),
+                            rho_estimate=torch.tensor([r.rho_estimate for r in recs], dtype=dt, device=dev),
+                            rho_ind=torch.tensor([int(r.rho_ind) for r in recs], **i32),
+                            run_time=t0.elapsed_time(t1) / 1000.0, sweeps=0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -228,31 +321,51 @@ def shard_bounds(B, world_size, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def solve_batch_sharded(solve_local, l, u, g=None, group=None, gather_x=False):
+def solve_batch_sharded(solve_local, l, u, g=None, group=None, gather_x=False, local_block=False, B_total=None):
     """Data-parallel batched solve over a ``torch.distributed`` process group (NCCL on GPUs, gloo in
-    the CPU tests).  Every rank passes the FULL ``l``, ``u`` (and ``g``); rank r solves its block
-    with ``solve_local(l_block, u_block, g_block) -> BatchResults`` (normally
-    ``ReLU_QP.solve_batch`` of a solver set up on that rank's GPU) and the per-column ``iter`` and
-    ``status`` (8 bytes per QP; optionally x) are all-gathered once.  Returns
-    ``(local BatchResults, iter [B], status [B], x [B, nx] or None)``."""
+    the CPU tests).  ``solve_local(l_block, u_block, g_block) -> BatchResults`` is normally
+    ``ReLU_QP.solve_batch`` of a solver set up on this rank's GPU.  Either every rank passes the FULL
+    ``l``, ``u`` (and ``g``) and rank r solves its contiguous block ``shard_bounds(B, world, r)``, or
+    (``local_block=True``) each rank passes only its own block (then ``B_total`` = number of columns of
+    the whole job, default world x block).  No collective touches the data path: the per-column ``iter``
+    and ``status`` (8 bytes per QP; optionally x) are all-gathered ONCE, into a preallocated tensor.
+    Returns ``(local BatchResults, iter [B], status [B], x [B, nx] or None)``."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    B = len(l)
-    lo, hi = shard_bounds(B, world, rank)
-    res = solve_local(l[lo:hi], u[lo:hi], None if g is None else g[lo:hi])
+    if local_block:
+        B = int(B_total) if B_total is not None else len(l) * world
+        lo, hi = shard_bounds(B, world, rank)
+        if hi - lo != len(l):
+            raise ValueError("rank {} owns columns [{}, {}) of {} but was given {} columns".format(rank, lo, hi, B, len(l)))
+        res = solve_local(l, u, g)
+    else:
+        B = len(l)
+        lo, hi = shard_bounds(B, world, rank)
+        res = solve_local(l[lo:hi], u[lo:hi], None if g is None else g[lo:hi])
     sizes = [shard_bounds(B, world, r) for r in range(world)]
     maxn = max(h - a for a, h in sizes)
+    even = all(h - a == maxn for a, h in sizes)
 
-    def gather(t, width=None):
-        shape = (maxn,) if width is None else (maxn, width)
-        pad = torch.zeros(shape, dtype=t.dtype, device=t.device)
-        pad[:t.shape[0]] = t
-        outs = [torch.empty_like(pad) for _ in range(world)]
-        dist.all_gather(outs, pad, group=group)
-        return torch.cat([o[:h - a] for o, (a, h) in zip(outs, sizes)])
+    def gather(t):
+        """[n_local, w] -> [B, w] on every rank (blocks padded to the largest when B % world != 0)"""
+        w = t.shape[1]
+        if t.shape[0] != maxn:
+            pad = torch.zeros((maxn, w), dtype=t.dtype, device=t.device)
+            pad[:t.shape[0]] = t
+            t = pad
+        out = torch.empty((world * maxn, w), dtype=t.dtype, device=t.device)
+        try:
+            dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+        except (RuntimeError, NotImplementedError):        # backend without the flat variant
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t.contiguous(), group=group)
+            out = torch.cat(parts)
+        if even:
+            return out
+        return torch.cat([out[r * maxn:r * maxn + (h - a)] for r, (a, h) in enumerate(sizes)])
 
-    packed = torch.stack([res.iter.to(torch.int32), res.status_code.to(torch.int32)], dim=1).contiguous()
-    both = gather(packed, 2)
-    x_all = gather(res.x.contiguous(), res.x.shape[1]) if gather_x else None
+    packed = torch.stack([res.iter.to(torch.int32), res.status_code.to(torch.int32)], dim=1)
+    both = gather(packed)
+    x_all = gather(res.x.contiguous()) if gather_x else None
     return res, both[:, 0], both[:, 1], x_all

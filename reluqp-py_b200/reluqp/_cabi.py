@@ -17,9 +17,9 @@ RQP_ERR_WATCHDOG = -6
 RQP_TRACE_STRIDE = 5
 EPOCH_LIMIT = 0x70000000
 
-EXPORTS = ("rqp_query", "rqp_workspace_size", "rqp_solve", "rqp_update_bias", "rqp_resolve",
+EXPORTS = ("rqp_query", "rqp_size_limit", "rqp_workspace_size", "rqp_solve", "rqp_update_bias", "rqp_resolve",
            "rqp_batch_workspace_size", "rqp_solve_batched", "rqp_copy_h2d", "rqp_stream_sync",
-           "rqp_probe_bandwidth",
+           "rqp_probe_bandwidth", "rqp_kernel_launches",
            "rqp_strerror", "rqp_last_cuda_error")
 
 
@@ -87,6 +87,7 @@ def load():
     lib = C.CDLL(LIB_PATH)
     vp, i32, sz = C.c_void_p, C.c_int32, C.c_size_t
     lib.rqp_query.argtypes = [C.c_int, C.POINTER(rqp_caps)]
+    lib.rqp_size_limit.argtypes = [i32, C.POINTER(i32)]
     lib.rqp_workspace_size.argtypes = [C.POINTER(rqp_problem), C.POINTER(rqp_settings), C.POINTER(sz)]
     lib.rqp_solve.argtypes = [C.POINTER(rqp_problem), C.POINTER(rqp_settings), C.POINTER(rqp_state),
                               vp, vp, i32, vp, sz, vp]
@@ -101,6 +102,8 @@ def load():
     lib.rqp_stream_sync.argtypes = [vp]
     for name in EXPORTS:
         getattr(lib, name).restype = C.c_int
+    lib.rqp_kernel_launches.argtypes = []
+    lib.rqp_kernel_launches.restype = C.c_ulonglong
     lib.rqp_strerror.argtypes = [C.c_int]
     lib.rqp_strerror.restype = C.c_char_p
     lib.rqp_last_cuda_error.argtypes = []

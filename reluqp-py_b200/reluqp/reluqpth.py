@@ -355,6 +355,15 @@ class ReLU_QP(object):
         else:
             self.QP = QP(setup_qp.H, setup_qp.g, setup_qp.A, setup_qp.l, setup_qp.u, device=device,
                          precision=precision)
+        if device.type == "cuda":          # refuse oversized problems before the layer matrices are formed
+            lim = C.c_int32(0)
+            _cabi.check(_cabi.load().rqp_size_limit(_cabi.dtype_code(precision), C.byref(lim)), "rqp_size_limit")
+            D = self.QP.nx + 2 * self.QP.nc
+            if D > lim.value:
+                raise ValueError(
+                    "problem too large for the single-QP kernels: D = nx + 2*nc = {} exceeds {} for {} (a thread "
+                    "keeps its share of the state in registers; include/rqp.h: rqp_size_limit)".format(
+                        D, lim.value, precision))
         self._pack_vectors()
         self.layers = ReLU_Layer(QP=self.QP, settings=st, setup_QP=setup_qp)
         self._tuning = launch_tuning
@@ -617,14 +626,24 @@ class ReLU_QP(object):
         return None
 
     # ------------------------------------------------------------------ batched (additive API)
-    def solve_batch(self, l, u, g=None, engine=0):
-        """Solve B QPs that share this solver's H, A (hence every W_rho) and differ in l, u
-        (``[B, nc]``) and optionally g (``[B, nx]``).  Column j is defined as what the reference
-        would return for ``update(l=l[j], u=u[j][, g=g[j]])`` followed by a cold ``solve()``.
-        Returns a ``BatchResults``; nothing of the single-QP state is touched."""
+    def _batch_engine(self):
         from ._batch import BatchEngine
         if self._engine is None:
             raise RuntimeError("ReLU_QP.solve_batch needs a CUDA device; there is no CPU fallback")
         if self._batch is None:
             self._batch = BatchEngine(self)
-        return self._batch.solve(l, u, g, engine=engine)
+        return self._batch
+
+    def solve_batch(self, l, u, g=None, engine=0, x_out=None):
+        """Solve B QPs that share this solver's H, A (hence every W_rho) and differ in l, u
+        (``[B, nc]``) and optionally g (``[B, nx]``).  Column j is defined as what the reference
+        would return for ``update(l=l[j], u=u[j][, g=g[j]])`` followed by a cold ``solve()``.
+        Host arrays travel with one asynchronous copy each (directly from the caller's memory when it is
+        pinned, see ``pinned_batch_arrays``); ``x_out`` (pinned host ``[B, nx]``) receives x.
+        Returns a ``BatchResults``; the single-QP state (``output``, ``rho_ind``, ``QP.l/u``) is not touched."""
+        return self._batch_engine().solve(l, u, g, engine=engine, x_out=x_out)
+
+    def pinned_batch_arrays(self, B, with_g=False):
+        """``(l, u[, g], x_out)`` as pinned host numpy arrays of the right shapes and dtype for ``solve_batch``."""
+        be = self._batch_engine()
+        return be.pinned_inputs(B, with_g) + (be.pinned_output(B),)

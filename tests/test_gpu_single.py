@@ -495,3 +495,29 @@ def test_infeasible_runs_to_max_iter():
     res = m.solve()
     ref = O.OracleSolver(H, g, A, l, u, max_iter=200).solve()
     assert res.info.status == ref.status == "max_iters_reached" and res.info.iter == 200
+
+
+def test_size_ceiling():
+    """the single-QP kernels keep a thread's share of v in registers.  Up to 16 vector columns per
+    thread with 512 threads: D <= 16384 in fp64 (round 1 stopped at 8192 with an unhelpful 'unsupported shape').
+    Just above the old ceiling the 512-thread kernel must run and agree with the oracle; above the new one
+    setup must refuse with a clear message before anything large is allocated."""
+    rng = np.random.RandomState(0)
+    nx, nc = 4100, 2050                              # D = 8200 > 8192: block 512, 16 columns per thread
+    M = rng.randn(nx, 64)
+    H = M @ M.T / 64 + np.eye(nx)
+    A = rng.randn(nc, nx) / np.sqrt(nx)
+    g = rng.randn(nx)
+    l, u = -np.ones(nc), np.ones(nc)
+    kw = dict(adaptive_rho=False, max_iter=20)       # one rho (W = 538 MB), 20 plain iterations, no check
+    m = gpu_model((H, g, A, l, u), **kw)
+    v = m.output
+    res = m.solve()
+    assert m.last_launch["block"] == 512 and res.info.iter == 20
+    ref = O.OracleSolver(H, g, A, l, u, **kw).solve()
+    assert rel_err(v[:nx].cpu().numpy(), ref.x.numpy()) < 1e-9
+    del m
+    H2 = np.eye(8200)
+    A2 = np.zeros((4100, 8200))                      # D = 16400 > 16384
+    with pytest.raises(ValueError, match="too large for the single-QP kernels"):
+        gpu_model((H2, np.zeros(8200), A2, -np.ones(4100), np.ones(4100)), adaptive_rho=False)

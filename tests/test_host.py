@@ -168,7 +168,7 @@ def test_cabi_exports_match_header():
     sizes agree with the C layout rules."""
     assert os.path.exists(_cabi.LIB_PATH), "build librqp.so first: make -C reluqp-py_b200"
     hdr = open(os.path.join(REPO, "include", "rqp.h")).read()
-    declared = set(re.findall(r"^(?:int|const char\*)\s+(rqp_\w+)\s*\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^(?:int|const char\*|unsigned long long)\s+(rqp_\w+)\s*\(", hdr, flags=re.M))
     assert declared == set(_cabi.EXPORTS)
     lib = ctypes.CDLL(_cabi.LIB_PATH)
     for name in declared:
@@ -183,6 +183,12 @@ def test_cabi_exports_match_header():
     # bad arguments are reported, not crashed on (no GPU needed: checks come first)
     assert lib.rqp_update_bias(1, 0, 0, 0, None, None, None, None) == -1
     assert lib.rqp_query(0, None) == -1
+    lim = ctypes.c_int32(0)
+    assert lib.rqp_size_limit(1, ctypes.byref(lim)) == 0 and lim.value == 16384
+    assert lib.rqp_size_limit(0, ctypes.byref(lim)) == 0 and lim.value == 32768
+    assert b"too large" in lib.rqp_strerror(-7)
+    lib.rqp_kernel_launches.restype = ctypes.c_ulonglong
+    assert lib.rqp_kernel_launches() == 0
 
 
 def test_layer_block_mask_matches_brute_force():

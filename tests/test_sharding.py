@@ -47,6 +47,11 @@ def _worker(rank, world, port, out_dir):
                                                      dtype=torch.int32))
 
     local, it, status, x = solve_batch_sharded(solve_local, L, U, gather_x=True)
+    # the same job with every rank passing only ITS block (what bench.py does with pinned per-rank arrays)
+    from reluqp._batch import shard_bounds as sb
+    lo, hi = sb(7, world, rank)
+    _, it2, status2, x2 = solve_batch_sharded(solve_local, L[lo:hi], U[lo:hi], gather_x=True, local_block=True, B_total=7)
+    assert torch.equal(it, it2) and torch.equal(status, status2) and torch.equal(x, x2)
     torch.save(dict(it=it, status=status, x=x, n_local=len(local.iter)), os.path.join(out_dir, "r{}.pt".format(rank)))
     dist.barrier()
     dist.destroy_process_group()

@@ -349,7 +349,7 @@ def main():
     ap.add_argument("--exch-flags", type=int, default=0)
     ap.add_argument("--batch", type=int, default=4096, help="QPs per GPU for --workload mpc_batched")
     ap.add_argument("--batch-dtype", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--batch-engine", type=int, default=0, help="0 auto, 1 SIMT, 2 tcgen05 1-CTA, 3 tcgen05 CTA pair")
+    ap.add_argument("--batch-engine", type=int, default=0, help="0 auto, 1 SIMT, 2 tcgen05 1-CTA, 4/5/6 tcgen05 with 128/64/32-column tiles")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other workloads")
     args = ap.parse_args()

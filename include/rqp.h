@@ -188,8 +188,9 @@ typedef struct rqp_batch {
     void* rho_estimate;         /* [B] out                                               */
     /* GEMM engine: 0 auto (fp32 with W_hi/W_lo -> tcgen05 3xTF32 cta_group::1 with chunked accumulation,
      * tile width picked per check window; fp64 -> DMMA mma.sync.m8n8k4.f64), 1 SIMT (FMA / DFMA tiles),
-     * fp32 only: 2 = tcgen05 cta_group::1 as in auto, 3 tcgen05 cta_group::2 (256x256 pair tiles, one
-     * accumulator over all of K), 4 / 5 / 6 tcgen05 cta_group::1 with 128 / 64 / 32-column tiles */
+     * fp32 only: 2 = tcgen05 cta_group::1 as in auto, 4 / 5 / 6 tcgen05 cta_group::1 with 128 / 64 / 32-column
+     * tiles.  (3 was round 1's cta_group::2 pair-tile kernel: removed -- one accumulator over all of K cost it
+     * a third more ADMM iterations than the chunked 1-CTA kernels; RQP_ERR_BAD_ARG now.) */
     int32_t engine;
     /* 1: W_hi / W_lo carry nc + 2 nx extra rows after the n_rho * D rows of the layer matrices: the TF32
      * planes of the residual operator [A 0 0; H 0 0; 0 0 A'] (row-major, ldw), so that A x, H x and

@@ -31,7 +31,7 @@
 namespace rqp {
 
 constexpr int kMaxSplitItems = 192;   // >= number of SMs: split-K work items (tile, rank) never exceed one per SM
-constexpr int BALIGN = 256;  // bucket alignment in slots = widest GEMM column tile (cta_group::2 pair tile)
+constexpr int BALIGN = 256;  // bucket alignment in slots (a multiple of the widest GEMM column tile, 128)
 
 template <typename T>
 struct BatchCtx {
@@ -822,7 +822,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     bool use_tc = false;
     if (std::is_same<T, float>::value) {
         const bool have_planes = bt->W_hi != nullptr && bt->W_lo != nullptr;
-        if (bt->engine < 0 || bt->engine > 6) return RQP_ERR_BAD_ARG;
+        if (bt->engine < 0 || bt->engine > 6 || bt->engine == 3) return RQP_ERR_BAD_ARG;
         if (bt->engine >= 2 && !have_planes) return RQP_ERR_BAD_ARG;
         use_tc = have_planes && bt->engine != 1;
     } else if (bt->engine >= 2) {
@@ -899,9 +899,6 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     // 128 x 128 tiles (half the operand traffic per flop) above
     const int dmma_big = getenv("RQP_DMMA_BIG") ? atoi(getenv("RQP_DMMA_BIG"))
                                                 : 64 * (2 * sm_count / ((D + 63) / 64)) + 1;
-    // auto never picks the CTA-pair kernel: it accumulates all of K in one TMEM accumulator, and the extra
-    // ADMM iterations that costs (see chunk_kb) outweigh its better operand reuse; engine 3 forces it
-    const int pair_min = getenv("RQP_PAIR_MIN") ? atoi(getenv("RQP_PAIR_MIN")) : 0x7fffffff;
     // residual products A x, H x, A' lambda on the tensor path: the W planes carry the residual operator
     // after the n_rho layer matrices (rqp_batch.res_planes)
     const bool res_tc = use_tc && bt->res_planes != 0 && getenv("RQP_NO_RES_TC") == nullptr;
@@ -909,8 +906,18 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     // 2 k-blocks (64 state elements) for the rows of the x block -- the rows whose rounding error the next
     // iteration multiplies by 1e3 * rho; measured on the C4 family: 169 -> 128 mean ADMM iterations, the
     // same as plain fp32 FMA.  RQP_TC_CHUNK=0 turns it off, RQP_TC_CHUNK_ALL=1 chunks every row tile.
-    const int tc_chunk = getenv("RQP_TC_CHUNK") ? atoi(getenv("RQP_TC_CHUNK")) : 2;
-    const bool tc_chunk_x = getenv("RQP_TC_CHUNK_ALL") == nullptr;
+    // Escalation for stragglers: the accumulator's truncation is a BIAS (every add rounds toward zero), i.e. a small
+    // systematic perturbation of W_rho, and on some families (rand_qp data with per-column g, eps_abs = 1e-4:
+    // |H x| ~ 570, threshold 1e-3) 2-block chunks leave the dual residual floating just above the threshold -- 782
+    // iterations on average with 9 of 96 columns never terminating, where 1-block chunks need 187 (plain fp32 FMA:
+    // 191, the reference's fp32 loop: 189).  1-block chunks cost the MPC bench 5 % for no fewer iterations, so the
+    // first tc_escalate_k iterations (8 check windows by default: every MPC column but a handful is done by then)
+    // run with 2-block chunks on the x rows and whatever is still active afterwards gets 1-block chunks on every row.
+    const int tc_chunk_env = getenv("RQP_TC_CHUNK") ? atoi(getenv("RQP_TC_CHUNK")) : -1;
+    const bool tc_chunk_all_env = getenv("RQP_TC_CHUNK_ALL") != nullptr;
+    const int tc_escalate_k = getenv("RQP_TC_ESCALATE") ? atoi(getenv("RQP_TC_ESCALATE")) : 8 * stng->check_interval;
+    int tc_chunk = tc_chunk_env >= 0 ? tc_chunk_env : 2;
+    bool tc_chunk_x = !tc_chunk_all_env;
     // tensor maps: W planes (128-row boxes) and the state planes with 128 / 64 / 32-row boxes
     CUtensorMap map_wh, map_wl, map_xh[3][2], map_xl[3][2];
     static const int kBoxRows[3] = {128, 64, 32};
@@ -946,9 +953,6 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     // kernel (one cooperative launch per check window, per-column-tile dependencies inside the kernel);
     // steps == 1 is one iteration, `pdl`: launched as a programmatic dependent of the previous iteration.
     // The plain fp32 state is written by the last iteration of the launch when write_plain is set.
-    auto one_sm_engine = [&]() {
-        return bt->engine == 2 || bt->engine >= 4 || (bt->engine != 3 && nact_host[0] < pair_min);
-    };
     // split-K: with fewer tiles than SMs, `ks` CTAs share a tile's k-blocks (largest of 8 / 4 / 2 that still
     // gives every work item its own SM); the per-tile latency -- 360 MMAs at ~66 cycles whatever the tile
     // width -- drops accordingly.  Changes the summation order (partials are added in rank order), so the
@@ -1001,7 +1005,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.steps = steps; a.done = nullptr;
         a.kmask = kmask; a.n_rt64 = n_rt64; a.rot = 0; a.ticket = nullptr;
         a.dbg = static_cast<unsigned long long*>(bt->reserved_dbg);
-        if (one_sm_engine()) {
+        {
             // 1-CTA tiles of 128 rows x BN columns.  BN is the widest tile that still gives every active
             // column tile its own SM in one wave (engine 4 / 5 / 6 force 128 / 64 / 32).
             a.n_row_tiles = (D + 127) / 128;
@@ -1024,10 +1028,6 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
             return tc_launch(map_wh, map_wl, map_xh[b][src], map_xl[b][src], map_xh[b][src ^ 1], map_xl[b][src ^ 1], a,
                              kBoxRows[b], bound, pdl, sm_count, st);
         }
-        if (steps != 1) return RQP_ERR_BAD_ARG;
-        a.ksplit = 1; a.scratch = nullptr; a.kcnt = nullptr;
-        a.n_col_tiles = cap / 256; a.n_row_tiles = (D + 255) / 256;   // CTA-pair tiles: 256 x 256
-        return tc2_launch(map_wh, map_wl, map_xh[0][src], map_xl[0][src], a, sm_count, st);
     };
     auto gemm_iter = [&](int src) {
         GemmArgs<T> a;
@@ -1115,6 +1115,10 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         if (k + steps > stng->max_iter) steps = stng->max_iter - k;
         const double tw0 = trace_windows ? now_us() : 0.0;
         const int nact_w = nact_host[0], t32_w = nact_host[1];
+        if (tc_chunk_env < 0 && tc_escalate_k > 0 && k >= tc_escalate_k) {   // stragglers: finest chunks, every row
+            tc_chunk = 1;
+            tc_chunk_x = false;
+        }
         // Window mode pays when a CTA owns more than one tile (the epilogue of one overlaps the mainloop of
         // the next across iterations: 1.47 -> 1.25 ms per window at 4096 columns) and when tiles are split
         // over K (short mainloops: the relaunch cost of one kernel per iteration would dominate; B = 32:
@@ -1131,7 +1135,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         const int n_rt128 = (D + 127) / 128;
         const int tiles_w = use_tc ? nact_host[3 - pick_bn(n_rt128, bt->engine)] * n_rt128 : 0;
         const bool window_pays = use_tc && (tiles_w > sm_count || pick_ksplit(tiles_w, nk_iter) > 1);
-        if (use_tc && steps > 1 && one_sm_engine() && (tc_window == 2 || (tc_window == 1 && window_pays))) {
+        if (use_tc && steps > 1 && (tc_window == 2 || (tc_window == 1 && window_pays))) {
             // the whole window in one cooperative launch
             rc = gemm_iter_tc(cur, steps, true, false);
             if (rc != RQP_OK) return rc;
@@ -1140,7 +1144,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
             for (int s = 0; s < steps; ++s) {
                 if (use_tc) {
                     // last step of a window also writes the plain state; steps 2.. are programmatic
-                    // dependents of the previous step (the pair kernel ignores the flag)
+                    // dependents of the previous step
                     rc = gemm_iter_tc(cur, 1, s == steps - 1, s > 0 && pdl_ok);
                     if (rc != RQP_OK) return rc;
                 } else {

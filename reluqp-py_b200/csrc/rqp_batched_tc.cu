@@ -28,13 +28,9 @@ namespace rqp {
 constexpr int TC_BM = 128;       // state rows per tile (UMMA M)
 constexpr int TC_BN = 128;       // columns per tile (UMMA N) of the full-size 1-CTA kernel
 constexpr int TC_BK = 32;        // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                 // 16 KB per operand plane
-constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;                // W_hi, W_lo, X_hi, X_lo
 constexpr int TC_ACC_STAGES = 2;
 constexpr int TC_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
-constexpr int TC_EPI_WARPS = 8;
-constexpr size_t TC_SMEM_BYTES = size_t(TC_STAGES) * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 // 1-CTA kernel, templated on the column-tile width BN.  Narrow tiles (64, 32 columns) are for check
 // windows with few active columns: the per-iteration latency of a tile is the time one SM needs to
@@ -750,192 +746,6 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// =============================================================================================
-// cta_group::2 variant: a CTA PAIR (cluster of 2, same TPC) computes a 256 x 256 output tile.
-// Each CTA stages its own 128 state rows of W (A operand) and its own 128 of the tile's 256 columns
-// (half of the B operand); the pair's MMA (issued by the leader, rank 0) reads A from each CTA's own
-// shared memory and B from BOTH, so every operand byte feeds twice the MMA work of the 1-CTA kernel.
-// Protocol (as in CUTLASS sm100 2-SM pipelines): only the leader arms the full barrier, with the bytes
-// of both CTAs; both CTAs' TMA loads complete on the leader's barrier (peer bit of the mbarrier
-// address cleared); tcgen05.commit multicasts to the barriers of both CTAs; both epilogues arrive
-// remotely on the leader's accumulator-empty barrier.
-// =============================================================================================
-constexpr int TC2_BN = 256;                                        // columns per pair tile
-constexpr int TC2_TMEM_COLS = TC_ACC_STAGES * TC2_BN;              // 512: all of TMEM
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;                     // cute::Sm100MmaPeerBitMask
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, int c0, int c1,
-                                                uint64_t* leader_bar_local_alias) {
-    // the barrier operand is THIS CTA's address of the barrier with the peer bit cleared = the leader's
-    const uint32_t bar = smem_u32(leader_bar_local_alias) & kPeerBitMask;
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
-        "[%2];" ::"r"(smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
-                 "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                              uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
-    const uint16_t mask = 3;   // both CTAs of the pair
-    asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-            smem_u32(bar)),
-        "h"(mask)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar_local_alias) {
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar_local_alias) & kPeerBitMask)
-                 : "memory");
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-rqp_batched_tc2_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
-                       const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
-                       const TcArgs a) {
-    extern __shared__ unsigned char tc_smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) &
-                                                            ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + size_t(TC_STAGES) * TC_STAGE_BYTES);
-    uint64_t* full = bars;
-    uint64_t* empty = bars + TC_STAGES;
-    uint64_t* acc_full = bars + 2 * TC_STAGES;
-    uint64_t* acc_empty = acc_full + TC_ACC_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + TC_ACC_STAGES);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();          // 0 = leader
-    const int pair = blockIdx.x >> 1;
-    const int n_pairs = gridDim.x >> 1;
-    const int n_tiles = a.n_col_tiles * a.n_row_tiles;   // pair tiles: 256 rows x 256 columns
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&map_wh); prefetch_tmap(&map_wl); prefetch_tmap(&map_xh); prefetch_tmap(&map_xl);
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < TC_ACC_STAGES; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 2 * TC_EPI_WARPS); }
-        fence_mbar_init();
-    }
-    if (warp == 1) tmem_alloc_2sm(tmem_slot, TC2_TMEM_COLS);
-    tc_fence_before();
-    cluster_sync_all();        // barriers of BOTH CTAs are initialised before any remote arrive
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ================= TMA producer (both CTAs) =================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int t = pair; t < n_tiles; t += n_pairs) {
-                const int ct = t / a.n_row_tiles, rt = t % a.n_row_tiles;
-                const int rho = a.tile_rho[ct];
-                if (rho < 0) continue;
-                const int wrow = rho * a.D + rt * 256 + int(rank) * TC_BM;     // own 128 state rows
-                const int xrow = ct * TC2_BN + int(rank) * 128;               // own half of the columns
-                for (int kb = 0; kb < a.k_blocks; ++kb) {
-                    mbar_wait(empty + stage, phase ^ 1u);
-                    unsigned char* sp = base + size_t(stage) * TC_STAGE_BYTES;
-                    if (rank == 0) mbar_expect_tx(full + stage, 2 * TC_STAGE_BYTES);
-                    tma_load_2d_2sm(sp, &map_wh, kb * TC_BK, wrow, full + stage);
-                    tma_load_2d_2sm(sp + TC_TILE_BYTES, &map_wl, kb * TC_BK, wrow, full + stage);
-                    tma_load_2d_2sm(sp + 2 * TC_TILE_BYTES, &map_xh, kb * TC_BK, xrow, full + stage);
-                    tma_load_2d_2sm(sp + 3 * TC_TILE_BYTES, &map_xl, kb * TC_BK, xrow, full + stage);
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ================= MMA issuer (leader CTA only) =================
-        if (rank == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(256, TC2_BN);
-            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (int t = pair; t < n_tiles; t += n_pairs) {
-                const int ct = t / a.n_row_tiles;
-                if (a.tile_rho[ct] < 0) continue;
-                mbar_wait(acc_empty + acc, acc_phase ^ 1u);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * TC2_BN;
-                for (int kb = 0; kb < a.k_blocks; ++kb) {
-                    mbar_wait(full + stage, phase);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        unsigned char* sp = base + size_t(stage) * TC_STAGE_BYTES;
-                        const uint64_t dwh = make_kmajor_sw128_desc(sp);
-                        const uint64_t dwl = make_kmajor_sw128_desc(sp + TC_TILE_BYTES);
-                        const uint64_t dxh = make_kmajor_sw128_desc(sp + 2 * TC_TILE_BYTES);
-                        const uint64_t dxl = make_kmajor_sw128_desc(sp + 3 * TC_TILE_BYTES);
-#pragma unroll
-                        for (int k = 0; k < TC_BK / 8; ++k) {
-                            const uint64_t off = uint64_t((k * 8 * 4) >> 4);
-                            umma_tf32_2sm(d_tmem, dwh + off, dxh + off, idesc, (kb | k) != 0 ? 1u : 0u);
-                            umma_tf32_2sm(d_tmem, dwh + off, dxl + off, idesc, 1u);
-                            umma_tf32_2sm(d_tmem, dwl + off, dxh + off, idesc, 1u);
-                        }
-                        umma_commit_2sm(empty + stage);
-                        if (kb == a.k_blocks - 1) umma_commit_2sm(acc_full + acc);
-                    }
-                    __syncwarp();
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
-                }
-                if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
-            }
-        }
-    } else {
-        // ================= epilogue (warps 2..5 of both CTAs) =================
-        const int quarter = warp & 3;
-        uint32_t acc = 0, acc_phase = 0;
-        for (int t = pair; t < n_tiles; t += n_pairs) {
-            const int ct = t / a.n_row_tiles, rt = t % a.n_row_tiles;
-            const int rho = a.tile_rho[ct];
-            if (rho < 0) continue;
-            mbar_wait(acc_full + acc, acc_phase);
-            tc_fence_after();
-            const int m = rt * 256 + int(rank) * TC_BM + quarter * 32 + lane;
-            const EpiRow e = make_epi_row(a, m, rho, a.Yh, a.Yl, a.Yplain);
-            const uint32_t taddr = tmem_base + acc * TC2_BN + (uint32_t(quarter * 32) << 16);
-            const int half = (warp - 2) >> 2;
-#pragma unroll 1
-            for (int c0 = half * (TC2_BN / 2); c0 < (half + 1) * (TC2_BN / 2); c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(taddr + c0, r);
-                tc_epilogue_chunk(a, e, r, ct * TC2_BN + c0, lane);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader(acc_empty + acc);
-            if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
-        }
-    }
-    tc_fence_before();
-    cluster_sync_all();
-    if (warp == 1) tmem_dealloc_2sm(tmem_base, TC2_TMEM_COLS);
-}
-
 // ---------------------------------------------------------------------------------------------
 // host: tensor maps + launch
 // ---------------------------------------------------------------------------------------------
@@ -967,24 +777,6 @@ int tc_make_map(CUtensorMap* map, const void* ptr, long long rows, long long col
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? RQP_OK : RQP_ERR_CUDA;
-}
-
-int tc2_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,
-               const TcArgs& args, int sm_count, cudaStream_t st) {
-    static bool attr_set[kMaxDevices] = {};
-    const int dev = current_device_slot();
-    if (!attr_set[dev]) {
-        RQP_CUDA_TRY(cudaFuncSetAttribute(rqp_batched_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          int(TC_SMEM_BYTES)));
-        attr_set[dev] = true;
-    }
-    const int n_tiles = args.n_col_tiles * args.n_row_tiles;
-    int pairs = sm_count / 2;
-    if (n_tiles < pairs) pairs = n_tiles;
-    rqp_batched_tc2_kernel<<<2 * pairs, TC_THREADS, TC_SMEM_BYTES, st>>>(wh, wl, xh, xl, args);
-    note_launch();
-    RQP_CUDA_TRY(cudaGetLastError());
-    return RQP_OK;
 }
 
 template <int BN>

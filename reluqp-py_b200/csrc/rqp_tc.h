@@ -6,7 +6,7 @@
 namespace rqp {
 
 struct TcArgs {
-    const int* tile_rho;    // [cap / 256] rho index per 256-slot group (pair kernel)
+    const int* tile_rho;    // [cap / BALIGN] rho index per slot group (SIMT / DMMA engines; unused by tcgen05)
     const int* btab;        // bucket table: {nb, (rho, first slot, active columns) x nb} (1-CTA kernels)
     const int* orig;        // [cap]
     const float* b_all;     // [n_rho][D]
@@ -39,8 +39,6 @@ struct TcArgs {
 
 // 2-D fp32 row-major [rows][ld] tensor, box = 32 columns (128 B) x box_rows rows, SWIZZLE_128B, zero OOB fill
 int tc_make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows = 128);
-int tc2_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,
-               const TcArgs& args, int sm_count, cudaStream_t st);
 // xh / xl: planes read by even iterations (the only ones unless window mode), xh1 / xl1: by odd iterations
 int tc_launch(const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& xh, const CUtensorMap& xl,
               const CUtensorMap& xh1, const CUtensorMap& xl1, const TcArgs& args, int bn, int n_tiles_bound, bool pdl,

@@ -1,7 +1,7 @@
 """probe (not a test): whole-solve time of the batched fp32 path per engine / tile width / PDL setting.
 
     python tools/batched_probe.py [B ...]      e.g. 4096 16384
-engine: 0 auto, 1 SIMT, 2 tcgen05 1-CTA auto width, 3 CTA pair, 4/5/6 1-CTA with 128/64/32-column tiles."""
+engine: 0 auto, 1 SIMT, 2 tcgen05 1-CTA auto width, 4/5/6 1-CTA with 128/64/32-column tiles."""
 import os
 import sys
 import time

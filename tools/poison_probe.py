@@ -11,7 +11,7 @@ plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
 Lm, Um = plant.bounds(plant.sample_x0(300))
 for dt in (torch.float32, torch.float64):
     m = reluqpth.ReLU_QP(); m.setup(plant.H, plant.g, plant.A, Lm[0], Um[0], device="cuda", precision=dt, warm_starting=False)
-    for eng in ((0, 1, 3) if dt == torch.float32 else (0, 1)):
+    for eng in ((0, 1, 6) if dt == torch.float32 else (0, 1)):
         show("mpc 300 %s engine %d" % (str(dt)[6:], eng), m.solve_batch(Lm, Um, engine=eng))
 nx, ne, ni, B, seed = 85, 20, 23, 300, 6
 H, g, A, l, u, _ = utils.rand_qp(nx, ne, ni, seed=seed, compute_sol=False)

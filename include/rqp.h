@@ -12,8 +12,16 @@
  * Ownership: the caller (PyTorch) allocates and owns every buffer, including the workspace.
  * The library keeps no pointer past the call that received it.  A workspace must be zero
  * filled once before its first use and belongs to one in-flight solve at a time.
- * Streams: work is enqueued on the cudaStream_t passed as `void* stream`; no call
- * synchronises the host except rqp_query and rqp_probe_bandwidth.
+ * Streams: work is enqueued on the cudaStream_t passed as `void* stream`.  Which calls block the host:
+ *   never block (pure enqueue, capturable in a CUDA graph): rqp_solve, rqp_solve_structured, rqp_update_bias,
+ *     rqp_copy_h2d;
+ *   block until the stream has drained: rqp_resolve (its last step), rqp_stream_sync, rqp_probe_bandwidth;
+ *   block repeatedly: rqp_solve_batched waits for the stream once per check window (the host picks the next
+ *     window's kernel shape from the active-column count the device wrote to pinned memory), once before the
+ *     first window and once more when rqp_batch.first_window_ms is set -- it cannot be captured in a graph;
+ *   no device work at all: rqp_query, rqp_size_limit, rqp_workspace_size, rqp_structured_workspace_size,
+ *     rqp_batch_workspace_size,
+ *     rqp_kernel_launches, rqp_strerror, rqp_last_cuda_error.
  */
 #ifndef RQP_H_
 #define RQP_H_
@@ -113,8 +121,10 @@ typedef struct rqp_state {
                                    at 1 once it exceeds 0x70000000 */
 } rqp_state;
 
-/* Written to DEVICE memory by the kernel (copy it back after the stream is synchronised).
- * Field meaning = Info in classes.py:67-88. */
+/* Written by the kernel through the pointer the caller passes (rqp_solve: result_dev): either device memory (copy
+ * it back after the stream is synchronised) or pinned, device-mapped HOST memory, which the kernel writes directly
+ * over PCIe and the host reads after the synchronise (what the Python layer does).  Field meaning = Info in
+ * classes.py:67-88. */
 typedef struct rqp_result {
     int32_t iter;
     int32_t status;             /* RQP_STATUS_*                                          */
@@ -157,6 +167,29 @@ int rqp_workspace_size(const rqp_problem* prob, const rqp_settings* stng, size_t
 int rqp_solve(const rqp_problem* prob, const rqp_settings* stng, rqp_state* state,
               rqp_result* result_dev, double* trace_dev, int32_t trace_cap,
               void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Structure-exploiting variant of rqp_solve: the same iteration evaluated from the blocks W_rho is
+ * assembled from (reluqpth.py:71-77) instead of the dense D x D matrix:
+ *   lambda+ = lambda + R (A x - z);  x+ = M_rho [x; R z - lambda+] + b_x;  z+ = clamp(A x+ + R^-1 lambda+, l, u)
+ * with M_rho = [sigma K_rho | K_rho A'] (nx x (nx + nc)), K_rho = (H + sigma I + A' R A)^-1, R = diag(Rv_rho),
+ * b_x = the first nx entries of b_rho = -K_rho g.  nx^2 + 2 nc nx matrix elements per iteration instead of
+ * (nx + 2 nc)^2.  Same state vector, settings, result record and semantics as rqp_solve; prob->W is not read
+ * (may be NULL); prob->b, H, AT, g, l, u, rhos are.  All pointers device memory, row-major, element type dtype.
+ */
+typedef struct rqp_structured {
+    const void* M;              /* [n_rho][nx][ldm]   ldm >= nx + nc, ldm % 4 == 0, padding columns ZERO   */
+    const void* Rv;             /* [n_rho][nc]        rho_vec of reluqpth.py:53-54 / :64-65                */
+    const void* Rinv;           /* [n_rho][nc]        1 / Rv                                               */
+    const void* Apad;           /* [nc][lda]          A with 16-byte aligned rows: lda >= nx, lda % 4 == 0 */
+    int64_t ldm, lda;
+} rqp_structured;
+
+int rqp_structured_workspace_size(const rqp_problem* prob, const rqp_structured* sp, const rqp_settings* stng,
+                                  size_t* bytes);
+int rqp_solve_structured(const rqp_problem* prob, const rqp_structured* sp, const rqp_settings* stng,
+                         rqp_state* state, rqp_result* result_dev, double* trace_dev, int32_t trace_cap,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * ReLU_QP.update's bias refresh (reluqpth.py:166-169): b[k] = Bmat[k] g for every rho in one

@@ -274,3 +274,28 @@ def kkt_residuals(H, g, A, l, u, x, z, lam):
     pri = (Ax - torch.minimum(torch.maximum(Ax, l), u)).abs().max()
     dua = (H @ x + g + A.T @ lam).abs().max()
     return float(pri), float(dua)
+
+
+def structured_iterations(H, g, A, l, u, rho, n_iter, sigma=1e-6, eq_tol=1e-6, v0=None):
+    """The SAME iteration written from the blocks W_rho is assembled from (``reluqpth.py:71-77``),
+    used to check the structure-exploiting kernel's algebra (``csrc/rqp_struct.cu``):
+
+        lambda+ = lambda + R (A x - z);   x+ = K (sigma x - g + A' (R z - lambda+));   z+ = clamp(A x+ + lambda+ / R)
+
+    with R = diag(rho_vec) (equality rows 1e3 rho), K = (H + sigma I + A' R A)^-1.  Returns [x; z; lambda] after
+    n_iter iterations from v0 (default 0) in float64; equals n_iter applications of ``relu_layer`` with W_rho, b_rho
+    up to rounding."""
+    H, g, A, l, u = (_as_tensor(t, torch.float64) for t in (H, g, A, l, u))
+    nx, nc = H.shape[0], A.shape[0]
+    rvec = rho * torch.ones(nc, dtype=torch.float64)
+    rvec[(u - l) <= eq_tol] = rho * 1e3
+    K = torch.inverse(H + sigma * torch.eye(nx, dtype=torch.float64) + A.T @ (rvec[:, None] * A))
+    v = torch.zeros(nx + 2 * nc, dtype=torch.float64) if v0 is None else _as_tensor(v0, torch.float64).clone()
+    x, z, lam = v[:nx].clone(), v[nx:nx + nc].clone(), v[nx + nc:].clone()
+    t = A @ x
+    for _ in range(n_iter):
+        lam = lam + rvec * (t - z)
+        x = K @ (sigma * x - g + A.T @ (rvec * z - lam))
+        t = A @ x
+        z = torch.minimum(torch.maximum(t + lam / rvec, l), u)
+    return torch.cat([x, z, lam])

@@ -125,6 +125,26 @@ int rqp_solve(const rqp_problem* prob, const rqp_settings* stng, rqp_state* stat
                          static_cast<cudaStream_t>(stream));
 }
 
+int rqp_structured_workspace_size(const rqp_problem* prob, const rqp_structured* sp, const rqp_settings* stng,
+                                  size_t* bytes) {
+    if (!bytes) return RQP_ERR_BAD_ARG;
+    rqp_caps caps;
+    int rc = current_caps(&caps);
+    if (rc != RQP_OK) return rc;
+    return struct_workspace_size(prob, sp, stng, caps, bytes);
+}
+
+int rqp_solve_structured(const rqp_problem* prob, const rqp_structured* sp, const rqp_settings* stng, rqp_state* state,
+                         rqp_result* result_dev, double* trace_dev, int32_t trace_cap, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    rqp_caps caps;
+    int rc = current_caps(&caps);
+    if (rc != RQP_OK) return rc;
+    if (caps.cc_major < 10 || !caps.cooperative_launch) return RQP_ERR_UNSUPPORTED;
+    return launch_struct(prob, sp, stng, state, result_dev, trace_dev, trace_cap, workspace, workspace_bytes, caps,
+                         static_cast<cudaStream_t>(stream));
+}
+
 int rqp_update_bias(int32_t dtype, int32_t n_rho, int32_t D, int32_t nx, const void* Bmat, const void* g,
                     void* b_out, void* stream) {
     if (!Bmat || !g || !b_out || n_rho < 1 || D < 1 || nx < 1) return RQP_ERR_BAD_ARG;

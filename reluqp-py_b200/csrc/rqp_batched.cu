@@ -744,6 +744,15 @@ struct PinnedRecord {
     PinnedRecord& operator=(const PinnedRecord&) = delete;
 };
 
+// CUDA event pair that is destroyed on every exit path (the RQP_CUDA_TRY early returns included)
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() {
+        if (a) cudaEventDestroy(a);
+        if (b) cudaEventDestroy(b);
+    }
+};
+
 struct BatchLayout {
     int cap, n_tiles;
     size_t off_V[2], off_Vh[2], off_Vl[2], off_Bias[2], off_orig[2], off_ri[2], off_rhoc[2], off_T, off_key, off_pri, off_dua,
@@ -1126,11 +1135,11 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         // mainloop is serial either way and PDL launches are as fast.
         // optional: device time of the first window's iteration launches (rqp_batch.first_window_ms)
         const bool time_window = bt->first_window_ms != nullptr && k == 0;
-        cudaEvent_t ev_w0 = nullptr, ev_w1 = nullptr;
+        EventPair ev_w;
         if (time_window) {
-            RQP_CUDA_TRY(cudaEventCreate(&ev_w0));
-            RQP_CUDA_TRY(cudaEventCreate(&ev_w1));
-            RQP_CUDA_TRY(cudaEventRecord(ev_w0, st));
+            RQP_CUDA_TRY(cudaEventCreate(&ev_w.a));
+            RQP_CUDA_TRY(cudaEventCreate(&ev_w.b));
+            RQP_CUDA_TRY(cudaEventRecord(ev_w.a, st));
         }
         const int n_rt128 = (D + 127) / 128;
         const int tiles_w = use_tc ? nact_host[3 - pick_bn(n_rt128, bt->engine)] * n_rt128 : 0;
@@ -1155,13 +1164,11 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         }
         k += steps;
         if (time_window) {
-            RQP_CUDA_TRY(cudaEventRecord(ev_w1, st));
-            RQP_CUDA_TRY(cudaEventSynchronize(ev_w1));
+            RQP_CUDA_TRY(cudaEventRecord(ev_w.b, st));
+            RQP_CUDA_TRY(cudaEventSynchronize(ev_w.b));
             float ms = 0.f;
-            RQP_CUDA_TRY(cudaEventElapsedTime(&ms, ev_w0, ev_w1));
+            RQP_CUDA_TRY(cudaEventElapsedTime(&ms, ev_w.a, ev_w.b));
             *bt->first_window_ms = ms;
-            cudaEventDestroy(ev_w0);
-            cudaEventDestroy(ev_w1);
         }
         const double tw1 = trace_windows ? now_us() : 0.0;
         if (trace_windows) {

@@ -19,6 +19,12 @@ int plan_single(const rqp_problem* prob, const rqp_settings* stng, const rqp_cap
 int launch_single(const rqp_problem* prob, const rqp_settings* stng, rqp_state* state, rqp_result* result_dev,
                   double* trace_dev, int32_t trace_cap, void* ws, size_t ws_bytes, const rqp_caps& caps,
                   cudaStream_t stream);
+// rqp_struct.cu
+int struct_workspace_size(const rqp_problem* prob, const rqp_structured* sp, const rqp_settings* stng,
+                          const rqp_caps& caps, size_t* bytes);
+int launch_struct(const rqp_problem* prob, const rqp_structured* sp, const rqp_settings* stng, rqp_state* state,
+                  rqp_result* result_dev, double* trace_dev, int32_t trace_cap, void* ws, size_t ws_bytes,
+                  const rqp_caps& caps, cudaStream_t stream);
 // rqp_batched.cu
 int batch_workspace_size(const rqp_problem* prob, const rqp_settings* stng, int32_t B, const rqp_caps& caps,
                          size_t* bytes);

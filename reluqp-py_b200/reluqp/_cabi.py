@@ -17,7 +17,8 @@ RQP_ERR_WATCHDOG = -6
 RQP_TRACE_STRIDE = 5
 EPOCH_LIMIT = 0x70000000
 
-EXPORTS = ("rqp_query", "rqp_size_limit", "rqp_workspace_size", "rqp_solve", "rqp_update_bias", "rqp_resolve",
+EXPORTS = ("rqp_query", "rqp_size_limit", "rqp_workspace_size", "rqp_solve", "rqp_structured_workspace_size",
+           "rqp_solve_structured", "rqp_update_bias", "rqp_resolve",
            "rqp_batch_workspace_size", "rqp_solve_batched", "rqp_copy_h2d", "rqp_stream_sync",
            "rqp_probe_bandwidth", "rqp_kernel_launches",
            "rqp_strerror", "rqp_last_cuda_error")
@@ -36,6 +37,11 @@ class rqp_problem(C.Structure):
                 ("W", C.c_void_p), ("b", C.c_void_p), ("H", C.c_void_p), ("A", C.c_void_p),
                 ("AT", C.c_void_p), ("g", C.c_void_p), ("l", C.c_void_p), ("u", C.c_void_p),
                 ("rhos", C.c_void_p)]
+
+
+class rqp_structured(C.Structure):
+    _fields_ = [("M", C.c_void_p), ("Rv", C.c_void_p), ("Rinv", C.c_void_p), ("Apad", C.c_void_p),
+                ("ldm", C.c_int64), ("lda", C.c_int64)]
 
 
 class rqp_settings(C.Structure):
@@ -91,6 +97,10 @@ def load():
     lib.rqp_workspace_size.argtypes = [C.POINTER(rqp_problem), C.POINTER(rqp_settings), C.POINTER(sz)]
     lib.rqp_solve.argtypes = [C.POINTER(rqp_problem), C.POINTER(rqp_settings), C.POINTER(rqp_state),
                               vp, vp, i32, vp, sz, vp]
+    lib.rqp_structured_workspace_size.argtypes = [C.POINTER(rqp_problem), C.POINTER(rqp_structured),
+                                                  C.POINTER(rqp_settings), C.POINTER(sz)]
+    lib.rqp_solve_structured.argtypes = [C.POINTER(rqp_problem), C.POINTER(rqp_structured), C.POINTER(rqp_settings),
+                                         C.POINTER(rqp_state), vp, vp, i32, vp, sz, vp]
     lib.rqp_update_bias.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp]
     lib.rqp_resolve.argtypes = [C.POINTER(rqp_problem), C.POINTER(rqp_settings), C.POINTER(rqp_state),
                                 vp, vp, i32, vp, sz, vp, vp, sz, i32, vp, vp, sz, vp]

@@ -64,7 +64,8 @@ class Settings(object):
                  device=None,
                  precision=torch.float64,
                  eps_rel=0.0,
-                 setup_precision=None):
+                 setup_precision=None,
+                 structured=False):
         self.verbose = verbose
         self.warm_starting = warm_starting
         self.scaling = scaling                              # accepted, no effect (as in the reference)
@@ -84,6 +85,8 @@ class Settings(object):
         self.precision = precision
         # dtype the layer matrices are formed in before being rounded to `precision`
         self.setup_precision = torch.float64 if setup_precision is None else setup_precision
+        # True: iterate on the blocks W_rho is made of (M_rho = [sigma K | K A'], A, R) instead of the dense matrix
+        self.structured = bool(structured)
 
 
 class Info(object):

@@ -46,6 +46,7 @@ class _Timer(object):
 
     def __init__(self, device):
         self.cuda = device.type == "cuda"
+        self.device = device
         if self.cuda:
             self.start = torch.cuda.Event(enable_timing=True)
             self.end = torch.cuda.Event(enable_timing=True)
@@ -54,13 +55,15 @@ class _Timer(object):
     def tic(self):
         self.t0 = time.perf_counter()
         if self.cuda:
-            self.start.record()
+            with torch.cuda.device(self.device):      # events belong to the solver's device, whatever is current
+                self.start.record()
 
     def toc(self, sync=True):
         """Seconds since tic().  sync=False (update): do not block the host; the time is the host
         time spent enqueueing, the device part is absorbed by the following solve's run_time."""
         if self.cuda and sync:
-            self.end.record()
+            with torch.cuda.device(self.device):
+                self.end.record()
             self.end.synchronize()
             return self.start.elapsed_time(self.end) / 1000.0
         return time.perf_counter() - self.t0
@@ -85,7 +88,8 @@ class ReLU_Layer(object):
         self.W_all, self.B_all, self.b_all = self.setup_matrices()
         D = QP.nx + 2 * QP.nc
         n = len(self.rho_list)
-        self.W_ks = {i: self.W_all[i, :, :D] for i in range(n)}
+        # structured mode (setup(structured=True)): the dense W_rho are never assembled; M_ks / R_ks instead
+        self.W_ks = {i: self.W_all[i, :, :D] for i in range(n)} if self.W_all is not None else None
         self.B_ks = {i: self.B_all[i] for i in range(n)}
         self.b_ks = {i: self.b_all[i] for i in range(n)}
         self.clamp_inds = (QP.nx, QP.nx + QP.nc)
@@ -130,7 +134,15 @@ class ReLU_Layer(object):
         D = nx + 2 * nc
         ldw = _round_up(D, 4)
         n = len(self.rho_list)
-        W_all = torch.zeros((n, D, ldw), device=dev, dtype=st.precision)
+        structured = bool(getattr(st, "structured", False))
+        W_all = None if structured else torch.zeros((n, D, ldw), device=dev, dtype=st.precision)
+        if structured:
+            # the blocks the structure-exploiting kernel iterates on (rqp_structured in include/rqp.h):
+            # M_rho = [sigma K | K A'] with 16-byte aligned, zero-padded rows; rho_vec and its reciprocal; padded A
+            ldm, lda = _round_up(nx + nc, 4), _round_up(nx, 4)
+            self.M_all = torch.zeros((n, nx, ldm), device=dev, dtype=st.precision)
+            self.A_pad = torch.zeros((nc, lda), device=dev, dtype=st.precision)
+            self.A_pad[:, :nx] = A
         B_all = torch.zeros((n, D, nx), device=dev, dtype=st.precision)
         b_all = torch.zeros((n, D), device=dev, dtype=st.precision)
         eq = (u - l) <= st.eq_tol
@@ -154,16 +166,20 @@ class ReLU_Layer(object):
             KAt = K @ At                                  #              [m, nx, nc]
             AK = A @ K                                    #              [m, nc, nx]
             AKAt = AK @ At                                #              [m, nc, nc]
-            W = W_all[c0:c0 + m]
-            W[:, :nx, :nx] = K @ S
-            W[:, :nx, nx:nx + nc] = (2 * KAt) * rvec[:, None, :]
-            W[:, :nx, nx + nc:D] = -KAt
-            W[:, nx:nx + nc, :nx] = AK @ S + A
-            W[:, nx:nx + nc, nx:nx + nc] = (2 * AKAt) * rvec[:, None, :] - Ic
-            W[:, nx:nx + nc, nx + nc:D] = -AKAt + torch.diag_embed(1.0 / rvec)
-            W[:, nx + nc:, :nx] = RA
-            W[:, nx + nc:, nx:nx + nc] = -torch.diag_embed(rvec)
-            W[:, nx + nc:, nx + nc:D] = Ic
+            if structured:
+                self.M_all[c0:c0 + m, :, :nx] = st.sigma * K
+                self.M_all[c0:c0 + m, :, nx:nx + nc] = KAt
+            else:
+                W = W_all[c0:c0 + m]
+                W[:, :nx, :nx] = K @ S
+                W[:, :nx, nx:nx + nc] = (2 * KAt) * rvec[:, None, :]
+                W[:, :nx, nx + nc:D] = -KAt
+                W[:, nx:nx + nc, :nx] = AK @ S + A
+                W[:, nx:nx + nc, nx:nx + nc] = (2 * AKAt) * rvec[:, None, :] - Ic
+                W[:, nx:nx + nc, nx + nc:D] = -AKAt + torch.diag_embed(1.0 / rvec)
+                W[:, nx + nc:, :nx] = RA
+                W[:, nx + nc:, nx:nx + nc] = -torch.diag_embed(rvec)
+                W[:, nx + nc:, nx + nc:D] = Ic
             B_all[c0:c0 + m, :nx] = -K
             B_all[c0:c0 + m, nx:nx + nc] = -AK
             # b_rho = B_rho g (:77) in the SETUP dtype, rounded once: with precision=float32 on fp64-formed
@@ -172,6 +188,11 @@ class ReLU_Layer(object):
             # multiplied by K^-1 and kept rand_qp(nx >= 3200) in fp32 from ever terminating.)
             b_all[c0:c0 + m, :nx] = -(K @ q.g)
             b_all[c0:c0 + m, nx:nx + nc] = -(AK @ q.g)
+        if structured:
+            self.R_all = rvec_all.to(st.precision).contiguous()
+            self.Rinv_all = (1.0 / rvec_all).to(st.precision).contiguous()
+            self.M_ks = {i: self.M_all[i, :, :nx + nc] for i in range(n)}
+            self.R_ks = {i: self.R_all[i] for i in range(n)}
         return W_all, B_all, b_all
 
     def forward(self, input, idx):
@@ -201,10 +222,12 @@ class _Engine(object):
         self.AT = qp.A.T.contiguous()
         D = qp.nx + 2 * qp.nc
         self.D = D
+        self.structured = layers.W_all is None
         self.prob = _cabi.rqp_problem(
             dtype=_cabi.dtype_code(self.dtype), nx=qp.nx, nc=qp.nc, n_rho=len(layers.rho_list),
-            ldw=layers.W_all.shape[2],
-            W=layers.W_all.data_ptr(), b=layers.b_all.data_ptr(), H=qp.H.data_ptr(), A=qp.A.data_ptr(),
+            ldw=_round_up(D, 4) if self.structured else layers.W_all.shape[2],
+            W=None if self.structured else layers.W_all.data_ptr(), b=layers.b_all.data_ptr(), H=qp.H.data_ptr(),
+            A=qp.A.data_ptr(),
             AT=self.AT.data_ptr(), g=qp.g.data_ptr(), l=qp.l.data_ptr(), u=qp.u.data_ptr(),
             rhos=layers.rhos.data_ptr())
         self.stng = _cabi.rqp_settings()
@@ -212,10 +235,20 @@ class _Engine(object):
                            exchange_flags=0)
         self.tuning.update({k: int(v) for k, v in tuning.items()})
         self._fill_settings()
+        self.sp = None
+        if self.structured:
+            self.sp = _cabi.rqp_structured(M=layers.M_all.data_ptr(), Rv=layers.R_all.data_ptr(),
+                                           Rinv=layers.Rinv_all.data_ptr(), Apad=layers.A_pad.data_ptr(),
+                                           ldm=layers.M_all.shape[2], lda=layers.A_pad.shape[1])
         with torch.cuda.device(self.device):
             sz = C.c_size_t(0)
-            _cabi.check(self.lib.rqp_workspace_size(C.byref(self.prob), C.byref(self.stng), C.byref(sz)),
-                        "rqp_workspace_size")
+            if self.structured:
+                _cabi.check(self.lib.rqp_structured_workspace_size(C.byref(self.prob), C.byref(self.sp),
+                                                                   C.byref(self.stng), C.byref(sz)),
+                            "rqp_structured_workspace_size")
+            else:
+                _cabi.check(self.lib.rqp_workspace_size(C.byref(self.prob), C.byref(self.stng), C.byref(sz)),
+                            "rqp_workspace_size")
         self.ws = torch.zeros(sz.value, dtype=torch.uint8, device=self.device)
         self.epoch = 1
         # result record: pinned host memory the kernel writes directly (zero-copy over PCIe),
@@ -260,10 +293,15 @@ class _Engine(object):
         self.state.epoch = self.epoch
         res_ptr = self.res_host.data_ptr() if self.mapped else self.res_dev.data_ptr()
         stream = _cabi.raw_stream(self.device.index)
-        rc = self.lib.rqp_solve(C.byref(self.prob), C.byref(self.stng), C.byref(self.state), res_ptr,
-                                self.trace.data_ptr() if self.trace is not None else None,
-                                self.trace_cap, self.ws.data_ptr(), self.ws.numel(), stream)
-        _cabi.check(rc, "rqp_solve")
+        trace_ptr = self.trace.data_ptr() if self.trace is not None else None
+        if self.structured:
+            rc = self.lib.rqp_solve_structured(C.byref(self.prob), C.byref(self.sp), C.byref(self.stng),
+                                               C.byref(self.state), res_ptr, trace_ptr, self.trace_cap,
+                                               self.ws.data_ptr(), self.ws.numel(), stream)
+        else:
+            rc = self.lib.rqp_solve(C.byref(self.prob), C.byref(self.stng), C.byref(self.state), res_ptr,
+                                    trace_ptr, self.trace_cap, self.ws.data_ptr(), self.ws.numel(), stream)
+        _cabi.check(rc, "rqp_solve_structured" if self.structured else "rqp_solve")
         self.epoch = int(self.state.epoch)
         if not self.mapped:
             self.res_host.copy_(self.res_dev, non_blocking=True)
@@ -317,6 +355,7 @@ class ReLU_QP(object):
               precision=torch.float64,
               eps_rel=0.0,
               setup_precision=None,
+              structured=False,
               **launch_tuning):
         """
         Setup ReLU-QP solver problem of the form
@@ -326,8 +365,14 @@ class ReLU_QP(object):
 
         solver settings can be specified as additional keyword arguments (same names and
         defaults as the reference, ``reluqpth.py:102-117``).  Extra, all optional: ``eps_rel``,
-        ``setup_precision`` and kernel launch tuning (``grid``, ``block``, ``w_residency``,
+        ``setup_precision``, ``structured`` and kernel launch tuning (``grid``, ``block``, ``w_residency``,
         ``watchdog_ms``; see include/rqp.h).
+
+        ``structured=True`` iterates on the blocks W_rho is assembled from (``reluqpth.py:71-77``):
+        ``lam+ = lam + R(Ax - z); x+ = K(sigma x - g + A'(Rz - lam+)); z+ = clamp(Ax+ + lam+/R)`` -- the same
+        map, nx^2 + 2 nc nx instead of (nx + 2 nc)^2 matrix elements per iteration (C ABI
+        ``rqp_solve_structured``).  Pays when W_rho streams from L2 / HBM (D >~ 2000); ``layers.W_ks`` is not
+        formed (``layers.M_ks``, ``layers.R_ks`` instead); ``solve_batch`` and ``resolve`` need the dense mode.
         """
         bad = set(launch_tuning) - {"grid", "block", "w_residency", "watchdog_ms", "poll_backoff_ns", "prepoll_cycles",
                                     "exchange_flags"}
@@ -344,7 +389,8 @@ class ReLU_QP(object):
                                  adaptive_rho_interval=adaptive_rho_interval,
                                  adaptive_rho_tolerance=adaptive_rho_tolerance, max_iter=max_iter,
                                  eps_abs=eps_abs, check_interval=check_interval, device=device,
-                                 precision=precision, eps_rel=eps_rel, setup_precision=setup_precision)
+                                 precision=precision, eps_rel=eps_rel, setup_precision=setup_precision,
+                                 structured=structured)
         st = self.settings
         sdt = st.setup_precision
         if precision == torch.float64:
@@ -405,7 +451,7 @@ class ReLU_QP(object):
             self._glu[lo:hi].copy_(value.to(self.settings.precision), non_blocking=True)
             return None
         if self._glu_pending:                     # an earlier async copy may still read the staging buffer
-            if self._engine is not None:
+            if self._engine is not None and torch.cuda.current_device() == self.settings.device.index:
                 _cabi.check(self._engine.lib.rqp_stream_sync(_cabi.raw_stream(self.settings.device.index)),
                             "rqp_stream_sync")
             elif self._glu_event is not None:
@@ -424,10 +470,12 @@ class ReLU_QP(object):
             es = self._glu_es
             _cabi.check(eng.lib.rqp_copy_h2d(self._glu_ptr + lo * es, self._glu_host_ptr + lo * es, (hi - lo) * es,
                                              _cabi.raw_stream(self.settings.device.index)), "rqp_copy_h2d")
-        else:
-            self._glu[lo:hi].copy_(self._glu_host[lo:hi], non_blocking=True)
-            if self._glu_event is not None:
+        elif self._glu_event is not None:
+            with torch.cuda.device(self.settings.device):     # copy and event on the SOLVER's device and stream
+                self._glu[lo:hi].copy_(self._glu_host[lo:hi], non_blocking=True)
                 self._glu_event.record()
+        else:
+            self._glu[lo:hi].copy_(self._glu_host[lo:hi])
         self._glu_pending = self._glu_event is not None
 
     def update(self, g=None, l=None, u=None, Hx=None, Ax=None):
@@ -523,6 +571,11 @@ class ReLU_QP(object):
         eng = self._engine
         if eng is None:
             raise RuntimeError("ReLU_QP.resolve needs a CUDA device; there is no CPU fallback")
+        if eng.structured:                       # rqp_resolve drives the dense kernel: same result through the calls
+            self.update(g=g, l=l, u=u)
+            res = self.solve()
+            res.x_host = res.x.cpu().numpy()
+            return res
         st = self.settings
         nx, nc = self.QP.nx, self.QP.nc
         if any(torch.is_tensor(v) and v.device.type != "cpu" for v in (g, l, u)):
@@ -549,6 +602,7 @@ class ReLU_QP(object):
         eng.state.epoch = eng.epoch
         if not eng.mapped:
             raise RuntimeError("resolve() needs the mapped result record (RQP_RESULT_MAPPED=1)")
+        self._glu_pending = hi > lo     # if the call fails after enqueueing the copy, the next _stage() must wait
         with torch.cuda.device(st.device):
             rc = eng.lib.rqp_resolve(C.byref(eng.prob), C.byref(eng.stng), C.byref(eng.state),
                                      eng.res_host.data_ptr(), None, 0, eng.ws.data_ptr(), eng.ws.numel(),
@@ -630,6 +684,8 @@ class ReLU_QP(object):
         from ._batch import BatchEngine
         if self._engine is None:
             raise RuntimeError("ReLU_QP.solve_batch needs a CUDA device; there is no CPU fallback")
+        if self._engine.structured:
+            raise RuntimeError("solve_batch needs the dense layer matrices: set the solver up without structured=True")
         if self._batch is None:
             self._batch = BatchEngine(self)
         return self._batch

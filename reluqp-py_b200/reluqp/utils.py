@@ -3,8 +3,8 @@
 ``rand_qp`` / ``update_qp`` restate the reference generators
 (``ReLU-QP-py/reluqp/utils.py:11-39`` and ``:42-70``).  They use the legacy global numpy
 stream and draw in the reference's order, so for a given seed H, g, A, l, u are
-bit-identical to the reference's (tests/test_generators.py checks the sha256 recorded
-in SURVEY.md and the committed golden problems).  The reference imports cvxpy at module
+bit-identical to the reference's (tests/test_host.py::test_rand_qp_bit_exact checks the sha256
+recorded in SURVEY.md; tests/test_oracle.py checks the sha256 of every committed golden problem).  The reference imports cvxpy at module
 import time; here it is only touched when ``compute_sol=True`` and present.
 """
 import warnings

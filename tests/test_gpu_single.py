@@ -521,3 +521,110 @@ def test_size_ceiling():
     A2 = np.zeros((4100, 8200))                      # D = 16400 > 16384
     with pytest.raises(ValueError, match="too large for the single-QP kernels"):
         gpu_model((H2, np.zeros(8200), A2, -np.ones(4100), np.ones(4100)), adaptive_rho=False)
+
+
+def test_reference_example_runs_unchanged(capsys):
+    """the reference's example (ReLU-QP-py/examples/reluqpth-simple.py:1-16) must run unchanged against
+    this package: its body is executed as a script (examples/reluqpth-simple.py here is the same calls) and the
+    printed status must be 'solved' with x equal to the oracle's."""
+    import os
+    import runpy
+    from conftest import PKG
+    runpy.run_path(os.path.join(PKG, "examples", "reluqpth-simple.py"), run_name="__main__")
+    out = capsys.readouterr().out.strip().splitlines()
+    assert out[0] == "solved"
+    prob = utils.rand_qp(nx=10, n_eq=5, n_ineq=5)[:5]
+    ref = O.OracleSolver(*prob).solve()
+    xs = np.array([float(t) for t in " ".join(out[1:]).replace("tensor([", "").split("]")[0].replace("\n", " ").split(",")])
+    assert rel_err(xs, ref.x.numpy()) < 1e-3          # printed with 4 decimals
+
+
+def test_packaging_metadata():
+    """setup.py mirrors the reference's (name 'reluqp', find_packages): the package directory is importable as is."""
+    import os
+    from conftest import PKG
+    src = open(os.path.join(PKG, "setup.py")).read()
+    assert "name=\"reluqp\"" in src and "find_packages" in src
+    assert os.path.exists(os.path.join(PKG, "reluqp", "__init__.py"))
+
+
+# ------------------------------------------------------------------------------------------------
+# structure-exploiting iteration (setup(structured=True) -> rqp_solve_structured, SURVEY 8f-4)
+# ------------------------------------------------------------------------------------------------
+def test_structured_small_goldens(golden):
+    """Same goldens as the dense kernel: known-answer QP (cold, warm, corner-case settings), C1 at three
+    tolerances, update + warm re-solve.  fp64: identical iteration count / status / rho index, x and z within 1e-6."""
+    prob = known_answer_problem()
+    m = gpu_model(prob, structured=True)
+    assert m.layers.W_ks is None and m.layers.M_ks[7].shape == (3, 8)
+    res = m.solve()
+    assert torch.allclose(res.x.cpu(), torch.tensor([2.0, -1, 1], dtype=torch.float64))   # reluqpth.py:360
+    check(m, res, golden.case("small", "ka"))
+    assert m.rho_ind == 6
+    check(m, m.solve(), golden.case("small", "ka_warm2"))          # warm start: t = A x_0 is recomputed at entry
+    for name in ("ka_maxiter30", "ka_ci10", "ka_rho1", "ka_cold"):
+        gold = golden.case("small", name)
+        m = gpu_model(prob, structured=True, **gold["settings"])
+        check(m, m.solve(), gold)
+        assert m.rho_ind == (7 if name == "ka_cold" else gold["rho_ind_after"])
+    gold = golden.case("small", "ka_noadapt")
+    m = gpu_model(prob, structured=True, **gold["settings"])
+    check(m, m.solve(), gold, scalars=False)
+    c1 = utils.rand_qp(10, 5, 5, seed=1, compute_sol=False)[:5]
+    for name in ("c1_e3", "c1_e4", "c1_e6"):
+        gold = golden.case("small", name)
+        m = gpu_model(c1, structured=True, **gold["settings"])
+        check(m, m.solve(), gold)
+        assert m.rho_ind == gold["rho_ind_after"]
+    m = gpu_model(c1, structured=True, eps_abs=1e-6)
+    m.solve()
+    _, g2, _, l2, u2, _ = utils.update_qp(c1[0], c1[2], 5, 5, seed=7, compute_sol=False)
+    m.update(g=g2, l=l2, u=u2)
+    check(m, m.solve(), golden.case("small", "c1_update_warm"))
+
+
+def test_structured_sweep_and_mpc(golden):
+    """Every third problem of the 50-problem sweep (random_qps.py:108) and 8 golden MPC columns through the
+    structured kernel: identical iteration counts in fp64."""
+    names = sorted(golden.meta["sweep"].keys())[::3]
+    for name in names:
+        g = golden.case("sweep", name)
+        prob = utils.rand_qp(g["nx"], g["n_eq"], g["n_ineq"], seed=g["seed"], compute_sol=False)[:5]
+        m = gpu_model(prob, structured=True, **g["settings"])
+        check(m, m.solve(), g, scalars=False)
+    plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+    X0 = golden.arrays("mpc")["X0"]
+    L, U = plant.bounds(X0)
+    m = gpu_model((plant.H, plant.g, plant.A, L[0], U[0]), structured=True, warm_starting=False)
+    for j in range(0, 32, 4):
+        m.update(l=L[j], u=U[j])
+        check(m, m.solve(), golden.case("mpc", "mpc_col{}".format(j)), scalars=False)
+
+
+@pytest.mark.parametrize("nx,seed", [(1000, 1), (2000, 2), (3200, 0), (4000, 0)])
+def test_structured_large_both_dtypes(golden, capsys, nx, seed):
+    """The sizes the structured path is for (W_rho streams from L2 / HBM): fp64 identical iteration counts and x, z
+    within 1e-6 of the reference goldens; fp32 solved, x within 1e-4 of the fp64 golden, iterations reported; and
+    the per-iteration time next to the dense kernel's (reported)."""
+    prob = utils.rand_qp(nx, nx // 4, nx // 4, seed=seed, compute_sol=False)[:5]
+    tag = "nx{}_s{}".format(nx, seed)
+    g64 = golden.case("xl", tag + "_fp64")
+    g32 = golden.case("xl", tag + "_fp32hybrid")
+    rows = []
+    for prec in (torch.float64, torch.float32):
+        for structured in (True, False):
+            m = gpu_model(prob, precision=prec, structured=structured)
+            res = m.solve()
+            x, z = state_of(m, res)
+            if prec == torch.float64:
+                check(m, res, g64, scalars=False)
+            else:
+                assert res.info.status == g32["status"] == "solved"
+                assert rel_err(x, g64["x"]) < TOL32 and rel_err(z, g64["z"]) < TOL32
+                assert res.info.iter <= g32["iter"]
+            rows.append((prec, structured, res.info.iter, m.last_launch["kernel_loop_us"] / res.info.iter))
+            del m
+    with capsys.disabled():
+        print("\n[structured {}] ".format(tag) + "; ".join(
+            "{} {}: {} iters, {:.1f} us/iter".format("f64" if p == torch.float64 else "f32",
+                                                     "structured" if s else "dense", it, us) for p, s, it, us in rows))

@@ -191,3 +191,21 @@ def test_xl_cases(golden, nx, seed):
     r = O.OracleSolver(*prob, precision=torch.float32, setup_precision=torch.float64).solve()
     assert (r.iter, r.status) == (g32["iter"], g32["status"])
     assert rel_err(r.x.double().numpy(), g32["x"]) < 1e-6
+
+
+def test_structured_iteration_is_the_dense_layer():
+    """lambda+ = lambda + R(Ax - z); x+ = K(sigma x - g + A'(Rz - lambda+)); z+ = clamp(Ax+ +
+    lambda+/R) is the SAME map as v <- clamp(W_rho v + b_rho) (reluqpth.py:71-77, :84-89) -- the algebra the
+    structure-exploiting kernel relies on, checked on CPU for several rho, from zero and from a random state."""
+    prob = utils.rand_qp(40, 10, 10, seed=2, compute_sol=False)[:5]
+    s = O.OracleSolver(*prob)
+    nx, nc = s.nx, s.nc
+    rng = np.random.RandomState(0)
+    for ri in (3, 7, 11):
+        for v0 in (None, rng.randn(nx + 2 * nc)):
+            v = torch.zeros(nx + 2 * nc, dtype=torch.float64) if v0 is None else torch.as_tensor(v0).clone()
+            for _ in range(12):
+                O.relu_layer(v, s.W[ri], s.b[ri], s.l, s.u, nx, nx + nc)
+            vs = O.structured_iterations(*prob, rho=s.rho_list[ri], n_iter=12, v0=v0)
+            # rho = 62.5 (R = 6.25e4 on equality rows): the assembled W_rho itself carries ~1e-9 of cancellation error
+            assert rel_err(vs.numpy(), v.numpy()) < (1e-10 if ri <= 7 else 1e-7), ri

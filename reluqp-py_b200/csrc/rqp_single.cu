@@ -225,15 +225,19 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
     const int ring_T = nchunks * cpt_rt;              // tiles per iteration
     uint32_t ring_phase = 0;                          // bit s: parity to wait for on stage s
     int ring_cstage = 0, ring_pnext = 0;
-    auto ring_issue = [&](int t, int stage, int ri) {  // thread 0 only
+    // called by ALL lanes of warp 0: lane 0 arms the barrier, then lanes 0..nr-1 issue one row copy each (one
+    // UBLKCP instruction for the whole tile instead of a serial loop in one thread: the issue time of a tile sat
+    // on the critical path of every ring step, ncu r02: 30 % of the samples at the step's CTA barrier)
+    auto ring_issue = [&](int t, int stage, int ri) {
         const int ch = t / cpt_rt, ic = t - ch * cpt_rt;
         const int nr = min(RM, rows - ch * RM);
         const int e0 = ic * NT * VEC;
         const uint32_t cb = uint32_t(min(NT * VEC, int(ldw) - e0)) * uint32_t(sizeof(T));
         const T* src = Wall + (size_t(ri) * D + r0 + size_t(ch) * RM) * ldw + e0;
         unsigned char* dst = reinterpret_cast<unsigned char*>(Ws) + size_t(stage) * RM * NT * 16;
-        mbar_expect_tx(rbar + stage, uint32_t(nr) * cb);
-        for (int r = 0; r < nr; ++r) bulk_g2s(dst + size_t(r) * NT * 16, src + size_t(r) * ldw, cb, rbar + stage);
+        if (lane == 0) mbar_expect_tx(rbar + stage, uint32_t(nr) * cb);
+        __syncwarp();
+        if (lane < nr) bulk_g2s(dst + size_t(lane) * NT * 16, src + size_t(lane) * ldw, cb, rbar + stage);
     };
     auto ring_wait = [&](int stage) -> bool {
         wd.arm();
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
         return true;
     };
     auto ring_start = [&](int ri) {                    // all stages idle -> fill with tiles 0..S-1
-        if (tid == 0)
+        if (warp == 0)
             for (int s = 0; s < RING_STAGES; ++s) ring_issue(s % ring_T, s, ri);
         ring_cstage = 0;
         ring_pnext = RING_STAGES % ring_T;
@@ -598,12 +602,18 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                             if (!ring_wait(stage)) ok = false;
                             const T* sp = Ws + size_t(stage) * RM * NT * VEC + size_t(tid) * VEC;
                             if (tid + i * NT < nvec) {
+                                // all RM row slots of the stage are read, whatever nr: the 8 loads are independent
+                                // and issue back to back (guarding each row made the compiler serialise load ->
+                                // dot -> load ..., 8 exposed shared-memory latencies per tile: ncu r02).  Slots
+                                // beyond nr hold stale tiles; their sums land in rows nobody finalises.
+                                Vec16<T> wq[RM];
 #pragma unroll
-                                for (int r = 0; r < RM; ++r)
-                                    if (r < nr) acc[r] = Vec16<T>::lds(sp + size_t(r) * NT * VEC).dot(vv[i], acc[r]);
+                                for (int r = 0; r < RM; ++r) wq[r] = Vec16<T>::lds(sp + size_t(r) * NT * VEC);
+#pragma unroll
+                                for (int r = 0; r < RM; ++r) acc[r] = wq[r].dot(vv[i], acc[r]);
                             }
                             __syncthreads();                    // every warp is done with this stage
-                            if (tid == 0) ring_issue(ring_pnext, stage, rho_ind);
+                            if (warp == 0) ring_issue(ring_pnext, stage, rho_ind);
                             ring_pnext = (ring_pnext + 1 == ring_T) ? 0 : ring_pnext + 1;
                             ring_cstage = (stage + 1 == RING_STAGES) ? 0 : stage + 1;
                         }

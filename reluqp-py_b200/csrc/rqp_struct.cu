@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(SNT, 1) rqp_struct_kernel(const StructParams p
     __syncthreads();
     uint32_t ring_phase = 0;
     int ring_cstage = 0, ring_pnext = 0;
-    auto ring_issue = [&](int t, int stage, int ri) {       // thread 0: tile t of the per-iteration sequence
+    // all lanes of warp 0: tile t of the per-iteration sequence; lane 0 arms the barrier, lanes 0..nr-1 copy a row each
+    auto ring_issue = [&](int t, int stage, int ri) {
         const T* base;
         long long ld;
         int row0, nrows_tot, ic, ch, nch;
@@ -152,8 +153,9 @@ __global__ void __launch_bounds__(SNT, 1) rqp_struct_kernel(const StructParams p
         const uint32_t cb = uint32_t(min(SNT * VEC, int(ld) - e0)) * uint32_t(sizeof(T));
         const T* src = base + (size_t(row0) + size_t(ch) * SRM) * ld + e0;
         unsigned char* dst = reinterpret_cast<unsigned char*>(ring) + size_t(stage) * SRM * SNT * 16;
-        mbar_expect_tx(rbar + stage, uint32_t(nr) * cb);
-        for (int r = 0; r < nr; ++r) bulk_g2s(dst + size_t(r) * SNT * 16, src + size_t(r) * ld, cb, rbar + stage);
+        if (lane == 0) mbar_expect_tx(rbar + stage, uint32_t(nr) * cb);
+        __syncwarp();
+        if (lane < nr) bulk_g2s(dst + size_t(lane) * SNT * 16, src + size_t(lane) * ld, cb, rbar + stage);
     };
     auto ring_wait = [&](int stage) -> bool {
         wd.arm();
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(SNT, 1) rqp_struct_kernel(const StructParams p
     };
     auto ring_start = [&](int ri) {
         if (TT == 0) return;
-        if (tid == 0)
+        if (warp == 0)
             for (int s = 0; s < p.stages; ++s) ring_issue(s % TT, s, ri);
         ring_cstage = 0;
         ring_pnext = p.stages % TT;
@@ -195,12 +197,16 @@ __global__ void __launch_bounds__(SNT, 1) rqp_struct_kernel(const StructParams p
 #pragma unroll
                     for (int q = 0; q < VEC; ++q) vp[q] = (e + q < ncols) ? us[e + q] : T(0);
                     const T* sp = ring + size_t(stage) * SRM * SNT * VEC + size_t(tid) * VEC;
+                    // all SRM row slots are read (independent loads, issued back to back); slots beyond nr hold
+                    // stale tiles and feed sums nobody reads
+                    Vec16<T> wq[SRM];
 #pragma unroll
-                    for (int r = 0; r < SRM; ++r)
-                        if (r < nr) acc[r] = Vec16<T>::lds(sp + size_t(r) * SNT * VEC).dot(vp, acc[r]);
+                    for (int r = 0; r < SRM; ++r) wq[r] = Vec16<T>::lds(sp + size_t(r) * SNT * VEC);
+#pragma unroll
+                    for (int r = 0; r < SRM; ++r) acc[r] = wq[r].dot(vp, acc[r]);
                 }
                 __syncthreads();                            // every warp is done with this stage
-                if (tid == 0) ring_issue(ring_pnext, stage, rho_ind);
+                if (warp == 0) ring_issue(ring_pnext, stage, rho_ind);
                 ring_pnext = (ring_pnext + 1 == TT) ? 0 : ring_pnext + 1;
                 ring_cstage = (stage + 1 == p.stages) ? 0 : stage + 1;
             }
@@ -215,23 +221,44 @@ __global__ void __launch_bounds__(SNT, 1) rqp_struct_kernel(const StructParams p
         return s;
     };
     // gather n elements (nv vector columns) with flag `flag` from `cells` into dst (shared memory)
+    // Up to GB columns of a thread are polled together (all loads in flight at once: one L2 round trip per batch
+    // instead of one per column); columns whose flags have not arrived are polled again.
     auto gather = [&](const uint64_t* cells, int n, int nv, uint32_t flag, T* dst) {
+        constexpr int GB = 4;
         wd.arm();
-        for (int c = tid; c < nv && ok; c += SNT) {
-            const int nval = max(0, min(VEC, n - c * VEC));
-            const uint32_t nd = (1u << nval) - 1u;
-            T out[VEC];
-            while (ok) {
-                uint64_t w[4];
-                ld_relaxed_u64x2(cells + size_t(c) * 4, w[0], w[1]);
-                ld_relaxed_u64x2(cells + size_t(c) * 4 + 2, w[2], w[3]);
-                const uint32_t m = C::unpack(w, flag, out);
-                if ((m & nd) == nd) break;
-                if (wd.expired()) ok = false;
-            }
+        for (int c0g = tid; c0g < nv && ok; c0g += GB * SNT) {
+            uint32_t pending = 0;
 #pragma unroll
-            for (int e = 0; e < VEC; ++e)
-                if ((nd >> e) & 1u) dst[c * VEC + e] = out[e];
+            for (int b = 0; b < GB; ++b)
+                if (c0g + b * SNT < nv) pending |= 1u << b;
+            while (pending != 0u && ok) {
+                uint64_t w[GB][4];
+#pragma unroll
+                for (int b = 0; b < GB; ++b) {
+                    if (pending & (1u << b)) {
+                        const uint64_t* cp = cells + size_t(c0g + b * SNT) * 4;
+                        ld_relaxed_u64x2(cp, w[b][0], w[b][1]);
+                        ld_relaxed_u64x2(cp + 2, w[b][2], w[b][3]);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < GB; ++b) {
+                    if (pending & (1u << b)) {
+                        const int c = c0g + b * SNT;
+                        const int nval = max(0, min(VEC, n - c * VEC));
+                        const uint32_t nd = (1u << nval) - 1u;
+                        T out[VEC];
+                        const uint32_t m = C::unpack(w[b], flag, out);
+                        if ((m & nd) == nd) {
+                            pending &= ~(1u << b);
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e)
+                                if ((nd >> e) & 1u) dst[c * VEC + e] = out[e];
+                        }
+                    }
+                }
+                if (pending != 0u && wd.expired()) ok = false;
+            }
         }
     };
 

@@ -62,6 +62,9 @@ typedef struct rqp_caps {
     int32_t cooperative_launch;
     int64_t l2_bytes;
     int64_t global_mem_bytes;
+    int32_t max_clusters8;          /* clusters of 8 CTAs (1 CTA per SM) the device can hold at once        */
+    int32_t cl_min_cell_bytes;      /* tuning: the single-QP kernel switches to its cluster (2-D) mode when a
+                                       CTA would otherwise poll at least this many bytes of exchange cells    */
 } rqp_caps;
 
 /*
@@ -104,7 +107,11 @@ typedef struct rqp_settings {
                                    with register loads, 3 force register resident, 4 force
                                    streamed through the bulk-copy shared-memory ring, 5 force
                                    the single-CTA kernel (auto picks it for D <= 112 when
-                                   grid and block are 0)                                  */
+                                   grid and block are 0), 6 force the cluster (2-D) mode of the
+                                   register-resident kernel (clusters of 8 CTAs, partial sums
+                                   through distributed shared memory; auto picks it for the
+                                   exchange-bound sizes when all clusters fit), 7 force the
+                                   row-per-warp mode of the register-resident kernel        */
     int32_t watchdog_ms;        /* 0 = 4000 ms per in-kernel wait                       */
     int32_t prepoll_cycles;     /* tuning: SM cycles to spin after the CTA barrier before the
                                    first exchange poll (0 = default 600, < 0 = none)      */

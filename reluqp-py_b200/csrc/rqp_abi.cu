@@ -25,6 +25,11 @@ static int query_device(int device, rqp_caps* caps) {
     caps->cooperative_launch = prop.cooperativeLaunch;
     caps->l2_bytes = prop.l2CacheSize;
     caps->global_mem_bytes = int64_t(prop.totalGlobalMem);
+    // clusters of 8 that fit at one CTA per SM: GPCs hold 16-20 SMs on B200, i.e. two clusters each; the launch
+    // itself asks cudaOccupancyMaxActiveClusters for the exact kernel and refuses if the grid does not fit
+    caps->max_clusters8 = prop.multiProcessorCount / 9;
+    const char* e = getenv("RQP_CL_MIN_BYTES");
+    caps->cl_min_cell_bytes = e ? atoi(e) : 0;        // 0 = never automatically (measured slower, see plan_single)
     return RQP_OK;
 }
 

@@ -239,6 +239,18 @@ struct Vec16<float> {
         r.q = *reinterpret_cast<const float4*>(p);
         return r;
     }
+    static __device__ __forceinline__ Vec16 zero() {
+        Vec16 r;
+        r.q = make_float4(0.f, 0.f, 0.f, 0.f);
+        return r;
+    }
+    static __device__ __forceinline__ void sts(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    static __device__ __forceinline__ void lds_to(const float* p, float (&v)[4]) {
+        const float4 q = *reinterpret_cast<const float4*>(p);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    }
 };
 template <>
 struct Vec16<double> {
@@ -257,6 +269,18 @@ struct Vec16<double> {
         Vec16 r;
         r.q = *reinterpret_cast<const double2*>(p);
         return r;
+    }
+    static __device__ __forceinline__ Vec16 zero() {
+        Vec16 r;
+        r.q = make_double2(0.0, 0.0);
+        return r;
+    }
+    static __device__ __forceinline__ void sts(double* p, const double (&v)[2]) {
+        *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+    }
+    static __device__ __forceinline__ void lds_to(const double* p, double (&v)[2]) {
+        const double2 q = *reinterpret_cast<const double2*>(p);
+        v[0] = q.x; v[1] = q.y;
     }
 };
 
@@ -373,5 +397,19 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
         : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// Thread-block clusters: a store into the shared memory of another CTA of the cluster (distributed shared
+// memory) and the cluster-wide barrier that orders it (arrive.release / wait.acquire, all threads of all CTAs).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dsmem_store_f64(const double* local_slot, uint32_t target_rank, double v) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_slot)), "r"(target_rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 }  // namespace rqp

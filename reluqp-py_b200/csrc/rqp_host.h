@@ -9,6 +9,8 @@ namespace rqp {
 
 struct SinglePlan {
     int grid, block, cpt, rpc, rows_smem, rmode, ring;
+    int cpl;         // row-per-warp mode: 16-byte pieces of its row a lane keeps (template value; 0 = off)
+    int cl, cl_cps;  // cluster (2-D) mode: cluster size (0 = off) and vector columns of v per CTA of a cluster
     int check_tpw;   // > 0: the residual-check matrix rows of each warp stay in shared memory (tasks per warp)
     size_t smem_bytes;
     size_t vcells_bytes, pcells_bytes, ws_bytes;

@@ -80,6 +80,7 @@ struct SingleParams {
     int check_tpw;        // > 0: rows of A / H / A' each warp needs in a check are kept in shared memory
     int replicas;         // copies of the exchange cells; CTA c reads copy c % replicas (spreads the hot
                           // lines every CTA polls over more L2 slices), publishers write all copies
+    int cl_cps;           // cluster (2-D) mode: vector columns of v per CTA of a cluster (0 = not that mode)
 };
 
 // Partial sums are DOUBLE for both element types: with fp32 data every 16-byte piece contributes a 4-term fp32
@@ -110,8 +111,32 @@ __device__ __forceinline__ void chunk_dot(const T* __restrict__ wrow0, long long
 // RMODE: the CTA's slab has at most RM rows and is held in REGISTERS (thread t keeps the
 // 16-byte pieces of its own columns for all rows), loaded once per rho straight from global
 // memory; shared memory then only carries the reductions.
-template <typename T, int CPT, int NT, bool RMODE>
+//
+// CL > 0 (with RMODE): 2-D decomposition over thread-block CLUSTERS of CL = 8 CTAs (= the 8 warps of a CTA).
+// A cluster owns 8 * CL consecutive rows of W_rho; CTA `rank` of the cluster holds, for ALL of those rows, only
+// the columns of its own 1/CL slice of v (warp w keeps rows 8 w .. 8 w + 7 of the cluster, lane l the vector
+// columns l, l + 32, .. of the slice: the same register footprint as 8 full rows).  Per iteration a CTA then
+// polls 1/CL of the exchange cells (C2: 1.9 KB instead of 15.4 KB) instead of all of v, multiplies, and hands its
+// 8 * CL partial row sums to their owners through distributed shared memory (st.shared::cluster: warp w's rows
+// belong to CTA w of the cluster); after one cluster barrier the owner adds the CL partial sums of each of its 8
+// rows in rank order (bit-reproducible), applies bias and clamp and publishes.  Rows, bias, bounds, checks and the
+// rho logic are exactly the 1-D kernel's (CTA b still finalises rows 8 b .. 8 b + 7).  A CTA that runs into its
+// watchdog keeps walking through the iterations without waiting (it must keep arriving at cluster barriers);
+// everybody reads the abort flag at the end.
+//
+// CPL > 0 (with RMODE, CL == 0): ROW-PER-WARP mode, the default for the exchange-bound sizes.  The CTA still owns 8
+// rows and still polls every exchange cell once (thread t its columns t, t + NT, ..), but the gathered v goes
+// through shared memory and warp w multiplies ROW w alone: lane l keeps the CPL 16-byte pieces l, l + 32, .. of
+// that row in registers, so a row's dot product ends inside one warp (4 interleaved partial sums, one 5-step
+// shuffle tree) and lane 0 finalises and publishes it at once.  Against the column-owner scheme (every thread a
+// slice of all 8 rows: 9-shuffle transposing tree, partial sums of 8 warps through shared memory, a second CTA
+// barrier, a sequential 8-term sum per row) the part of an iteration between "v has arrived" and "row published"
+// shrinks from ~1100 to ~450 cycles at C2.  One CTA barrier per iteration (between the store of v into shared
+// memory and the products); v is double buffered there so that barrier is the only one.
+template <typename T, int CPT, int NT, bool RMODE, int CL = 0, int CPL = 0>
 __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p) {
+    static_assert(CL == 0 || (RMODE && CL == NT / 32), "cluster mode: register-resident, one CTA of the cluster per warp");
+    static_assert(CPL == 0 || (RMODE && CL == 0 && NT == 256), "row-per-warp mode: register-resident, 8 warps = 8 rows");
     using C = Cell<T>;
     constexpr int VEC = C::kVec;
     constexpr int NW = NT / 32;
@@ -134,17 +159,22 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* Ws = reinterpret_cast<T*>(smem_raw);                    // [rows_smem][ldw], or the streaming ring
     const size_t ws_elems = p.ring ? size_t(RING_STAGES) * RM * NT * VEC : size_t(p.rows_smem) * ldw;
-    T* vs = Ws + ws_elems;                                     // [ldw]   (check phase only)
+    T* vs = Ws + ws_elems;                                     // [ldw] (check phase only); row-per-warp mode: [2][ldw]
     // cross-warp partial sums, double for both element types: [2][NW][rpc_pad]
-    double* red = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(vs + ldw) + 15) & ~uintptr_t(15));
+    double* red = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(vs + (CPL > 0 ? 2 : 1) * ldw) + 15) & ~uintptr_t(15));
+    const T* vs_chk = vs;                                      // the iterate a residual pass reads (staged by the caller)
     double* part = red + 2 * NW * rpc_pad;                     // [NW][8]
     double* tot = part + NW * 8;                               // [NW][8]
     Decision* dec = reinterpret_cast<Decision*>(tot + NW * 8);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(dec + 1);
     uint64_t* rbar = mbar + 1;                                 // [RING_STAGES] ring "full" barriers
     uint64_t* cbar = rbar + RING_STAGES;                       // check rows landed
+    // cluster mode: partial row sums handed over by the CTAs of the cluster, [2][CL][RM] (same offset in every CTA)
+    double* clpart = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(cbar + 1) + 15) & ~uintptr_t(15));
     // check rows: [NW][check_tpw][nx + nc] after the barriers (16-byte aligned)
-    T* crow = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(cbar + 1) + 15) & ~uintptr_t(15));
+    T* crow = reinterpret_cast<T*>(clpart + (CL > 0 ? 2 * CL * RM : 0));
+    const int cl_rank = CL > 0 ? int(blockIdx.x % (CL > 0 ? CL : 1)) : 0;
+    const int cl_row0 = CL > 0 ? int(blockIdx.x / (CL > 0 ? CL : 1)) * (CL * RM) : 0;   // first row of the cluster
 
     Watchdog wd{p.watchdog_ns, p.abort_flag, 0, 0};
     const uint32_t epoch = p.epoch;
@@ -157,15 +187,18 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
     uint32_t need[CPT];   // which elements of the column are real state (not ldw padding)
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
-        const int c = tid + i * NT;
-        const int nval = (c < nvec) ? max(0, min(VEC, D - c * VEC)) : 0;
+        // 1-D: vector columns tid, tid + NT, ..; cluster mode: columns lane, lane + 32, .. of this CTA's slice
+        const bool in_slice = CL == 0 || (lane + i * 32 < p.cl_cps);
+        const int c = CL > 0 ? cl_rank * p.cl_cps + lane + i * 32 : tid + i * NT;
+        const int nval = (in_slice && c < nvec) ? max(0, min(VEC, D - c * VEC)) : 0;
         need[i] = (1u << nval) - 1u;
         coff[i] = min(c, nvec - 1) * VEC;
     }
 
     // ---- finalize-thread registers: thread t < rows owns state element r0 + t
-    const bool is_fin = tid < rows;
-    const int my_row = r0 + tid;
+    // finalize thread of a row: thread t for row r0 + t; row-per-warp mode: lane 0 of warp w for row r0 + w
+    const bool is_fin = CPL > 0 ? (lane == 0 && warp < rows) : (tid < rows);
+    const int my_row = r0 + (CPL > 0 ? warp : tid);
     int rho_ind = p.rho_ind0;
     T rho = rhos[rho_ind];
     T my_b = T(0), my_lo = -CUDART_INF, my_hi = CUDART_INF, my_v = T(0);
@@ -258,7 +291,8 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
         for (int s = 0; s < RING_STAGES; ++s) good = ring_wait(s) && good;
         return good;
     };
-    Vec16<T> wreg[RMODE ? RM : 1][RMODE ? CPT : 1];
+    Vec16<T> wreg[(RMODE && CPL == 0) ? RM : 1][(RMODE && CPL == 0) ? CPT : 1];
+    Vec16<T> wrow[CPL > 0 ? CPL : 1];      // row-per-warp mode: pieces lane, lane + 32, .. of row r0 + warp
     // Per-phase cycle counters of thread 0 / CTA 0 (result.phase_cycles).  Kept only in the register-resident
     // kernels, where they are free; the shared-memory / streaming kernels sit at 255 registers and the 16
     // counter registers cost them ~10 % per iteration (C3: 9.7 -> 8.8 us), so there the counters read 0.
@@ -272,15 +306,30 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
             if (kTimers) ph[6] += clock64() - ts;
             return true;
         }
+        if (CPL > 0) {
+            // row r0 + warp (clamped: warps beyond the slab repeat the last row, never published); pieces beyond
+            // the row's nvec vector columns are zero
+            const T* Wr = Wall + (size_t(ri) * D + size_t(min(r0 + warp, D - 1))) * ldw;
+#pragma unroll
+            for (int j = 0; j < (CPL > 0 ? CPL : 1); ++j) {
+                const int c = lane + 32 * j;
+                wrow[j] = Vec16<T>::ldg(Wr + size_t(min(c, nvec - 1)) * VEC);
+                if (c >= nvec) wrow[j] = Vec16<T>::zero();
+            }
+            if (kTimers) ph[6] += clock64() - ts;
+            return true;
+        }
         if (RMODE) {
-            const T* Wg = Wall + (size_t(ri) * D + r0) * ldw;
+            const T* Wg = Wall + (size_t(ri) * D + (CL > 0 ? 0 : r0)) * ldw;
 #pragma unroll
             for (int r = 0; r < RM; ++r) {
 #pragma unroll
                 for (int i = 0; i < CPT; ++i) {
-                    // rows beyond the slab repeat the last row (never written out)
-                    wreg[RMODE ? r : 0][RMODE ? i : 0] =
-                        Vec16<T>::ldg(Wg + (long long)min(r, rows - 1) * ldw + coff[i]);
+                    // rows beyond the slab repeat the last row (never written out); cluster mode: warp w keeps
+                    // rows 8 w .. 8 w + 7 of the CLUSTER (clamped to the last row of W)
+                    const long long row = CL > 0 ? (long long)min(cl_row0 + warp * RM + r, D - 1)
+                                                 : (long long)min(r, rows - 1);
+                    wreg[(RMODE && CPL == 0) ? r : 0][(RMODE && CPL == 0) ? i : 0] = Vec16<T>::ldg(Wg + row * ldw + coff[i]);
                 }
             }
             if (kTimers) ph[6] += clock64() - ts;
@@ -356,9 +405,10 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
         const T* __restrict__ Am = static_cast<const T*>(p.A);
         const T* __restrict__ ATm = static_cast<const T*>(p.AT);
         const T* __restrict__ gv = static_cast<const T*>(p.g);
-        const T* xs = vs;
-        const T* zs = vs + nx;
-        const T* ls = vs + nx + nc;
+        if (!staged) vs_chk = vs;
+        const T* xs = vs_chk;
+        const T* zs = xs + nx;
+        const T* ls = xs + nx + nc;
         double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0, m4 = 0.0, m5 = 0.0, m6 = 0.0, osum = 0.0;
         const int GW = G * NW;
         if (crow_pending) {     // first check: the rows were requested at kernel start
@@ -512,10 +562,51 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
     // flags have not arrived yet are polled again.
     T vv[CPT][VEC];
     bool have_vv = false;
+    bool vs_ready = false;      // row-per-warp mode: v_{k-1} already sits in its shared-memory buffer (after a check)
+    double row_sum = 0.0;
     auto gather = [&](int kk) {
         const uint64_t* vslot = my_cells + size_t(kk & 1) * nvec * 4;
         const uint32_t fprev = epoch + uint32_t(kk);
-        {
+        if constexpr (CL > 0) {
+            // cluster mode: thread t < cl_cps polls vector column t of this CTA's slice and parks it in shared
+            // memory (vs[0 .. cl_cps * VEC): free outside the checks); after the CTA barrier every warp reads the
+            // columns its lanes own.  One poll per column per CTA: 1 / CL of the cells instead of all of them.
+            if (tid < p.cl_cps) {
+                const int c = cl_rank * p.cl_cps + tid;
+                const int nval = (c < nvec) ? max(0, min(VEC, D - c * VEC)) : 0;
+                const uint32_t nd = (1u << nval) - 1u;
+                T out[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) out[e] = T(0);
+                bool first = true;
+                wd.arm();
+                while (nd != 0u && ok) {
+                    uint64_t w[4];
+                    const uint64_t* cp = vslot + size_t(c) * 4;
+                    ld_relaxed_u64x2(cp, w[0], w[1]);
+                    ld_relaxed_u64x2(cp + 2, w[2], w[3]);
+                    const uint32_t m = C::unpack(w, fprev, out);
+                    const bool hit = (m & nd) == nd;
+                    if (first && p.prepoll_adapt) {
+                        const bool miss = __any_sync(__activemask(), !hit);
+                        spin = miss ? min(spin + 96, 1500) : max(spin - 3, 0);
+                    }
+                    first = false;
+                    if (hit) break;
+                    if (kTimers) ph[5] += 1;
+                    if (wd.expired()) ok = false;
+                }
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) vs[tid * VEC + e] = ((nd >> e) & 1u) ? out[e] : T(0);
+            }
+            if (__syncthreads_or(!ok)) ok = false;          // uniform over the CTA from here on
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) {
+                const int cs = min(lane + i * 32, p.cl_cps - 1);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) vv[i][e] = (need[i] >> e) & 1u ? vs[cs * VEC + e] : T(0);
+            }
+        } else {
             uint64_t w[CPT][4];
             uint32_t pending = 0;
 #pragma unroll
@@ -576,7 +667,29 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
             // ---- slab GEMV, 8 rows per chunk
             double* redk = red + size_t(k & 1) * NW * rpc_pad + size_t(warp) * rpc_pad;
             const T* Wg = Wall + (size_t(rho_ind) * D + r0) * ldw;
-            if (RMODE) {
+            if constexpr (CPL > 0) {
+                // v_{k-1} -> shared memory (unless a check just left it there), one CTA barrier, then warp w alone
+                // forms row r0 + w: 4 interleaved partial sums per lane, one shuffle tree, lane 0 has the sum
+                T* vbuf = vs + size_t((k - 1) & 1) * ldw;
+                if (!vs_ready) {
+#pragma unroll
+                    for (int i = 0; i < CPT; ++i) {
+                        const int c = tid + i * NT;
+                        if (c < nvec) Vec16<T>::sts(vbuf + size_t(c) * VEC, vv[i]);
+                    }
+                    if (__syncthreads_or(!ok)) { aborted = true; break; }
+                }
+                vs_ready = false;
+                double a4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int j = 0; j < (CPL > 0 ? CPL : 1); ++j) {
+                    const int c = min(lane + 32 * j, nvec - 1);
+                    T vp[VEC];
+                    Vec16<T>::lds_to(vbuf + size_t(c) * VEC, vp);
+                    a4[j & 3] = wrow[j].dot(vp, a4[j & 3]);
+                }
+                row_sum = warp_sum((a4[0] + a4[1]) + (a4[2] + a4[3]));
+            } else if (RMODE) {
                 double acc[RM];
 #pragma unroll
                 for (int r = 0; r < RM; ++r) acc[r] = 0.0;
@@ -584,10 +697,17 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 for (int i = 0; i < CPT; ++i) {
 #pragma unroll
                     for (int r = 0; r < RM; ++r)
-                        acc[r] = wreg[RMODE ? r : 0][RMODE ? i : 0].dot(vv[i], acc[r]);
+                        acc[r] = wreg[(RMODE && CPL == 0) ? r : 0][(RMODE && CPL == 0) ? i : 0].dot(vv[i], acc[r]);
                 }
                 warp_multi_reduce8(acc, lane);
-                if ((lane & 3) == 0) redk[lane >> 2] = acc[0];
+                if constexpr (CL > 0) {
+                    // partial sums of the cluster's rows 8 warp .. 8 warp + 7 over this CTA's columns -> the shared
+                    // memory of their owner, CTA `warp` of the cluster, slot [k & 1][this rank][row]
+                    if ((lane & 3) == 0)
+                        dsmem_store_f64(clpart + (size_t(k & 1) * CL + cl_rank) * RM + (lane >> 2), uint32_t(warp), acc[0]);
+                } else {
+                    if ((lane & 3) == 0) redk[lane >> 2] = acc[0];
+                }
             } else if (p.ring) {
                 for (int ch = 0; ch < nchunks; ++ch) {
                     const int rbase = ch * RM;
@@ -639,15 +759,29 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 if ((lane & 3) == 0) redk[rbase + (lane >> 2)] = acc[0];
             }
             const long long tp2 = kTimers ? clock64() : 0;
-            if (__syncthreads_or(!ok)) { aborted = true; break; }
+            if constexpr (CL > 0) {
+                cluster_barrier();                      // every CTA's partial sums have landed (release / acquire)
+                if (!ok) aborted = true;                // keep walking: peers wait for us at every cluster barrier
+            } else if constexpr (CPL == 0) {
+                if (__syncthreads_or(!ok)) { aborted = true; break; }
+            }
             const long long tp3 = clock64();
 
             // ---- finalize own rows: cross-warp sum (fixed order), bias, clamp, publish v_k
             if (is_fin) {
-                const double* rk = red + size_t(k & 1) * NW * rpc_pad + tid;
-                double ys = rk[0];
+                // 1-D: partial sums of the CTA's warps; cluster mode: of the cluster's CTAs, in rank order
+                const double* rk = CL > 0 ? clpart + size_t(k & 1) * (CL > 0 ? CL : 1) * RM + tid
+                                          : red + size_t(k & 1) * NW * rpc_pad + tid;
+                constexpr int NPART = CL > 0 ? CL : NW;
+                const size_t pstride = CL > 0 ? size_t(RM) : size_t(rpc_pad);
+                double ys;
+                if constexpr (CPL > 0) {
+                    ys = row_sum;                       // row-per-warp mode: the warp's own sum, nothing to combine
+                } else {
+                    ys = rk[0];
 #pragma unroll
-                for (int w = 1; w < NW; ++w) ys += rk[size_t(w) * rpc_pad];
+                    for (int w = 1; w < NPART; ++w) ys += rk[size_t(w) * pstride];
+                }
                 const T y = T(ys + double(my_b));        // fp32: the one rounding of this row's W v + b
                 my_v = clamp_keep_nan(y, my_lo, my_hi);
                 uint64_t* dst = p.vcells + size_t(k & 1) * nvec * 4;
@@ -667,9 +801,22 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
 #endif
 
             // ---- residual check (reluqpth.py:218)
-            if (p.adaptive && (k % p.check_interval) == 0) {
+            if (p.adaptive && (k % p.check_interval) == 0 && !(CL > 0 && aborted)) {
                 bool staged = false;
-                if (RMODE) {
+                if constexpr (CPL > 0) {
+                    // v_k into ITS shared-memory buffer: the check reads it there, and so does iteration k + 1
+                    gather(k);
+                    T* vbuf = vs + size_t(k & 1) * ldw;
+#pragma unroll
+                    for (int i = 0; i < CPT; ++i) {
+                        const int c = tid + i * NT;
+                        if (c < nvec) Vec16<T>::sts(vbuf + size_t(c) * VEC, vv[i]);
+                    }
+                    vs_chk = vbuf;
+                    staged = true;          // residual_pass starts with a CTA barrier (uniform abort included)
+                    have_vv = true;
+                    vs_ready = true;
+                } else if (RMODE && CL == 0) {
                     // one gather of v_k serves the check (through shared memory) and iteration k + 1 (registers)
                     gather(k);
                     have_vv = true;
@@ -685,8 +832,22 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 }
                 const bool good = residual_pass(k, epoch + uint32_t(k), false, staged);
                 if (kTimers) ph[4] += clock64() - tp4;
-                if (!good) { aborted = true; break; }
+                if (!good) {
+                    aborted = true;
+                    if (CL == 0) break;
+                    ok = false;                         // cluster mode: no more waiting, but keep arriving
+                }
                 if (solved) break;
+                if constexpr (CL > 0) {
+                    // the pass left all of v_k in shared memory: this CTA's slice for iteration k + 1 comes from there
+#pragma unroll
+                    for (int i = 0; i < CPT; ++i) {
+                        const int c = coff[i] / VEC;
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) vv[i][e] = (need[i] >> e) & 1u ? vs[c * VEC + e] : T(0);
+                    }
+                    have_vv = true;
+                }
             }
         }
     }
@@ -698,6 +859,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
     }
 
     if (p.ring) ring_drain();   // no bulk copy may still target this CTA's shared memory at exit
+    if (CL > 0 && ld_relaxed_u32(p.abort_flag) != 0u) aborted = true;     // somebody else's watchdog
     if (is_fin) static_cast<T*>(p.v)[my_row] = my_v;
     if (blockIdx.x == 0 && tid == 0) {
         rqp_result r;
@@ -977,14 +1139,15 @@ static int launch_tiny(const SingleParams& prm, cudaStream_t stream) {
 // -------------------------------------------------------------------------------------------
 // Host side: launch geometry + dispatch.
 // -------------------------------------------------------------------------------------------
-static size_t smem_fixed_bytes(int elem, long long ldw, int rpc, int block) {
+static size_t smem_fixed_bytes(int elem, long long ldw, int rpc, int block, int vs_copies = 1) {
     const int NW = block / 32;
     const int rpc_pad = (rpc + RM - 1) / RM * RM;
-    size_t o = size_t(ldw) * elem;                 // vs
+    size_t o = size_t(vs_copies) * size_t(ldw) * elem;   // vs (two copies in row-per-warp mode)
     o = (o + 15) & ~size_t(15);
     o += size_t(2) * NW * rpc_pad * sizeof(double);  // red (double for both element types)
     o += size_t(2) * NW * 8 * sizeof(double);      // part, tot
     o += sizeof(Decision) + 16 + 8 * RING_STAGES + 8 + 16;  // dec, mbar, ring barriers, check-row barrier, alignment
+    o += size_t(2) * 8 * RM * sizeof(double);      // cluster mode: partial sums handed over by the 8 CTAs of a cluster
     return o;
 }
 
@@ -1027,7 +1190,53 @@ int plan_single(const rqp_problem* prob, const rqp_settings* stng, const rqp_cap
     const bool can_reg = (rpc <= RM) && (cpt <= 4) && (block == 256);
     if (stng->w_residency == 3 && !can_reg) return RQP_ERR_UNSUPPORTED;
     plan->rmode = (stng->w_residency == 3 || (stng->w_residency == 0 && can_reg)) ? 1 : 0;
+    // cluster (2-D) mode: clusters of 8 CTAs own 64 rows each, a CTA keeps 1/8 of the columns of those rows in
+    // registers (same footprint) and polls 1/8 of the exchange cells; needs every cluster co-resident
+    plan->cl = 0;
+    plan->cl_cps = 0;
+    {
+        const int kCl = 8;
+        const int n_clusters = (D + kCl * RM - 1) / (kCl * RM);
+        const int cps = (nvec + kCl - 1) / kCl;
+        const int cptc = (cps + 31) / 32;
+        const bool can_cl = block == 256 && stng->grid <= 0 && cptc <= 4 && n_clusters * kCl <= caps.sm_count &&
+                            n_clusters <= caps.max_clusters8;
+        if (stng->w_residency == 6 && !can_cl) return RQP_ERR_UNSUPPORTED;
+        // explicit only (or RQP_CL_MIN_BYTES=n: from n bytes of exchange cells per CTA on): measured SLOWER than the
+        // 1-D exchange at every size (C2 fp64: 2.19 vs 1.57 us per iteration, tools/cl_probe.py): polling 1/8 of
+        // the cells saves ~300 cycles of ingest, but the cluster barrier that orders the distributed-shared-memory
+        // handoff sits on the critical path with ~1400 cycles (it waits for the slowest of the cluster's 8 CTAs,
+        // each of which waited for its own 15 publishers)
+        const bool want_cl = stng->w_residency == 6 ||
+                             (stng->w_residency == 0 && can_cl && can_reg && caps.cl_min_cell_bytes > 0 &&
+                              size_t(nvec) * 32 >= size_t(caps.cl_min_cell_bytes));
+        if (want_cl && can_cl) {
+            plan->cl = kCl;
+            plan->cl_cps = cps;
+            plan->rmode = 1;
+            grid = n_clusters * kCl;
+            rpc = RM;
+            cpt = 1;
+            while (cpt < cptc) cpt *= 2;
+        }
+    }
+    // row-per-warp mode: 8 rows per CTA, one per warp; the lane keeps ceil(nvec / 32) pieces of its row
+    plan->cpl = 0;
+    {
+        const int cpl_rt = (nvec + 31) / 32;
+        const bool can_rpw = block == 256 && rpc <= RM && cpt <= 4 && cpl_rt <= 20 && plan->cl == 0;
+        if (stng->w_residency == 7 && !can_rpw) return RQP_ERR_UNSUPPORTED;
+        // explicit only: measured slower than the column-owner scheme at every size (C2 fp64: 1.71 vs 1.56 us per
+        // iteration; tools/cl_probe.py, profiles/r02_exchange_modes.txt) -- the row's 15 shared-memory loads, 30
+        // dependent-ish DFMAs and the shuffle tree cost what the cross-warp sum and the second barrier saved
+        const bool want_rpw = stng->w_residency == 7;
+        if (want_rpw && can_rpw) {
+            plan->cpl = cpl_rt <= 4 ? 4 : (cpl_rt <= 8 ? 8 : (cpl_rt <= 12 ? 12 : (cpl_rt <= 16 ? 16 : 20)));
+            plan->rmode = 1;
+        }
+    }
     if (plan->rmode) rows_smem = 0;
+    const size_t fixed_final = plan->cpl ? smem_fixed_bytes(elem, prob->ldw, rpc, block, 2) : fixed;
     // streaming ring: slabs too large for L2 (W_rho > ~96 MB) are HBM bound; a bulk-copy ring gives
     // the DMA engine the memory-level parallelism that 8 warps of register loads cannot
     const size_t ring_bytes = size_t(RING_STAGES) * RM * 256 * 16;
@@ -1043,7 +1252,7 @@ int plan_single(const rqp_problem* prob, const rqp_settings* stng, const rqp_cap
     plan->cpt = cpt;
     plan->rpc = rpc;
     plan->rows_smem = rows_smem;
-    plan->smem_bytes = fixed + (plan->ring ? ring_bytes : size_t(rows_smem) * row_bytes) + 128;
+    plan->smem_bytes = fixed_final + (plan->ring ? ring_bytes : size_t(rows_smem) * row_bytes) + 128;
     // residual-check rows resident in shared memory when they fit beside everything else (small and
     // medium problems: the checks then never touch L2 for matrix rows); bulk copies need 16-byte rows
     {
@@ -1064,9 +1273,41 @@ int plan_single(const rqp_problem* prob, const rqp_settings* stng, const rqp_cap
     return RQP_OK;
 }
 
-template <typename T, int CPT, int NT, bool RMODE = false>
+// cluster mode: clusters of 8 CTAs, cooperative (all clusters co-resident: the exchange spins across clusters)
+template <typename T, int CPT>
+static int launch_cluster(const SingleParams& prm, const SinglePlan& plan, cudaStream_t stream) {
+    auto kern = rqp_single_kernel<T, CPT, 256, true, 8>;
+    static size_t smem_ok_dev[kMaxDevices] = {};
+    size_t& smem_ok = smem_ok_dev[current_device_slot()];
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(plan.grid));
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = plan.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 8; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    if (plan.smem_bytes > smem_ok || smem_ok == 0) {
+        RQP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes)));
+        int ncl = 0;
+        cfg.numAttrs = 1;       // the occupancy query takes the cluster shape
+        RQP_CUDA_TRY(cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg));
+        cfg.numAttrs = 2;
+        if (ncl * 8 < plan.grid) return RQP_ERR_LAUNCH_TOO_LARGE;
+        smem_ok = plan.smem_bytes;
+    }
+    RQP_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, prm));
+    note_launch();
+    return RQP_OK;
+}
+
+template <typename T, int CPT, int NT, bool RMODE = false, int CL = 0, int CPL = 0>
 static int launch_one(const SingleParams& prm, const SinglePlan& plan, cudaStream_t stream) {
-    auto kern = rqp_single_kernel<T, CPT, NT, RMODE>;
+    auto kern = rqp_single_kernel<T, CPT, NT, RMODE, CL, CPL>;
     // per-instantiation cache of the largest dynamic shared memory size already opted into (and
     // checked to be launchable); saves two runtime calls per solve
     static size_t smem_ok_dev[kMaxDevices] = {};
@@ -1087,6 +1328,25 @@ static int launch_one(const SingleParams& prm, const SinglePlan& plan, cudaStrea
 
 template <typename T, int NT>
 static int launch_cpt(const SingleParams& prm, const SinglePlan& plan, cudaStream_t stream) {
+    if (plan.cpl) {
+        if (NT != 256) return RQP_ERR_UNSUPPORTED;
+        // (columns polled per thread, row pieces per lane): nvec <= 256 -> 1 column per thread, <= 512 -> 2, else 4
+        if (plan.cpl == 4 && plan.cpt == 1) return launch_one<T, 1, 256, true, 0, 4>(prm, plan, stream);
+        if (plan.cpl == 8 && plan.cpt == 1) return launch_one<T, 1, 256, true, 0, 8>(prm, plan, stream);
+        if (plan.cpl == 12 && plan.cpt == 2) return launch_one<T, 2, 256, true, 0, 12>(prm, plan, stream);
+        if (plan.cpl == 16 && plan.cpt == 2) return launch_one<T, 2, 256, true, 0, 16>(prm, plan, stream);
+        if (plan.cpl == 20 && plan.cpt == 4) return launch_one<T, 4, 256, true, 0, 20>(prm, plan, stream);
+        return RQP_ERR_UNSUPPORTED;
+    }
+    if (plan.cl) {
+        if (NT != 256) return RQP_ERR_UNSUPPORTED;
+        switch (plan.cpt) {
+            case 1: return launch_cluster<T, 1>(prm, plan, stream);
+            case 2: return launch_cluster<T, 2>(prm, plan, stream);
+            case 4: return launch_cluster<T, 4>(prm, plan, stream);
+        }
+        return RQP_ERR_UNSUPPORTED;
+    }
     if (plan.rmode) {
         if (NT != 256) return RQP_ERR_UNSUPPORTED;
         switch (plan.cpt) {
@@ -1157,6 +1417,7 @@ int launch_single(const rqp_problem* prob, const rqp_settings* stng, rqp_state* 
     prm.prepoll_adapt = (stng->prepoll_cycles == 0 && (stng->exchange_flags & 2) == 0) ? 1 : 0;
     prm.exch_flags = stng->exchange_flags & 0xff;
     prm.ring = plan.ring;
+    prm.cl_cps = plan.cl_cps;
     prm.check_tpw = plan.check_tpw;
     // bits 8.. of exchange_flags: number of exchange-cell replicas (0 = default)
     {

@@ -28,7 +28,7 @@ class rqp_caps(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("cc_major", C.c_int32), ("cc_minor", C.c_int32),
                 ("sm_count", C.c_int32), ("max_smem_per_block", C.c_int32),
                 ("cooperative_launch", C.c_int32), ("l2_bytes", C.c_int64),
-                ("global_mem_bytes", C.c_int64)]
+                ("global_mem_bytes", C.c_int64), ("max_clusters8", C.c_int32), ("cl_min_cell_bytes", C.c_int32)]
 
 
 class rqp_problem(C.Structure):

@@ -628,3 +628,29 @@ def test_structured_large_both_dtypes(golden, capsys, nx, seed):
         print("\n[structured {}] ".format(tag) + "; ".join(
             "{} {}: {} iters, {:.1f} us/iter".format("f64" if p == torch.float64 else "f32",
                                                      "structured" if s else "dense", it, us) for p, s, it, us in rows))
+
+
+@pytest.mark.parametrize("prec", [torch.float64, torch.float32])
+def test_exchange_modes_agree(golden, prec):
+    """The three register-resident exchange schemes -- column owner (w_residency=3, the default), clusters of 8 CTAs
+    with partial sums through distributed shared memory (6) and row per warp (7) -- on C2 (D=960: 120 CTAs, 15
+    clusters) and a rand_qp problem whose grid is not a multiple of 8 (D=298: 38 CTAs -> 5 clusters, 2 idle CTAs):
+    same status and iteration count as the golden / as each other, x equal to rounding (fp64) or bit for bit where the
+    summation order is the same."""
+    plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+    L, U = plant.bounds(golden.arrays("mpc")["X0"])
+    cases = [((plant.H, plant.g, plant.A, L[0], U[0]), golden.case("mpc", "mpc_col0")),
+             (utils.rand_qp(150, 37, 37, seed=0, compute_sol=False)[:5], None)]
+    for prob, gold in cases:
+        out = {}
+        for mode in (3, 6, 7):
+            m = gpu_model(prob, precision=prec, w_residency=mode, warm_starting=False)
+            res = m.solve()
+            out[mode] = (res.info.iter, res.info.status, res.x.double().cpu().numpy())
+            res2 = m.solve()                                     # second solve on the same workspace (epochs advance)
+            assert (res2.info.iter, res2.info.status) == out[mode][:2]
+        for mode in (6, 7):
+            assert out[mode][:2] == out[3][:2], (mode, out[mode][:2], out[3][:2])
+            assert rel_err(out[mode][2], out[3][2]) < (1e-12 if prec == torch.float64 else 1e-5)
+        if gold is not None and prec == torch.float64:
+            assert out[3][0] == gold["iter"] and rel_err(out[3][2], gold["x"]) < TOL64

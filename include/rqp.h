@@ -126,6 +126,13 @@ typedef struct rqp_state {
                                    after zero-filling the workspace and pass the returned
                                    value to the next call; re-zero the workspace and restart
                                    at 1 once it exceeds 0x70000000 */
+    /* Optional "posted completion" for latency-critical callers (the MPC loop): when post_seq != 0 the LAST CTA
+     * to finish writes the result record and then, after a system-scope fence, sets result->seq = post_seq; with
+     * the record (and x_host) in pinned, device-mapped host memory the host can spin on result->seq instead of
+     * synchronising the stream.  x_host (may be NULL): mapped host buffer that also receives x (the first nx
+     * state entries).  Both 0 / NULL: the record is written by CTA 0 as before and seq stays 0. */
+    void* x_host;
+    uint64_t post_seq;
 } rqp_state;
 
 /* Written by the kernel through the pointer the caller passes (rqp_solve: result_dev): either device memory (copy
@@ -147,6 +154,7 @@ typedef struct rqp_result {
      * [3] cross-warp sum + publish, [4] residual checks, [5] number of failed poll rounds,
      * [6] W slab (re)loads, [7] 1 if the slab lives in registers */
     uint64_t phase_cycles[8];
+    uint64_t seq;               /* rqp_state.post_seq of the solve that wrote this record, written LAST    */
 } rqp_result;
 
 /* One record per residual check: {k, rho_ind_after, pri, dua, rho_estimate} as 5 doubles. */

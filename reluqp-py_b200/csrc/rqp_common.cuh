@@ -196,6 +196,28 @@ struct Watchdog {
     }
 };
 
+// Completion of a solve (rqp_state.post_seq): every CTA calls this after its last write; the LAST one to arrive
+// (self-resetting counter in the workspace header) writes the record and then, behind a system-scope fence, its
+// seq field -- a host spinning on the mapped record sees complete results and a complete x.  The decisions in the
+// record are identical in every CTA; error also reflects the global abort flag.  post_seq == 0: CTA 0 writes.
+__device__ __forceinline__ void post_result(rqp_result* dst, rqp_result& r, uint32_t* ws_header, unsigned long long post_seq,
+                                            int G) {
+    // ws_header[0] abort flag, [16] completion counter, [32..33] t_begin of CTA 0
+    if (post_seq == 0ull) {
+        if (blockIdx.x == 0) *dst = r;
+        return;
+    }
+    __threadfence_system();
+    const uint32_t old = atomicInc(ws_header + 16, uint32_t(G - 1));
+    if (old != uint32_t(G - 1)) return;
+    if (ld_relaxed_u32(ws_header) != 0u) r.error = RQP_ERR_WATCHDOG;
+    r.t_begin_ns = *reinterpret_cast<volatile unsigned long long*>(ws_header + 32);
+    r.seq = 0ull;
+    *dst = r;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(&dst->seq) = post_seq;
+}
+
 // ---------------------------------------------------------------------------------------------
 // 128-bit register vectors.
 // ---------------------------------------------------------------------------------------------

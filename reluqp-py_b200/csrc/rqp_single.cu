@@ -81,6 +81,8 @@ struct SingleParams {
     int replicas;         // copies of the exchange cells; CTA c reads copy c % replicas (spreads the hot
                           // lines every CTA polls over more L2 slices), publishers write all copies
     int cl_cps;           // cluster (2-D) mode: vector columns of v per CTA of a cluster (0 = not that mode)
+    void* x_host;         // optional mapped host copy of x
+    unsigned long long post_seq;   // != 0: posted completion (rqp_state.post_seq)
 };
 
 // Partial sums are DOUBLE for both element types: with fp32 data every 16-byte piece contributes a 4-term fp32
@@ -364,7 +366,10 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
     bool solved = false, aborted = false;
     T pri = CUDART_NAN, dua = CUDART_NAN, obj = CUDART_NAN;
     uint64_t t_begin = 0;
-    if (blockIdx.x == 0 && tid == 0) t_begin = globaltimer_ns();
+    if (blockIdx.x == 0 && tid == 0) {
+        t_begin = globaltimer_ns();
+        if (p.post_seq != 0ull) *reinterpret_cast<volatile unsigned long long*>(p.abort_flag + 32) = t_begin;
+    }
 
     // Residual evaluation on v_k (flag fk in vcells buffer k&1).  final_pass: no index move, no
     // termination test (reluqpth.py:243).  Returns false on watchdog abort (uniform over the CTA).
@@ -860,9 +865,15 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
 
     if (p.ring) ring_drain();   // no bulk copy may still target this CTA's shared memory at exit
     if (CL > 0 && ld_relaxed_u32(p.abort_flag) != 0u) aborted = true;     // somebody else's watchdog
-    if (is_fin) static_cast<T*>(p.v)[my_row] = my_v;
-    if (blockIdx.x == 0 && tid == 0) {
+    if (is_fin) {
+        static_cast<T*>(p.v)[my_row] = my_v;
+        if (p.x_host != nullptr && my_row < nx) static_cast<T*>(p.x_host)[my_row] = my_v;
+        if (p.post_seq != 0ull) __threadfence_system();
+    }
+    if (p.post_seq != 0ull) __syncthreads();        // this CTA's rows are written before thread 0 counts it in
+    if ((blockIdx.x == 0 || p.post_seq != 0ull) && tid == 0) {
         rqp_result r;
+        r.seq = 0ull;
         r.iter = k;
         r.status = solved ? RQP_STATUS_SOLVED : RQP_STATUS_MAX_ITER;
         r.rho_ind = rho_ind;
@@ -881,7 +892,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
         r.rows_in_smem = p.rows_smem;
 #pragma unroll
         for (int i = 0; i < 8; ++i) r.phase_cycles[i] = (unsigned long long)ph[i];
-        *p.result = r;
+        post_result(p.result, r, p.abort_flag, p.post_seq, G);
     }
 }
 
@@ -1085,9 +1096,17 @@ __global__ void __launch_bounds__(TINY_NT, 1) rqp_tiny_kernel(const SingleParams
     if (k > p.max_iter) k = p.max_iter;
     if (!solved) residual_pass(k, k & 1, true);              // fall-through: no index move (reluqpth.py:243)
 
-    for (int r = tid; r < D; r += TINY_NT) static_cast<T*>(p.v)[r] = vs[size_t(k & 1) * D + r];
+    for (int r = tid; r < D; r += TINY_NT) {
+        static_cast<T*>(p.v)[r] = vs[size_t(k & 1) * D + r];
+        if (p.x_host != nullptr && r < nx) static_cast<T*>(p.x_host)[r] = vs[size_t(k & 1) * D + r];
+    }
+    if (p.post_seq != 0ull) {
+        __threadfence_system();
+        __syncthreads();
+    }
     if (tid == 0) {
         rqp_result r;
+        r.seq = 0ull;
         r.iter = k;
         r.status = solved ? RQP_STATUS_SOLVED : RQP_STATUS_MAX_ITER;
         r.rho_ind = rho_ind;
@@ -1102,6 +1121,10 @@ __global__ void __launch_bounds__(TINY_NT, 1) rqp_tiny_kernel(const SingleParams
         for (int i = 0; i < 8; ++i) r.phase_cycles[i] = 0;
         r.phase_cycles[7] = 1;                               // W lives in registers
         *p.result = r;
+        if (p.post_seq != 0ull) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long*>(&p.result->seq) = p.post_seq;
+        }
     }
 }
 
@@ -1418,6 +1441,8 @@ int launch_single(const rqp_problem* prob, const rqp_settings* stng, rqp_state* 
     prm.exch_flags = stng->exchange_flags & 0xff;
     prm.ring = plan.ring;
     prm.cl_cps = plan.cl_cps;
+    prm.x_host = state->x_host;
+    prm.post_seq = state->post_seq;
     prm.check_tpw = plan.check_tpw;
     // bits 8.. of exchange_flags: number of exchange-cell replicas (0 = default)
     {

@@ -65,6 +65,8 @@ struct StructParams {
     uint32_t epoch;
     int rx, rc;          // x rows / constraint rows per CTA
     int stages;          // ring stages (4 or 2)
+    void* x_host;        // optional mapped host copy of x
+    unsigned long long post_seq;   // != 0: posted completion (rqp_state.post_seq)
 };
 
 template <typename T>
@@ -266,7 +268,10 @@ __global__ void __launch_bounds__(SNT, 1) rqp_struct_kernel(const StructParams p
     bool solved = false, aborted = false;
     T pri = CUDART_NAN, dua = CUDART_NAN, obj = CUDART_NAN;
     uint64_t t_begin = 0;
-    if (blockIdx.x == 0 && tid == 0) t_begin = globaltimer_ns();
+    if (blockIdx.x == 0 && tid == 0) {
+        t_begin = globaltimer_ns();
+        if (p.post_seq != 0ull) *reinterpret_cast<volatile unsigned long long*>(p.abort_flag + 32) = t_begin;
+    }
     __syncthreads();
 
     // t_0 = A x_0 for the owned constraint rows (zero on a cold start; a warm start needs it): one row per warp
@@ -438,13 +443,19 @@ __global__ void __launch_bounds__(SNT, 1) rqp_struct_kernel(const StructParams p
     }
     ring_drain();                                           // no bulk copy may still target this CTA's shared memory
     T* vout = static_cast<T*>(p.v);
-    if (own_x) vout[xi_] = xv;
+    if (own_x) {
+        vout[xi_] = xv;
+        if (p.x_host != nullptr) static_cast<T*>(p.x_host)[xi_] = xv;
+    }
+    if (p.post_seq != 0ull) __threadfence_system();
     if (own_c) {
         vout[nx + ci_] = z;
         vout[nx + nc + ci_] = lam;
     }
-    if (blockIdx.x == 0 && tid == 0) {
+    if (p.post_seq != 0ull) __syncthreads();
+    if ((blockIdx.x == 0 || p.post_seq != 0ull) && tid == 0) {
         rqp_result r;
+        r.seq = 0ull;
         r.iter = k;
         r.status = solved ? RQP_STATUS_SOLVED : RQP_STATUS_MAX_ITER;
         r.rho_ind = rho_ind;
@@ -457,7 +468,7 @@ __global__ void __launch_bounds__(SNT, 1) rqp_struct_kernel(const StructParams p
         r.grid = G; r.block = SNT; r.rows_per_cta = p.rx + p.rc; r.rows_in_smem = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) r.phase_cycles[i] = 0;
-        *p.result = r;
+        post_result(p.result, r, p.abort_flag, p.post_seq, G);
     }
 }
 
@@ -571,6 +582,7 @@ int launch_struct(const rqp_problem* prob, const rqp_structured* sp, const rqp_s
     prm.watchdog_ns = (unsigned long long)(stng->watchdog_ms > 0 ? stng->watchdog_ms : 4000) * 1000000ull;
     prm.epoch = state->epoch;
     prm.rx = plan.rx; prm.rc = plan.rc; prm.stages = plan.stages;
+    prm.x_host = state->x_host; prm.post_seq = state->post_seq;
     rc = prob->dtype == RQP_F64 ? launch_struct_t<double>(prm, plan, stream) : launch_struct_t<float>(prm, plan, stream);
     if (rc == RQP_OK) state->epoch += uint32_t(stng->max_iter) + 2u;
     return rc;

@@ -54,7 +54,8 @@ class rqp_settings(C.Structure):
 
 
 class rqp_state(C.Structure):
-    _fields_ = [("v", C.c_void_p), ("rho_ind", C.c_int32), ("epoch", C.c_uint32)]
+    _fields_ = [("v", C.c_void_p), ("rho_ind", C.c_int32), ("epoch", C.c_uint32), ("x_host", C.c_void_p),
+                ("post_seq", C.c_uint64)]
 
 
 class rqp_result(C.Structure):
@@ -64,7 +65,7 @@ class rqp_result(C.Structure):
                 ("n_checks", C.c_int32), ("n_rho_switches", C.c_int32),
                 ("t_begin_ns", C.c_uint64), ("t_end_ns", C.c_uint64),
                 ("grid", C.c_int32), ("block", C.c_int32), ("rows_per_cta", C.c_int32),
-                ("rows_in_smem", C.c_int32), ("phase_cycles", C.c_uint64 * 8)]
+                ("rows_in_smem", C.c_int32), ("phase_cycles", C.c_uint64 * 8), ("seq", C.c_uint64)]
 
 
 class rqp_batch(C.Structure):

@@ -90,20 +90,38 @@ class Settings(object):
 
 
 class Info(object):
-    """Per-solve information (reference ``classes.py:67-88``).  Times are seconds."""
+    """Per-solve information (reference ``classes.py:67-88``).  Times are seconds.  ``obj_val``, ``pri_res``,
+    ``dua_res`` and ``rho_estimate`` read as 0-dim tensors of the solver dtype, as in the reference; the solver hands
+    them over as Python floats and the tensors are built on first access (an MPC loop that only reads ``x`` and
+    ``status`` does not pay for them)."""
+
+    _SCALARS = ("obj_val", "pri_res", "dua_res", "rho_estimate")
 
     def __init__(self, iter=None, status=None, obj_val=None, pri_res=None, dua_res=None,
                  setup_time=0, solve_time=0, update_time=0, run_time=0, rho_estimate=None):
         self.iter = iter
         self.status = status
-        self.obj_val = obj_val
-        self.pri_res = pri_res
-        self.dua_res = dua_res
+        self._raw = {"obj_val": obj_val, "pri_res": pri_res, "dua_res": dua_res, "rho_estimate": rho_estimate}
+        self._dtype = None
         self.setup_time = setup_time
         self.solve_time = solve_time
         self.update_time = update_time
         self.run_time = run_time
-        self.rho_estimate = rho_estimate
+
+    def set_scalars(self, obj_val, pri_res, dua_res, rho_estimate, dtype):
+        self._raw = {"obj_val": obj_val, "pri_res": pri_res, "dua_res": dua_res, "rho_estimate": rho_estimate}
+        self._dtype = dtype
+
+    def _scalar(self, name):
+        v = self._raw[name]
+        if self._dtype is not None and isinstance(v, float):
+            v = self._raw[name] = torch.tensor(v, dtype=self._dtype)
+        return v
+
+
+for _n in Info._SCALARS:
+    setattr(Info, _n, property(lambda self, _n=_n: self._scalar(_n),
+                               lambda self, value, _n=_n: self._raw.__setitem__(_n, value)))
 
 
 class Results(object):

@@ -258,12 +258,20 @@ class _Engine(object):
         self.res_host = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
         self.res_dev = None if self.mapped else torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
         self.res_view = _cabi.rqp_result.from_address(self.res_host.data_ptr())
+        self.res_host_ptr = self.res_host.data_ptr()
+        self.ws_ptr, self.ws_bytes = self.ws.data_ptr(), self.ws.numel()
         self.trace_cap = 0
         self.trace = None
         self.state = _cabi.rqp_state()
+        # posted completion: the last CTA writes the (mapped) record's seq field last; the host spins on it instead
+        # of synchronising the stream (RQP_POST=0 turns it off)
+        self.post = self.mapped and os.environ.get("RQP_POST", "1") != "0"
+        self.seq = 0
+        self.x_host = None            # optional pinned [nx] buffer the kernel also writes x into (resolve)
 
     def _fill_settings(self, max_iter=None, adaptive=None):
         st, s = self.settings, self.stng
+        self._stng_key = None
         s.max_iter = int(st.max_iter if max_iter is None else max_iter)
         s.check_interval = int(st.check_interval)
         s.adaptive_rho = int(bool(st.adaptive_rho if adaptive is None else adaptive))
@@ -276,6 +284,15 @@ class _Engine(object):
         s.w_residency, s.watchdog_ms = self.tuning["w_residency"], self.tuning["watchdog_ms"]
         s.poll_backoff_ns = self.tuning["poll_backoff_ns"]
         s.prepoll_cycles, s.exchange_flags = self.tuning["prepoll_cycles"], self.tuning["exchange_flags"]
+
+    def _fill_settings_cached(self):
+        """_fill_settings only when a setting changed since the last call (the MPC loop calls this every step)."""
+        st = self.settings
+        key = (st.max_iter, st.check_interval, st.adaptive_rho, st.eps_abs, st.eps_rel, st.rho_min, st.rho_max,
+               st.adaptive_rho_tolerance)
+        if key != getattr(self, "_stng_key", None):
+            self._fill_settings()
+            self._stng_key = key
 
     def enable_trace(self, cap):
         if cap > self.trace_cap:
@@ -291,6 +308,7 @@ class _Engine(object):
         self.state.v = v.data_ptr()
         self.state.rho_ind = int(rho_ind)
         self.state.epoch = self.epoch
+        self._arm_post()
         res_ptr = self.res_host.data_ptr() if self.mapped else self.res_dev.data_ptr()
         stream = _cabi.raw_stream(self.device.index)
         trace_ptr = self.trace.data_ptr() if self.trace is not None else None
@@ -306,9 +324,36 @@ class _Engine(object):
         if not self.mapped:
             self.res_host.copy_(self.res_dev, non_blocking=True)
 
+    def _arm_post(self, x_host=None):
+        st = self.state
+        if self.post:
+            self.seq += 1
+            st.post_seq = self.seq
+            st.x_host = x_host.data_ptr() if x_host is not None else None
+        else:
+            st.post_seq, st.x_host = 0, None
+
+    def wait_posted(self):
+        """Spin on the mapped record until the kernel has posted this solve (bounded: falls back to a stream
+        synchronise after the watchdog time); returns False when posting is off."""
+        if not self.post:
+            return False
+        r, want = self.res_view, self.seq
+        if r.seq == want:
+            return True
+        limit = time.perf_counter() + 1e-3 * (self.stng.watchdog_ms or 4000) * 2 + 1.0
+        n = 0
+        while r.seq != want:
+            n += 1
+            if (n & 0xfff) == 0 and time.perf_counter() > limit:
+                return False
+        return True
+
     def finish(self):
-        """Wait for the stream and return the result record (a live ctypes view)."""
-        _cabi.check(self.lib.rqp_stream_sync(_cabi.raw_stream(self.device.index)), "rqp_stream_sync")
+        """Wait for the solve and return the result record (a live ctypes view): spin on the posted record, or
+        synchronise the stream when posting is off."""
+        if not self.wait_posted():
+            _cabi.check(self.lib.rqp_stream_sync(_cabi.raw_stream(self.device.index)), "rqp_stream_sync")
         r = self.res_view
         if r.error != 0:
             self.ws.zero_()       # exchange cells may hold flags of an aborted epoch
@@ -540,7 +585,7 @@ class ReLU_QP(object):
         st = self.settings
         nx, nc = self.QP.nx, self.QP.nc
         eng = self._engine
-        self._timer.tic_host()      # solve() ends with a stream synchronise: host time == device time
+        self._timer.tic_host()      # solve() ends by waiting for the kernel: host time == device time
         if st.verbose and st.adaptive_rho:
             eng.enable_trace(st.max_iter // max(1, st.check_interval) + 2)
         r = eng.run(self.output, self.rho_ind)
@@ -581,6 +626,8 @@ class ReLU_QP(object):
         if any(torch.is_tensor(v) and v.device.type != "cpu" for v in (g, l, u)):
             raise ValueError("resolve() takes host vectors; use update() + solve() for device tensors")
         self._timer.tic_host()
+        if eng.post and g is None:
+            return self._resolve_posted(l, u)
         spans = [sp for sp in (self._stage(0, nx, g) if g is not None else None,
                                self._stage(nx, nx + nc, l) if l is not None else None,
                                self._stage(nx + nc, nx + 2 * nc, u) if u is not None else None) if sp]
@@ -625,6 +672,66 @@ class ReLU_QP(object):
                             dua_res=r.dua_res, rho_estimate=r.rho_estimate, obj_val=r.obj_val)
         return self.results
 
+    def _resolve_posted(self, l, u):
+        """resolve(l=, u=) without a stream synchronise: the new bounds go from the pinned staging buffer to the
+        device with one asynchronous copy, the kernel writes x and the result record straight into pinned host
+        memory and posts completion (rqp_state.post_seq), and the host spins on the record.  The runtime sees one
+        copy and one cooperative launch per control step.  (Letting the kernel read l, u from pinned host memory
+        directly saves the copy call but costs the kernel 7 us of PCIe reads at its start -- measured, dropped.)"""
+        eng = self._engine
+        st = self.settings
+        nx, nc = self.QP.nx, self.QP.nc
+        es = self._glu_es
+        if self._glu_pending:       # an update() copy nobody has waited for yet may still be reading the staging buffer
+            _cabi.check(eng.lib.rqp_stream_sync(_cabi.raw_stream(st.device.index)), "rqp_stream_sync")
+            self._glu_pending = False
+        lo, hi = None, None
+        if l is not None:
+            np.copyto(self._glu_np[nx:nx + nc], l.numpy() if torch.is_tensor(l) else np.asarray(l), casting="unsafe")
+            lo, hi = nx, nx + nc
+        if u is not None:
+            np.copyto(self._glu_np[nx + nc:], u.numpy() if torch.is_tensor(u) else np.asarray(u), casting="unsafe")
+            lo, hi = (nx if lo is not None else nx + nc), nx + 2 * nc
+        xh = getattr(self, "_x_host", None)
+        if xh is None or xh.numel() != nx or xh.dtype != st.precision:
+            xh = self._x_host = torch.zeros(nx, dtype=st.precision).pin_memory()
+            self._x_host_np = xh.numpy()
+        eng._fill_settings_cached()
+        if eng.epoch + eng.stng.max_iter + 2 > _cabi.EPOCH_LIMIT:
+            eng.ws.zero_()
+            eng.epoch = 1
+        state = eng.state
+        state.v = self.output.data_ptr()
+        state.rho_ind = int(self.rho_ind)
+        state.epoch = eng.epoch
+        eng._arm_post(xh)
+        lib = eng.lib
+        with torch.cuda.device(st.device):
+            stream = _cabi.raw_stream(st.device.index)
+            if lo is not None:
+                rc = lib.rqp_copy_h2d(self._glu_ptr + lo * es, self._glu_host_ptr + lo * es, (hi - lo) * es, stream)
+                if rc != 0:
+                    _cabi.check(rc, "rqp_copy_h2d")
+            if eng.structured:
+                rc = lib.rqp_solve_structured(C.byref(eng.prob), C.byref(eng.sp), C.byref(eng.stng), C.byref(state),
+                                              eng.res_host_ptr, None, 0, eng.ws_ptr, eng.ws_bytes, stream)
+            else:
+                rc = lib.rqp_solve(C.byref(eng.prob), C.byref(eng.stng), C.byref(state), eng.res_host_ptr, None, 0,
+                                   eng.ws_ptr, eng.ws_bytes, stream)
+            if rc != 0:
+                _cabi.check(rc, "rqp_solve")
+        eng.epoch = int(state.epoch)
+        r = eng.finish()
+        info = self.results.info
+        info.update_time = 0.0
+        self.rho_ind = int(r.rho_ind)
+        out = self.output
+        self.x, self.z, self.lam = out[:nx], out[nx:nx + nc], out[nx + nc:nx + 2 * nc]
+        self.results.x_host = self._x_host_np
+        self.update_results(iter=int(r.iter), status=STATUS_NAMES[int(r.status)], pri_res=r.pri_res,
+                            dua_res=r.dua_res, rho_estimate=r.rho_estimate, obj_val=r.obj_val)
+        return self.results
+
     def warm_start(self, x=None, z=None, lam=None, rho=None):
         """Warm start primal / dual variables and rho.  Unlike the reference (where x, z, lam are
         stored but never reach the state vector) the state IS seeded here."""
@@ -650,8 +757,8 @@ class ReLU_QP(object):
         self.results.z = self.z
         info.iter = iter
         info.status = status
-        info.obj_val, info.pri_res, info.dua_res, info.rho_estimate = torch.tensor(
-            (obj_val, pri_res, dua_res, rho_estimate), dtype=dt).unbind(0)
+        # 0-dim tensors of the solver dtype, like the reference's -- built on first access (Info keeps the floats)
+        info.set_scalars(obj_val, pri_res, dua_res, rho_estimate, dt)
         run_time = self._timer.toc(sync=False)
         info.run_time = run_time
         info.solve_time = info.update_time + run_time

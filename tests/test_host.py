@@ -175,10 +175,10 @@ def test_cabi_exports_match_header():
         assert getattr(lib, name) is not None
     lib.rqp_strerror.restype = ctypes.c_char_p
     assert lib.rqp_strerror(0) == b"ok" and b"watchdog" in lib.rqp_strerror(-6)
-    assert ctypes.sizeof(_cabi.rqp_result) == 152
+    assert ctypes.sizeof(_cabi.rqp_result) == 160
     assert ctypes.sizeof(_cabi.rqp_settings) == 80
     assert ctypes.sizeof(_cabi.rqp_problem) == 96
-    assert ctypes.sizeof(_cabi.rqp_state) == 16
+    assert ctypes.sizeof(_cabi.rqp_state) == 32
     assert ctypes.sizeof(_cabi.rqp_batch) == 152
     # bad arguments are reported, not crashed on (no GPU needed: checks come first)
     assert lib.rqp_update_bias(1, 0, 0, 0, None, None, None, None) == -1

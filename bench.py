@@ -46,6 +46,8 @@ for p in (os.path.join(REPO, "reluqp-py_b200"), REPO):
 import torch  # noqa: E402
 
 L2_FLUSH_BYTES = 512 << 20
+# dram__bytes_read.sum + dram__bytes_write.sum of one large_qp solve launch (ncu --set full, profiles/r02_large_qp_ncu_full.csv)
+LARGE_QP_TRAFFIC = 351.0e6
 
 
 def measured_peaks():
@@ -597,9 +599,9 @@ def run_single(args, rank, world, dev):
         roofline=dict(bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s",
                       frac=achieved / peaks["hbm_gbs"],
                       # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full,
-                      # profiles/r01d_single_mpc_ncu_full.csv (mean of the two captured launches)
-                      traffic=28.4e6 if args.workload == "mpc_single" else None,
-                      traffic_source="profiles/r01d_single_mpc_ncu_full.csv" if args.workload == "mpc_single" else None,
+                      # profiles/r02_single_mpc_ncu_full.csv (mean of the two captured launches), r02_large_qp_ncu_full.csv
+                      traffic=33.4e6 if args.workload == "mpc_single" else (LARGE_QP_TRAFFIC if args.workload == "large_qp" else None),
+                      traffic_source="profiles/r02_single_mpc_ncu_full.csv" if args.workload == "mpc_single" else ("profiles/r02_large_qp_ncu_full.csv" if args.workload == "large_qp" else None),
                       peak_source=peaks["source"],
                       note="HBM-equivalent: W_rho stays in registers / shared memory / L2 across iterations, so "
                            "achieved can exceed the DRAM copy peak; algorithmic bytes = s*(D^2+3D+2nc) per iteration "

@@ -200,8 +200,8 @@ def run_batched(args, rank, world, dev):
         all_solved=weak["all_solved"],
         roofline=dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
                       # dram__bytes_read.sum + dram__bytes_write.sum of one window launch, ncu --set full
-                      traffic=(473.8e6 + 679.2e6) if (B == 4096 and dt == torch.float32 and args.batch_engine == 0) else None,
-                      traffic_source="profiles/r01d_batched_window_ncu_full.csv" if (B == 4096 and dt == torch.float32 and args.batch_engine == 0) else None,
+                      traffic=(500.15e6 + 687.35e6) if (B == 4096 and dt == torch.float32 and args.batch_engine == 0) else None,
+                      traffic_source="profiles/r02_batched_window_ncu_full.csv" if (B == 4096 and dt == torch.float32 and args.batch_engine == 0) else None,
                       peak_source=peak_source,
                       kernel="one full check window ({} iterations x {} columns) of the iteration GEMM".format(ci, B),
                       launch_ms=1e3 * win_s if win_s else None, flops_per_launch=win_flops,

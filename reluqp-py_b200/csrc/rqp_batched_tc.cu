@@ -23,6 +23,10 @@
 #include "rqp_host.h"
 #include "rqp_tc.h"
 
+#ifndef RQP_TC_KAHAN
+#define RQP_TC_KAHAN 0      // experiment switch (tools/kahan_variant.sh): compensated sum of the chunk partials
+#endif
+
 namespace rqp {
 
 constexpr int TC_BM = 128;       // state rows per tile (UMMA M)
@@ -646,6 +650,13 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                                   ? a.chunk_kb : (nk > 0 ? nk : 1);
             const int nchunks = (nk + chunk - 1) / chunk;
             uint32_t sum[NCH][32];
+#if RQP_TC_KAHAN
+            float comp[NCH][32];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) comp[c][j] = 0.f;
+#endif
             if (nchunks == 0) {
                 // empty K slice (the host avoids it; kept correct): contributes zeros, but must not run ahead
                 // of the iteration order the other ranks get from their operand dependency
@@ -675,9 +686,21 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                     } else {
                         uint32_t r[32];
                         tmem_ld32(taddr + c * 32, r);
+#if RQP_TC_KAHAN
+                        // experiment: error-free (two-sum) accumulation of the chunk partials
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float aa = __uint_as_float(sum[c][j]), bb = __uint_as_float(r[j]);
+                            const float ss = aa + bb;
+                            const float bv = ss - aa;
+                            comp[c][j] += (aa - (ss - bv)) + (bb - bv);
+                            sum[c][j] = __float_as_uint(ss);
+                        }
+#else
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             sum[c][j] = __float_as_uint(__uint_as_float(sum[c][j]) + __uint_as_float(r[j]));
+#endif
                     }
                 }
                 tc_fence_before();
@@ -685,6 +708,12 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                 if (lane == 0) mbar_arrive(acc_empty + acc);
                 if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
             }
+#if RQP_TC_KAHAN
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum[c][j] = __float_as_uint(__uint_as_float(sum[c][j]) + comp[c][j]);
+#endif
             const long long ts0 = clock64();
             if (a.ksplit > 1) {
                 // Split-K: every rank parks its partial sums of this warp's sub-block (32 rows x CPW columns)

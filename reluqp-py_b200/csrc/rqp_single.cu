@@ -93,20 +93,52 @@ __device__ __forceinline__ void chunk_dot(const T* __restrict__ wrow0, long long
                                           double (&acc)[RM]) {
 #pragma unroll
     for (int r = 0; r < RM; ++r) acc[r] = 0.0;
+    // A partial chunk (nrows < RM) reads its last row again for the missing ones instead of guarding each row: the
+    // guards made the compiler emit a branch per row and serialise load -> dot -> load (eight exposed latencies per
+    // chunk, the same pathology as in the ring step, ncu r02); the duplicate sums land in rows nobody finalises.
+    long long roff[RM];
+#pragma unroll
+    for (int r = 0; r < RM; ++r) roff[r] = (long long)(FULL ? r : min(r, nrows - 1)) * ldw;
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
         Vec16<T> w[RM];
 #pragma unroll
         for (int r = 0; r < RM; ++r) {
-            if (FULL || r < nrows) {
-                const T* ptr = wrow0 + (long long)r * ldw + coff[i];
-                w[r] = SMEM ? Vec16<T>::lds(ptr) : Vec16<T>::ldg(ptr);
-            }
+            const T* ptr = wrow0 + roff[r] + coff[i];
+            w[r] = SMEM ? Vec16<T>::lds(ptr) : Vec16<T>::ldg(ptr);
         }
 #pragma unroll
-        for (int r = 0; r < RM; ++r) {
-            if (FULL || r < nrows) acc[r] = w[r].dot(vv[i], acc[r]);
-        }
+        for (int r = 0; r < RM; ++r) acc[r] = w[r].dot(vv[i], acc[r]);
+    }
+}
+
+// Partial chunk of a SHARED-MEMORY slab with exactly NR (compile time) rows: no guards and no duplicate reads (the
+// mid sizes whose slab sits in shared memory are bound by its bandwidth, so re-reading a row costs real time).
+template <typename T, int CPT, int NR>
+__device__ __forceinline__ void chunk_dot_smem_nr(const T* wrow0, long long ldw, const int (&coff)[CPT],
+                                                  const T (&vv)[CPT][Cell<T>::kVec], double (&acc)[RM]) {
+#pragma unroll
+    for (int r = 0; r < RM; ++r) acc[r] = 0.0;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+        Vec16<T> w[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) w[r] = Vec16<T>::lds(wrow0 + (long long)r * ldw + coff[i]);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[r] = w[r].dot(vv[i], acc[r]);
+    }
+}
+template <typename T, int CPT>
+__device__ __forceinline__ void chunk_dot_smem_partial(const T* wrow0, long long ldw, int nr, const int (&coff)[CPT],
+                                                       const T (&vv)[CPT][Cell<T>::kVec], double (&acc)[RM]) {
+    switch (nr) {       // uniform over the CTA
+        case 1: chunk_dot_smem_nr<T, CPT, 1>(wrow0, ldw, coff, vv, acc); break;
+        case 2: chunk_dot_smem_nr<T, CPT, 2>(wrow0, ldw, coff, vv, acc); break;
+        case 3: chunk_dot_smem_nr<T, CPT, 3>(wrow0, ldw, coff, vv, acc); break;
+        case 4: chunk_dot_smem_nr<T, CPT, 4>(wrow0, ldw, coff, vv, acc); break;
+        case 5: chunk_dot_smem_nr<T, CPT, 5>(wrow0, ldw, coff, vv, acc); break;
+        case 6: chunk_dot_smem_nr<T, CPT, 6>(wrow0, ldw, coff, vv, acc); break;
+        default: chunk_dot_smem_nr<T, CPT, 7>(wrow0, ldw, coff, vv, acc); break;
     }
 }
 
@@ -632,9 +664,12 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) vv[i][e] = ((need[i] >> e) & 1u) ? out[e] : T(0);
             }
-            if (RMODE && p.prepoll_adapt) {     // latency-bound sizes only: the large kernels sit at 255 registers
+            if (p.prepoll_adapt) {
+                // every mode (round 2): a fixed spin is wrong by a factor of two somewhere -- fp32 D = 1600 needs
+                // ~1000 cycles (2.7 us per iteration; 3.6 with 600, 7.2 with none: early polls of 146 CTAs for
+                // 25 KB each queue in front of the publishes), other sizes less
                 const bool miss = __any_sync(0xffffffffu, pending != 0u);
-                spin = miss ? min(spin + 96, 1500) : max(spin - 3, 0);
+                spin = miss ? min(spin + 96, 3000) : max(spin - 3, 0);
             }
             wd.arm();
             while (pending != 0u && ok) {
@@ -754,7 +789,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
                 if (rbase < rows_s) {  // rows_s is a multiple of RM unless it equals rows
                     const T* w0 = Ws + size_t(rbase) * ldw;
                     if (nr == RM) chunk_dot<T, CPT, true, true>(w0, ldw, nr, coff, vv, acc);
-                    else chunk_dot<T, CPT, true, false>(w0, ldw, nr, coff, vv, acc);
+                    else chunk_dot_smem_partial<T, CPT>(w0, ldw, nr, coff, vv, acc);
                 } else {
                     const T* w0 = Wg + size_t(rbase) * ldw;
                     if (nr == RM) chunk_dot<T, CPT, false, true>(w0, ldw, nr, coff, vv, acc);

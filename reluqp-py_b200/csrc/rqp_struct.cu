@@ -225,8 +225,17 @@ __global__ void __launch_bounds__(SNT, 1) rqp_struct_kernel(const StructParams p
     // gather n elements (nv vector columns) with flag `flag` from `cells` into dst (shared memory)
     // Up to GB columns of a thread are polled together (all loads in flight at once: one L2 round trip per batch
     // instead of one per column); columns whose flags have not arrived are polled again.
-    auto gather = [&](const uint64_t* cells, int n, int nv, uint32_t flag, T* dst) {
+    // `spin` (per exchange, tuned per warp while the solve runs as in the dense kernel): cycles to wait after this
+    // CTA's own publish before the first poll -- polls that arrive before the other CTAs' stores have landed come
+    // back empty, cost a second L2 round trip and queue in front of those very stores.
+    auto gather = [&](const uint64_t* cells, int n, int nv, uint32_t flag, T* dst, int& spin, long long t_pub) {
         constexpr int GB = 4;
+        if (spin > 0) {
+            const long long t_until = t_pub + spin;
+            while (clock64() < t_until) {
+            }
+        }
+        bool first = true;
         wd.arm();
         for (int c0g = tid; c0g < nv && ok; c0g += GB * SNT) {
             uint32_t pending = 0;
@@ -259,10 +268,16 @@ __global__ void __launch_bounds__(SNT, 1) rqp_struct_kernel(const StructParams p
                         }
                     }
                 }
+                if (first) {
+                    const bool miss = __any_sync(__activemask(), pending != 0u);
+                    spin = miss ? min(spin + 96, 3000) : max(spin - 3, 0);
+                    first = false;
+                }
                 if (pending != 0u && wd.expired()) ok = false;
             }
         }
     };
+    int spin_w = 600, spin_x = 600, spin_l = 0;
 
     int k = 0, n_checks = 0, n_switch = 0;
     bool solved = false, aborted = false;
@@ -290,7 +305,7 @@ __global__ void __launch_bounds__(SNT, 1) rqp_struct_kernel(const StructParams p
         // lambda to everybody
         uint64_t* lslot = p.lcells + size_t(n_checks & 1) * nvc * 4;
         if (own_c) C::publish(lslot, ci_, lam, pflag);
-        gather(lslot, nc, nvc, pflag, lams);
+        gather(lslot, nc, nvc, pflag, lams, spin_l, clock64());
         good = good && ok;
         if (__syncthreads_or(!good)) return false;
         const T* __restrict__ Hm = static_cast<const T*>(p.H);
@@ -411,7 +426,7 @@ __global__ void __launch_bounds__(SNT, 1) rqp_struct_kernel(const StructParams p
             lam = T(double(lam) + double(Rr) * (tval - double(z)));
             C::publish(wslot, ci_, T(double(Rr) * double(z) - double(lam)), fk);
         }
-        gather(wslot, nc, nvc, fk, us + nx);
+        gather(wslot, nc, nvc, fk, us + nx, spin_w, clock64());
         if (__syncthreads_or(!ok)) { aborted = true; break; }
         // ---- phase A: x+ = M_rho [x; w] + b_x
         ring_gemv(xrows, chA, ncolA);
@@ -421,8 +436,9 @@ __global__ void __launch_bounds__(SNT, 1) rqp_struct_kernel(const StructParams p
             xv = T(cross_warp(tid) + double(bx));
             C::publish(xslot, xi_, xv, fk);
         }
+        const long long t_pubx = clock64();
         __syncthreads();                                    // red is rewritten by phase B
-        gather(xslot, nx, nvx, fk, us);
+        gather(xslot, nx, nvx, fk, us, spin_x, t_pubx);
         if (__syncthreads_or(!ok)) { aborted = true; break; }
         // ---- phase B: t+ = A x+,  z+ = clamp(t+ + R^-1 lambda+)
         ring_gemv(crows, chB, nx);

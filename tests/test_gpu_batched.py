@@ -565,3 +565,45 @@ def test_batched_fp32_parity_well_conditioned(capsys):
             ex, ez, float(res.iter.float().mean()), np.mean([r.iter for r in ref])))
     assert res.status == [r.status for r in ref]
     assert ex < 1e-4 and ez < 1e-4
+
+
+def test_host_array_paths_and_small_batch_isolation(golden):
+    """Host-side contracts of solve_batch (round 2): pageable numpy, pinned numpy (`pinned_batch_arrays`) and device
+    tensors give identical results; `x_out` receives x in pinned memory; the few-column path (B <= 40 in fp64) leaves
+    the single-QP solver's state alone (it used to overwrite QP.l / QP.u and advance the engine's epoch)."""
+    plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+    L, U = plant.bounds(golden.arrays("mpc")["X0"])
+    m = gpu_model((plant.H, plant.g, plant.A, L[0], U[0]), warm_starting=False)
+    nx = m.QP.nx
+    # large enough for the GEMM engines
+    L4, U4 = np.tile(L, (4, 1)), np.tile(U, (4, 1))
+    r_np = m.solve_batch(L4, U4)
+    Lh, Uh, Xh = m.pinned_batch_arrays(L4.shape[0])
+    Lh[...] = L4
+    Uh[...] = U4
+    r_pin = m.solve_batch(Lh, Uh, x_out=Xh)
+    r_dev = m.solve_batch(torch.as_tensor(L4, device="cuda"), torch.as_tensor(U4, device="cuda"))
+    for r in (r_pin, r_dev):
+        assert torch.equal(r.iter, r_np.iter) and torch.equal(r.x, r_np.x)
+    assert np.array_equal(Xh, r_np.x.cpu().numpy()) and r_pin.x_host is Xh
+    with pytest.raises(ValueError):
+        m.solve_batch(Lh, Uh, x_out=np.zeros((3, nx)))
+    # few columns: single-QP kernel per column, private state
+    l_before, u_before = m.QP.l.clone(), m.QP.u.clone()
+    epoch_before, rho_before = m._engine.epoch, m.rho_ind
+    out_before = m.output
+    r_small = m.solve_batch(L[:5], U[:5], x_out=Xh[:5])
+    assert r_small.sweeps == 0                                   # the small path ran
+    assert torch.equal(m.QP.l, l_before) and torch.equal(m.QP.u, u_before)
+    assert m._engine.epoch == epoch_before and m.rho_ind == rho_before and m.output is out_before
+    for j in range(5):
+        g = golden.case("mpc", "mpc_col{}".format(j))
+        assert int(r_small.iter[j]) == g["iter"] and rel_err(r_small.x[j].cpu().numpy(), g["x"]) < 1e-6
+    assert np.array_equal(Xh[:5], r_small.x.cpu().numpy())
+    # and the single-QP solver still solves ITS problem (column 0) afterwards
+    res = m.solve()
+    assert res.info.iter == golden.case("mpc", "mpc_col0")["iter"]
+    # structured solvers have no dense matrices for the batched engines: a clear error
+    ms = gpu_model((plant.H, plant.g, plant.A, L[0], U[0]), structured=True)
+    with pytest.raises(RuntimeError, match="dense layer matrices"):
+        ms.solve_batch(L4, U4)

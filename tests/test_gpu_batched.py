@@ -573,7 +573,7 @@ def test_host_array_paths_and_small_batch_isolation(golden):
     the single-QP solver's state alone (it used to overwrite QP.l / QP.u and advance the engine's epoch)."""
     plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
     L, U = plant.bounds(golden.arrays("mpc")["X0"])
-    m = gpu_model((plant.H, plant.g, plant.A, L[0], U[0]), warm_starting=False)
+    m = gpu_model((plant.H, plant.g, plant.A, L[0], U[0]))       # gpu_model sets warm_starting=False
     nx = m.QP.nx
     # large enough for the GEMM engines
     L4, U4 = np.tile(L, (4, 1)), np.tile(U, (4, 1))

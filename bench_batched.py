@@ -41,6 +41,25 @@ def tf32_peak_live(dev, seconds=0.0):
     return best
 
 
+def fp64_peak_live(dev):
+    """cuBLAS DGEMM rate (4096^3, best of 10): the fp64 tensor (DMMA) rate the library path reaches on this GPU."""
+    n = 4096
+    a = torch.randn((n, n), device=dev, dtype=torch.float64)
+    b = torch.randn((n, n), device=dev, dtype=torch.float64)
+    for _ in range(2):
+        torch.matmul(a, b)
+    best = 0.0
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        e1.synchronize()
+        best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    del a, b
+    return best
+
+
 def batched_config(args, world):
     """`config` of the JSON line -- identical in both arms (`--impl ours` and `--impl reference`)."""
     return dict(workload="mpc_batched", qps_per_gpu=args.batch, batch_dtype=args.batch_dtype,
@@ -186,8 +205,11 @@ def run_batched(args, rank, world, dev):
         peak_note = ("TF32 dense peak measured in this run ({:.0f} TFLOP/s; measured bf16 burst / 2 = {:.0f}); "
                      "3xTF32 executes 3x the algorithmic flops").format(tf32, peaks["bf16_tflops"] / 2.0)
     else:
-        peak, peak_source = 37.1, "tools/ubench/fp64_rate.cu on a B200 of this pool (profiles/r02_peaks.json)"
-        peak_note = "fp64 DMMA / DFMA issue-rate peak (no fp64 figure in MEASURED_PEAKS.json)"
+        dgemm = fp64_peak_live(dev)
+        peak = max(dgemm, 37.1)
+        peak_source = ("max(measured live: cuBLAS DGEMM 4096^3 best of 10 = {:.1f} TFLOP/s, 37.1 = DMMA / DFMA issue-rate "
+                       "microbenchmark tools/ubench/fp64_rate.cu)").format(dgemm)
+        peak_note = "fp64 tensor (DMMA) peak: no fp64 figure in MEASURED_PEAKS.json, so measured here"
     mma_mult = 3.0 if dt == torch.float32 and args.batch_engine != 1 else 1.0
     from bench_batched import batched_config
     line = dict(

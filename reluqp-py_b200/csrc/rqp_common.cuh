@@ -418,6 +418,21 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// Bulk copy with an L2 cache policy: `frac` of the lines are kept with evict_last priority, the rest evict_first.
+// For slabs a little larger than L2 this pins a stable subset across iterations instead of letting LRU thrash.
+__device__ __forceinline__ uint64_t l2_policy_fraction(float frac) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol) : "f"(frac));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                              uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------

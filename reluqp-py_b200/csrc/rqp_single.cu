@@ -83,6 +83,7 @@ struct SingleParams {
     int cl_cps;           // cluster (2-D) mode: vector columns of v per CTA of a cluster (0 = not that mode)
     void* x_host;         // optional mapped host copy of x
     unsigned long long post_seq;   // != 0: posted completion (rqp_state.post_seq)
+    float l2_frac;        // ring: fraction of W_rho's lines copied with L2 evict_last priority (0 = no hint)
 };
 
 // Partial sums are DOUBLE for both element types: with fp32 data every 16-byte piece contributes a 4-term fp32
@@ -290,6 +291,7 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
     // the exchange is waiting).
     const int cpt_rt = (nvec + NT - 1) / NT;          // column chunks actually present
     const int ring_T = nchunks * cpt_rt;              // tiles per iteration
+    const uint64_t l2pol = (p.ring && p.l2_frac > 0.f) ? l2_policy_fraction(p.l2_frac) : 0ull;
     uint32_t ring_phase = 0;                          // bit s: parity to wait for on stage s
     int ring_cstage = 0, ring_pnext = 0;
     // called by ALL lanes of warp 0: lane 0 arms the barrier, then lanes 0..nr-1 issue one row copy each (one
@@ -304,7 +306,12 @@ __global__ void __launch_bounds__(NT, 1) rqp_single_kernel(const SingleParams p)
         unsigned char* dst = reinterpret_cast<unsigned char*>(Ws) + size_t(stage) * RM * NT * 16;
         if (lane == 0) mbar_expect_tx(rbar + stage, uint32_t(nr) * cb);
         __syncwarp();
-        if (lane < nr) bulk_g2s(dst + size_t(lane) * NT * 16, src + size_t(lane) * ldw, cb, rbar + stage);
+        if (lane < nr) {
+            if (p.l2_frac > 0.f)
+                bulk_g2s_hint(dst + size_t(lane) * NT * 16, src + size_t(lane) * ldw, cb, rbar + stage, l2pol);
+            else
+                bulk_g2s(dst + size_t(lane) * NT * 16, src + size_t(lane) * ldw, cb, rbar + stage);
+        }
     };
     auto ring_wait = [&](int stage) -> bool {
         wd.arm();
@@ -1478,6 +1485,14 @@ int launch_single(const rqp_problem* prob, const rqp_settings* stng, rqp_state* 
     prm.cl_cps = plan.cl_cps;
     prm.x_host = state->x_host;
     prm.post_seq = state->post_seq;
+    // ring slabs up to ~2.5x the L2: keep a stable subset of W_rho (0.75 L2 worth) resident across iterations
+    prm.l2_frac = 0.f;
+    if (plan.ring) {
+        const double wb = double(prm.D) * double(prob->ldw) * (prob->dtype == RQP_F64 ? 8.0 : 4.0);
+        const char* e = getenv("RQP_L2_FRAC");
+        double f = e ? atof(e) : (wb <= 2.5 * double(caps.l2_bytes) ? 0.75 * double(caps.l2_bytes) / wb : 0.0);
+        prm.l2_frac = float(f > 1.0 ? 1.0 : (f < 0.0 ? 0.0 : f));
+    }
     prm.check_tpw = plan.check_tpw;
     // bits 8.. of exchange_flags: number of exchange-cell replicas (0 = default)
     {

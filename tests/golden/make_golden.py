@@ -305,6 +305,24 @@ def xl_cases():
         print(tag, xl[tag + "_fp64"]["iter"], xl[tag + "_fp32hybrid"]["iter"], xl[tag + "_fp32hybrid"]["status"],
               round(time.time() - t0, 1), flush=True)
         del m
+    # the 32 MPC columns of golden_mpc.npz once more, through the reference's fp32-hybrid loop (what the batched fp32
+    # engine is pinned to: status and iteration count per column, x for the distance-to-optimum comparison)
+    spec = importlib.util.spec_from_file_location("b200_mpc", os.path.join(REPO, "reluqp-py_b200", "reluqp", "mpc.py"))
+    mpc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mpc)
+    plant = mpc.RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+    X0 = np.load(os.path.join(HERE, "golden_mpc.npz"))["X0"]
+    L, U = plant.bounds(X0)
+    m = cast_model_fp32(ref_model(plant.H, plant.g, plant.A, L[0], U[0], warm_starting=False))
+    m.clear_primal_dual()
+    its = []
+    for j in range(X0.shape[0]):
+        m.update(l=L[j].astype(np.float32), u=U[j].astype(np.float32))
+        m.QP.l, m.QP.u = m.QP.l.to(torch.float32), m.QP.u.to(torch.float32)
+        r = run(m)
+        put(XL, xl, "mpc32_col{}".format(j), r, settings=dict(precision="float32"))
+        its.append(r["iter"])
+    print("mpc fp32-hybrid iters", its, flush=True)
     # x, z, lam in float32 are enough for the 1e-4 / 1e-6 comparisons?  No: fp64 cases are compared at 1e-6
     # relative, keep doubles (10 problems x 3 vectors x <= 8000 doubles: < 1 MB compressed)
     np.savez_compressed(os.path.join(HERE, "golden_xl.npz"), **{k: v.astype(np.float64) for k, v in XL.items()})

@@ -225,7 +225,7 @@ def test_mpc_single(golden):
     X0 = plant.sample_x0(32)
     L, U = plant.bounds(X0)
     m = gpu_model((plant.H, plant.g, plant.A, L[0], U[0]), warm_starting=False)
-    for j in range(8):
+    for j in range(32):                     # all 32 golden columns (round 1 checked 8)
         m.update(l=L[j], u=U[j])
         res = m.solve()
         gold = golden.case("mpc", "mpc_col{}".format(j))

@@ -209,3 +209,16 @@ def test_structured_iteration_is_the_dense_layer():
             vs = O.structured_iterations(*prob, rho=s.rho_list[ri], n_iter=12, v0=v0)
             # rho = 62.5 (R = 6.25e4 on equality rows): the assembled W_rho itself carries ~1e-9 of cancellation error
             assert rel_err(vs.numpy(), v.numpy()) < (1e-10 if ri <= 7 else 1e-5), ri
+
+
+def test_mpc_fp32_hybrid_columns(golden):
+    """golden_xl.npz mpc32_col*: the 32 golden MPC columns through the REAL reference's fp32-hybrid loop (fp64 setup,
+    fp32 iterate).  The oracle reproduces iteration count and status of every column; this is what the batched fp32
+    engine (tcgen05 3xTF32) is pinned to on the GPU."""
+    plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
+    L, U = plant.bounds(golden.arrays("mpc")["X0"])
+    res = O.solve_batch(plant.H, plant.g, plant.A, L, U, precision=torch.float32, setup_precision=torch.float64)
+    for j, r in enumerate(res):
+        g = golden.case("xl", "mpc32_col{}".format(j))
+        assert (r.iter, r.status) == (g["iter"], g["status"]), j
+        assert rel_err(r.x.double().numpy(), g["x"]) < 1e-5

@@ -143,6 +143,13 @@ def _measure(m, args, rank, world, dev, B_local, B_total, steps, warmup, flush, 
                 launches=n_launches, Ld=Ld, Ud=Ud)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE full-window launch from an `ncu --set full` capture, keyed by
+# (B, element bytes, engine, reduced iteration?) -> (bytes, file under profiles/)
+TRAFFIC = {
+    (4096, 4, 0, False): (500.15e6 + 687.35e6, "profiles/r02_batched_window_ncu_full.csv"),
+}
+
+
 def run_batched(args, rank, world, dev):
     from bench import ClockSampler, measured_peaks
     from reluqp import reluqpth
@@ -190,9 +197,11 @@ def run_batched(args, rank, world, dev):
     achieved = win_flops / win_s / 1e12 if win_s else whole
     # share of W_rho's k-blocks the engines actually visit (sparsity map of the layer matrices, starting rho)
     dense_frac = 1.0
-    km = getattr(m._batch, "kmask", None) if m._batch is not None else None
+    reduced = os.environ.get("RQP_BATCH_DENSE") is None      # what solve_batch ran (reluqp/_batch.py)
+    Dit = nx + nc if reduced else D                          # rows = K of the matrix an iteration multiplies by
+    km = m._batch._block_mask(reduced)[0] if m._batch is not None else None
     if km is not None:
-        kb = (D + 31) // 32
+        kb = (Dit + 31) // 32
         rows = km[m.rho_ind].cpu().numpy().astype(np.uint64)
         if len(rows) % 2:
             rows = np.concatenate([rows, np.zeros(1, dtype=np.uint64)])
@@ -211,6 +220,7 @@ def run_batched(args, rank, world, dev):
                        "microbenchmark tools/ubench/fp64_rate.cu)").format(dgemm)
         peak_note = "fp64 tensor (DMMA) peak: no fp64 figure in MEASURED_PEAKS.json, so measured here"
     mma_mult = 3.0 if dt == torch.float32 and args.batch_engine != 1 else 1.0
+    mma_mult *= (Dit * Dit) / float(D * D)         # reduced iteration: an (nx + nc)^2 product stands for the D^2 layer
     from bench_batched import batched_config
     line = dict(
         metric="qp_solves_per_sec", value=B * args.steps * world / weak["dev_s"], unit="solves/s",
@@ -218,12 +228,15 @@ def run_batched(args, rank, world, dev):
         higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32" if elem == 4 else "f64",
         data="synthetic", config=batched_config(args, world),
         engine={0: "auto (tcgen05 cta_group::1, 128x{128,64,32} tiles picked per check window, chunked accumulation of the x rows, PDL)", 1: "simt", 2: "tcgen05 cta_group::1"}.get(args.batch_engine, str(args.batch_engine)) if dt == torch.float32 else {0: "fp64 DMMA (mma.sync.m8n8k4.f64)", 1: "fp64 simt"}.get(args.batch_engine, "?"),
+        iteration_form=("reduced: [x+; A x+] = Wr [x; R z - lambda+] + br, (nx+nc)^2 = {}^2 product per column-iteration, "
+                        "z / lambda update in the GEMM epilogue".format(Dit)) if reduced else
+                       "dense layer v+ = clamp(W_rho v + b), D^2 = {}^2 product per column-iteration".format(D),
         iters_per_solve=weak["iters_mean"], iters_max=weak["iters_max"], sweeps=weak["sweeps"],
         all_solved=weak["all_solved"],
         roofline=dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
                       # dram__bytes_read.sum + dram__bytes_write.sum of one window launch, ncu --set full
-                      traffic=(500.15e6 + 687.35e6) if (B == 4096 and dt == torch.float32 and args.batch_engine == 0) else None,
-                      traffic_source="profiles/r02_batched_window_ncu_full.csv" if (B == 4096 and dt == torch.float32 and args.batch_engine == 0) else None,
+                      traffic=TRAFFIC.get((B, elem, args.batch_engine, reduced), (None, None))[0],
+                      traffic_source=TRAFFIC.get((B, elem, args.batch_engine, reduced), (None, None))[1],
                       peak_source=peak_source,
                       kernel="one full check window ({} iterations x {} columns) of the iteration GEMM".format(ci, B),
                       launch_ms=1e3 * win_s if win_s else None, flops_per_launch=win_flops,
@@ -232,7 +245,8 @@ def run_batched(args, rank, world, dev):
                       whole_solve=whole, whole_solve_frac=whole / peak,
                       note=peak_note + "; achieved = ALGORITHMIC flops 2*D^2 per column-iteration of one full check "
                       "window / its launch duration (CUDA events on the launching stream, measured live); executed = "
-                      "what the tensor pipe runs (3 TF32 MMAs per product, all-zero k-blocks of W_rho skipped); "
+                      "what the tensor pipe runs (3 TF32 MMAs per product, all-zero k-blocks skipped, the reduced "
+                      "iteration's (nx+nc)^2 product in place of the layer's D^2); "
                       "whole_solve = algorithmic flops of every column-iteration / time of WHOLE solves (checks, "
                       "regroups and the straggler tail included)"),
         e2e=dict(value=B * args.steps * world / weak["e2e_s"], unit="solves/s",

@@ -259,6 +259,23 @@ typedef struct rqp_batch {
      * launch(es) of the FIRST check window (every column still active), taken with CUDA events on the
      * caller's stream -- the per-launch duration of the dominant kernel for roofline reporting. */
     float* first_window_ms;
+    /* Reduced iteration (1 = on).  The layer's lambda rows are [R A, -R, I] and its x and z rows are
+     * products with K_rho (reluqpth.py:71-77), so the iteration can be carried on the reduced state s = [x; w],
+     * w = R z - lambda+ (lambda+ = lambda + R (A x - z)):
+     *     [x+; t+] = Wr_rho s + br_rho,   Wr_rho = [M_rho; A M_rho],  M_rho = [sigma K_rho | K_rho A'],
+     *     z+ = clamp(t+ + Rinv lambda+, l, u);  lambda++ = lambda+ + R (t+ - z+);  w+ = R z+ - lambda++
+     * -- one (nx + nc)^2 GEMM per iteration instead of (nx + 2 nc)^2, the z / lambda updates fused into its epilogue;
+     * the plain state [x; z; lambda] is materialised at every check (same checks, same results layout).
+     * Wr [n_rho][nx + nc][ldw] (prob->ldw, columns >= nx + nc ZERO), br [n_rho][nx + nc], Bred [n_rho][nx + nc][nx]
+     * (= [-K; -A K], only with G), Rv / Rinv [n_rho][nc] (rho_vec of reluqpth.py:53-54 and its reciprocal).  With
+     * reduced != 0 the TF32 planes W_hi / W_lo hold the n_rho * (nx + nc) rows of Wr (+ the residual operator
+     * rows over the plane layout [x; w; lambda]) and kmask describes Wr.  prob->W is then not read. */
+    int32_t reduced;
+    const void* Wr;
+    const void* br;
+    const void* Bred;
+    const void* Rv;
+    const void* Rinv;
 } rqp_batch;
 
 int rqp_batch_workspace_size(const rqp_problem* prob, const rqp_settings* stng, int32_t B,

@@ -80,7 +80,30 @@ struct BatchCtx {
     int nx, nc, D, n_rho, ldv, cap, B;
     long long ldw;
     double thr_p, thr_d, eps_rel, rho_min, rho_max, tol;
+    // reduced iteration (rqp_batch.reduced): the GEMM operand is s = [x; w] (kept in Vh / Vl, layout [x; w; lambda]);
+    // V holds the plain state [x; z; lambda] at window boundaries only; lamp = lambda+ of every slot
+    int reduced, Dit;   // Dit = rows of the iteration matrix: D, or nx + nc when reduced
+    const T* Rv;        // [n_rho][nc]
+    const T* Rinv;      // [n_rho][nc]
+    T* lamp;            // [cap][nc]
 };
+
+// operand form of a state entry: the value itself (fp64 / SIMT engines) or its two TF32 planes (tcgen05 engine)
+template <typename T>
+__device__ __forceinline__ void put_operand(T* dh, T* dl, int i, T v, int tc) {
+    if constexpr (std::is_same<T, float>::value) {
+        if (tc) {
+            uint32_t r;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+            const float h = __uint_as_float(r);
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v - h));
+            dh[i] = h;
+            dl[i] = __uint_as_float(r);
+            return;
+        }
+    }
+    dh[i] = v;
+}
 
 // ------------------------------------------------------------------------------------------------
 // init: all columns start from v = 0 at their given rho index, one bucket per distinct index
@@ -160,7 +183,46 @@ __global__ void batch_scatter(BatchCtx<T> c, int vsrc, int src, int iter_now, in
         int slot = 0;
         if (lane == 0) slot = c.starts[k] + atomicAdd(c.cursor + k, 1);
         slot = __shfl_sync(0xffffffffu, slot, 0);
-        if (c.tc) {
+        if (c.reduced) {
+            // Window start of the reduced iteration: rebuild the operand s = [x; w] and lambda+ of the column from
+            // its plain state (x, z, lambda), A x of the check that has just run (Tres) and the column's (possibly
+            // NEW) rho:  lambda+ = lambda + R (A x - z),  w = R z - lambda+.  The lambda block of the operand
+            // buffer carries lambda for the residual products of a fall-through that follows directly.
+            T* dp = c.V[vsrc ^ 1] + size_t(slot) * c.ldv;
+            T* dh = c.Vh[vsrc ^ 1] + size_t(slot) * c.ldv;
+            T* dl = c.tc ? c.Vl[vsrc ^ 1] + size_t(slot) * c.ldv : nullptr;
+            T* la = c.lamp + size_t(slot) * c.nc;
+            if (!copy_state) {
+                for (int i = lane; i < c.ldv; i += 32) {
+                    dp[i] = T(0);
+                    dh[i] = T(0);
+                    if (dl) dl[i] = T(0);
+                }
+                for (int i = lane; i < c.nc; i += 32) la[i] = T(0);
+            } else {
+                const T* ax = c.Tres + size_t(j) * (c.nc + 2 * c.nx);
+                const T* Rk = c.Rv + size_t(k) * c.nc;
+                for (int i = lane; i < c.nx; i += 32) {
+                    const T x = vrow[i];
+                    dp[i] = x;
+                    put_operand(dh, dl, i, x, c.tc);
+                }
+                for (int i = lane; i < c.nc; i += 32) {
+                    const T z = vrow[c.nx + i], lam = vrow[c.nx + c.nc + i], R = __ldg(Rk + i);
+                    const T lp = fma(R, ax[i] - z, lam);
+                    dp[c.nx + i] = z;
+                    dp[c.nx + c.nc + i] = lam;
+                    put_operand(dh, dl, c.nx + i, T(fma(R, z, -lp)), c.tc);
+                    put_operand(dh, dl, c.nx + c.nc + i, lam, c.tc);
+                    la[i] = lp;
+                }
+                for (int i = c.D + lane; i < c.ldv; i += 32) {
+                    dp[i] = T(0);
+                    dh[i] = T(0);
+                    if (dl) dl[i] = T(0);
+                }
+            }
+        } else if (c.tc) {
             const T* sh = c.Vh[vsrc] + size_t(j) * c.ldv;
             const T* sl = c.Vl[vsrc] + size_t(j) * c.ldv;
             T* dh = c.Vh[vsrc ^ 1] + size_t(slot) * c.ldv;
@@ -187,9 +249,9 @@ __global__ void batch_scatter(BatchCtx<T> c, int vsrc, int src, int iter_now, in
         if (c.G != nullptr) {
             // b_j = B_rho g_j for the column's (possibly new) rho (reluqpth.py:166-169)
             const T* gj = c.G + size_t(o) * c.nx;
-            const T* Bk = c.Bmat + size_t(k) * c.D * c.nx;
-            T* brow = c.Bias[dst] + size_t(slot) * c.D;
-            for (int m = 0; m < c.D; ++m) {
+            const T* Bk = c.Bmat + size_t(k) * c.Dit * c.nx;      // reduced: Bred = [-K; -A K]
+            T* brow = c.Bias[dst] + size_t(slot) * c.Dit;
+            for (int m = 0; m < c.Dit; ++m) {
                 T s = T(0);
                 for (int i = lane; i < c.nx; i += 32) s = fma(__ldg(Bk + size_t(m) * c.nx + i), __ldg(gj + i), s);
                 s = warp_sum(s);
@@ -242,7 +304,55 @@ struct GemmArgs {
     // EPI_ITER, DMMA engine: sparsity map of the layer matrices (rqp_batch.kmask) or null
     const unsigned long long* kmask;
     int n_rt64;
+    // EPI_ITER, reduced iteration (D = nx + nc rows: x rows, then t = A x+ rows): see epi_iter_store
+    int reduced;
+    const T* Rv;
+    const T* Rinv;
+    T* lamp;               // [cap][nc]
+    T* plain;              // [cap][ldp] plain state [x; z; lambda], written by the last iteration of a window, or null
+    int ldp;
 };
+
+// Epilogue of one output element of an iteration GEMM: acc = (Mat_rho X)[m] for slot n (original column o).
+// Dense layer: + b, clamp of the z rows (reluqpth.py:84-89).  Reduced iteration: rows < nx are x+ = acc + b_x;
+// rows >= nx are t+ = A x+, from which the element's owner advances z, lambda+ and w in place:
+//   z+ = clamp(t+ + lambda+ / R, l, u);  lambda++ = lambda+ + R (t+ - z+);  w+ = R z+ - lambda++
+// (lambda+ is the lambda of the iterate being produced).
+template <typename T>
+__device__ __forceinline__ void epi_iter_store(const GemmArgs<T>& a, int n, int o, int m, int rho_i, T y) {
+    y += a.bias_cols ? a.bias_cols[size_t(n) * a.D + m] : __ldg(a.b_all + size_t(rho_i) * a.D + m);
+    if (!a.reduced) {
+        if (m >= a.nx && m < a.nx + a.nc) {
+            const T lo = __ldg(a.L + size_t(o) * a.nc + (m - a.nx));
+            const T hi = __ldg(a.U + size_t(o) * a.nc + (m - a.nx));
+            y = clamp_keep_nan(y, lo, hi);
+        }
+        a.out[size_t(n) * a.ldo + a.mo + m] = y;
+        return;
+    }
+    T* out = a.out + size_t(n) * a.ldo;
+    T* pl = a.plain ? a.plain + size_t(n) * a.ldp : nullptr;
+    if (m < a.nx) {
+        out[m] = y;
+        if (pl) pl[m] = y;
+        return;
+    }
+    const int i = m - a.nx;
+    const T R = __ldg(a.Rv + size_t(rho_i) * a.nc + i), Ri = __ldg(a.Rinv + size_t(rho_i) * a.nc + i);
+    T* la = a.lamp + size_t(n) * a.nc + i;
+    const T lp = *la;
+    const T lo = __ldg(a.L + size_t(o) * a.nc + i);
+    const T hi = __ldg(a.U + size_t(o) * a.nc + i);
+    // explicit fma: the same roundings as the tcgen05 epilogue (rqp_batched_tc.cu) and the regroup pass
+    const T z = clamp_keep_nan(T(fma(lp, Ri, y)), lo, hi);
+    const T lpn = fma(R, y - z, lp);
+    out[m] = fma(R, z, -lpn);
+    *la = lpn;
+    if (pl) {
+        pl[m] = z;
+        pl[m + a.nc] = lp;
+    }
+}
 
 template <typename T, int EPI>
 __global__ void __launch_bounds__(256, 1) bgemm_simt(GemmArgs<T> a) {
@@ -324,16 +434,9 @@ __global__ void __launch_bounds__(256, 1) bgemm_simt(GemmArgs<T> a) {
             for (int e = 0; e < 2; ++e) {
                 const int m = m0 + 32 * j + 2 * tx + e;
                 if (m >= a.M) continue;
-                T y = acc[i][2 * j + e];
-                if (EPI == EPI_ITER) {
-                    y += a.bias_cols ? a.bias_cols[size_t(n) * a.D + m] : __ldg(a.b_all + size_t(rho_i) * a.D + m);
-                    if (m >= a.nx && m < a.nx + a.nc) {
-                        const T lo = __ldg(a.L + size_t(o) * a.nc + (m - a.nx));
-                        const T hi = __ldg(a.U + size_t(o) * a.nc + (m - a.nx));
-                        y = clamp_keep_nan(y, lo, hi);
-                    }
-                }
-                a.out[size_t(n) * a.ldo + a.mo + m] = y;
+                const T y = acc[i][2 * j + e];
+                if (EPI == EPI_ITER) epi_iter_store(a, n, o, m, rho_i, y);
+                else a.out[size_t(n) * a.ldo + a.mo + m] = y;
             }
         }
     }
@@ -509,16 +612,9 @@ __global__ void __launch_bounds__(32 * WM * WN * KS, 1) bgemm_dmma(GemmArgs<doub
             for (int i = 0; i < 4; ++i) {
                 const int m = m0 + 32 * wm + 8 * i + fr;
                 if (m >= a.M) continue;
-                double y = acc[i][j][e];
-                if (EPI == EPI_ITER) {
-                    y += a.bias_cols ? a.bias_cols[size_t(n) * a.D + m] : __ldg(a.b_all + size_t(rho_i) * a.D + m);
-                    if (m >= a.nx && m < a.nx + a.nc) {
-                        const double lo = __ldg(a.L + size_t(o) * a.nc + (m - a.nx));
-                        const double hi = __ldg(a.U + size_t(o) * a.nc + (m - a.nx));
-                        y = clamp_keep_nan(y, lo, hi);
-                    }
-                }
-                a.out[size_t(n) * a.ldo + a.mo + m] = y;
+                const double y = acc[i][j][e];
+                if (EPI == EPI_ITER) epi_iter_store(a, n, o, m, rho_i, y);
+                else a.out[size_t(n) * a.ldo + a.mo + m] = y;
             }
         }
     }
@@ -620,16 +716,9 @@ __global__ void __launch_bounds__(256) bgemm_simt64(GemmArgs<T> a) {
         for (int i = 0; i < 4; ++i) {
             const int m = m0 + tx * 4 + i;
             if (m >= a.M) continue;
-            T y = acc[j][i];
-            if (EPI == EPI_ITER) {
-                y += a.bias_cols ? a.bias_cols[size_t(n) * a.D + m] : __ldg(a.b_all + size_t(rho_i) * a.D + m);
-                if (m >= a.nx && m < a.nx + a.nc) {
-                    const T lo = __ldg(a.L + size_t(o) * a.nc + (m - a.nx));
-                    const T hi = __ldg(a.U + size_t(o) * a.nc + (m - a.nx));
-                    y = clamp_keep_nan(y, lo, hi);
-                }
-            }
-            a.out[size_t(n) * a.ldo + a.mo + m] = y;
+            const T y = acc[j][i];
+            if (EPI == EPI_ITER) epi_iter_store(a, n, o, m, rho_i, y);
+            else a.out[size_t(n) * a.ldo + a.mo + m] = y;
         }
     }
 }
@@ -756,7 +845,7 @@ struct EventPair {
 struct BatchLayout {
     int cap, n_tiles;
     size_t off_V[2], off_Vh[2], off_Vl[2], off_Bias[2], off_orig[2], off_ri[2], off_rhoc[2], off_T, off_key, off_pri, off_dua,
-        off_counts, off_starts, off_cursor, off_tile, off_btab, off_done, off_kcnt, off_scratch, off_nact, total;
+        off_counts, off_starts, off_cursor, off_tile, off_btab, off_done, off_kcnt, off_scratch, off_nact, off_lamp, total;
 };
 
 static BatchLayout batch_layout(const rqp_problem* p, int B, int ldv, bool with_g) {
@@ -769,7 +858,8 @@ static BatchLayout batch_layout(const rqp_problem* p, int B, int ldv, bool with_
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
     for (int i = 0; i < 2; ++i) l.off_V[i] = take(size_t(l.cap) * ldv * es);
     const bool planes = p->dtype == RQP_F32;
-    for (int i = 0; i < 2; ++i) l.off_Vh[i] = take(planes ? size_t(l.cap) * ldv * es : 0);
+    // Vh: TF32 hi planes (fp32 tcgen05 engine) or the operand [x; w] of the reduced iteration (any dtype)
+    for (int i = 0; i < 2; ++i) l.off_Vh[i] = take(size_t(l.cap) * ldv * es);
     for (int i = 0; i < 2; ++i) l.off_Vl[i] = take(planes ? size_t(l.cap) * ldv * es : 0);
     for (int i = 0; i < 2; ++i) l.off_Bias[i] = take(with_g ? size_t(l.cap) * D * es : 0);
     for (int i = 0; i < 2; ++i) l.off_orig[i] = take(size_t(l.cap) * 4);
@@ -789,6 +879,7 @@ static BatchLayout batch_layout(const rqp_problem* p, int B, int ldv, bool with_
     l.off_kcnt = take(planes ? size_t(kMaxSplitItems) * 8 * 4 : 0);
     l.off_scratch = take(planes ? size_t(kMaxSplitItems) * 128 * 128 * 4 : 0);
     l.off_nact = take(4);
+    l.off_lamp = take(size_t(l.cap) * p->nc * es);       // reduced iteration: lambda+ per slot
     l.total = o;
     return l;
 }
@@ -828,6 +919,16 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     c.out_pri = static_cast<T*>(bt->pri_res); c.out_dua = static_cast<T*>(bt->dua_res);
     c.out_rho = static_cast<T*>(bt->rho_estimate);
     // GEMM engine
+    const bool reduced = bt->reduced != 0;
+    if (reduced && (!bt->Rv || !bt->Rinv || !bt->br || (with_g && !bt->Bred))) return RQP_ERR_BAD_ARG;
+    const int Dit = reduced ? nx + nc : D;      // rows (and K) of the iteration matrix
+    if (reduced) {
+        c.W = static_cast<const T*>(bt->Wr); c.b_all = static_cast<const T*>(bt->br);
+        c.Bmat = static_cast<const T*>(bt->Bred);
+    }
+    c.reduced = reduced ? 1 : 0; c.Dit = Dit;
+    c.Rv = static_cast<const T*>(bt->Rv); c.Rinv = static_cast<const T*>(bt->Rinv);
+    c.lamp = reinterpret_cast<T*>(w8 + lay.off_lamp);
     bool use_tc = false;
     if (std::is_same<T, float>::value) {
         const bool have_planes = bt->W_hi != nullptr && bt->W_lo != nullptr;
@@ -838,8 +939,9 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         return RQP_ERR_UNSUPPORTED;   // tcgen05 has no fp64 kind; fp64 keeps the SIMT engine
     }
     c.tc = use_tc ? 1 : 0;
+    if (reduced && !use_tc && !bt->Wr) return RQP_ERR_BAD_ARG;
     for (int i = 0; i < 2; ++i) {
-        c.Vh[i] = use_tc ? reinterpret_cast<T*>(w8 + lay.off_Vh[i]) : nullptr;
+        c.Vh[i] = (use_tc || reduced) ? reinterpret_cast<T*>(w8 + lay.off_Vh[i]) : nullptr;
         c.Vl[i] = use_tc ? reinterpret_cast<T*>(w8 + lay.off_Vl[i]) : nullptr;
         c.V[i] = reinterpret_cast<T*>(w8 + lay.off_V[i]);
         c.Bias[i] = with_g ? reinterpret_cast<T*>(w8 + lay.off_Bias[i]) : nullptr;
@@ -907,7 +1009,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     // 64 x 64 split-K tiles (a quarter of the latency per tile) while they fit in two waves of SMs,
     // 128 x 128 tiles (half the operand traffic per flop) above
     const int dmma_big = getenv("RQP_DMMA_BIG") ? atoi(getenv("RQP_DMMA_BIG"))
-                                                : 64 * (2 * sm_count / ((D + 63) / 64)) + 1;
+                                                : 64 * (2 * sm_count / ((Dit + 63) / 64)) + 1;
     // residual products A x, H x, A' lambda on the tensor path: the W planes carry the residual operator
     // after the n_rho layer matrices (rqp_batch.res_planes)
     const bool res_tc = use_tc && bt->res_planes != 0 && getenv("RQP_NO_RES_TC") == nullptr;
@@ -928,10 +1030,13 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     int tc_chunk = tc_chunk_env >= 0 ? tc_chunk_env : 2;
     bool tc_chunk_x = !tc_chunk_all_env;
     // tensor maps: W planes (128-row boxes) and the state planes with 128 / 64 / 32-row boxes
-    CUtensorMap map_wh, map_wl, map_xh[3][2], map_xl[3][2];
+    // (reduced iteration: the iteration launches read the operand planes through maps that END at nx + nc -- the
+    // lambda block behind it is written only at window boundaries and must read as zeros when the last k-block
+    // straddles it; the residual launches use the full-width maps)
+    CUtensorMap map_wh, map_wl, map_xh[3][2], map_xl[3][2], map_xh_it[3][2], map_xl_it[3][2];
     static const int kBoxRows[3] = {128, 64, 32};
     if (use_tc) {
-        const long long w_rows = (long long)prob->n_rho * D + (res_tc ? nc + 2 * nx : 0);
+        const long long w_rows = (long long)prob->n_rho * Dit + (res_tc ? nc + 2 * nx : 0);
         // The maps' inner extent is D, not the padded leading dimension: elements D..ld-1 of a row are padding
         // (never written in the state planes: stale memory there could be NaN, and 0 * NaN poisons a whole
         // column) and must read as TMA out-of-bounds zeros.
@@ -941,6 +1046,8 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
             for (int i = 0; i < 2 && rc0 == RQP_OK; ++i) {
                 rc0 = tc_make_map(&map_xh[b][i], c.Vh[i], cap, D, ldv, kBoxRows[b]);
                 if (rc0 == RQP_OK) rc0 = tc_make_map(&map_xl[b][i], c.Vl[i], cap, D, ldv, kBoxRows[b]);
+                if (rc0 == RQP_OK) rc0 = tc_make_map(&map_xh_it[b][i], c.Vh[i], cap, Dit, ldv, kBoxRows[b]);
+                if (rc0 == RQP_OK) rc0 = tc_make_map(&map_xl_it[b][i], c.Vl[i], cap, Dit, ldv, kBoxRows[b]);
             }
         if (rc0 != RQP_OK) return rc0;
     }
@@ -975,10 +1082,10 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         return 1;
     };
     // sparsity map of the layer matrices (rqp_batch.kmask): engines skip all-zero k-blocks
-    const unsigned long long* kmask = (D <= 2048 && getenv("RQP_NO_KMASK") == nullptr)
+    const unsigned long long* kmask = (Dit <= 2048 && getenv("RQP_NO_KMASK") == nullptr)
                                           ? static_cast<const unsigned long long*>(bt->kmask) : nullptr;
-    const int n_rt64 = (D + 63) / 64;
-    const int nk_iter = (kmask != nullptr && bt->kmask_min_blocks > 0) ? bt->kmask_min_blocks : (D + 31) / 32;
+    const int n_rt64 = (Dit + 63) / 64;
+    const int nk_iter = (kmask != nullptr && bt->kmask_min_blocks > 0) ? bt->kmask_min_blocks : (Dit + 31) / 32;
     // window mode: rotate the tile -> CTA assignment by `rot` CTAs per iteration (coprime with the grid, about
     // a quarter of it, odd so that a CTA's row tile changes too); see tc_first_item
     const bool tc_rotate = getenv("RQP_NO_ROTATE") == nullptr;
@@ -1008,16 +1115,19 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.Yh_alt = reinterpret_cast<float*>(c.Vh[src]); a.Yl_alt = reinterpret_cast<float*>(c.Vl[src]);
         const int last_dst = (steps & 1) ? (src ^ 1) : src;
         a.Yplain = write_plain ? reinterpret_cast<float*>(c.V[last_dst]) : nullptr;
-        a.D = D; a.nx = nx; a.nc = nc; a.ldv = ldv;
-        a.raw = 0; a.M = D; a.w_row0 = 0; a.chunk_kb = tc_chunk; a.chunk_rows = tc_chunk_x ? nx : 0;
-        a.k_blocks = (D + 31) / 32;
+        a.D = Dit; a.nx = nx; a.nc = nc; a.ldv = ldv;
+        a.raw = 0; a.M = Dit; a.w_row0 = 0; a.chunk_kb = tc_chunk; a.chunk_rows = tc_chunk_x ? nx : 0;
+        a.k_blocks = (Dit + 31) / 32;
+        a.reduced = reduced ? 1 : 0;
+        a.Rv = reinterpret_cast<const float*>(c.Rv); a.Rinv = reinterpret_cast<const float*>(c.Rinv);
+        a.lamp = reinterpret_cast<float*>(c.lamp);
         a.steps = steps; a.done = nullptr;
         a.kmask = kmask; a.n_rt64 = n_rt64; a.rot = 0; a.ticket = nullptr;
         a.dbg = static_cast<unsigned long long*>(bt->reserved_dbg);
         {
             // 1-CTA tiles of 128 rows x BN columns.  BN is the widest tile that still gives every active
             // column tile its own SM in one wave (engine 4 / 5 / 6 force 128 / 64 / 32).
-            a.n_row_tiles = (D + 127) / 128;
+            a.n_row_tiles = (Dit + 127) / 128;
             const int b = pick_bn(a.n_row_tiles, bt->engine);
             a.n_col_tiles = 0;
             int rc1 = set_ksplit(a, nact_host[3 - b] * a.n_row_tiles);
@@ -1034,26 +1144,29 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
                     else a.rot = pick_rot(grid);
                 }
             }
-            return tc_launch(map_wh, map_wl, map_xh[b][src], map_xl[b][src], map_xh[b][src ^ 1], map_xl[b][src ^ 1], a,
-                             kBoxRows[b], bound, pdl, sm_count, st);
+            return tc_launch(map_wh, map_wl, map_xh_it[b][src], map_xl_it[b][src], map_xh_it[b][src ^ 1],
+                             map_xl_it[b][src ^ 1], a, kBoxRows[b], bound, pdl, sm_count, st);
         }
     };
-    auto gemm_iter = [&](int src) {
+    // last: final iteration of a window (the reduced iteration then also writes the plain state)
+    auto gemm_iter = [&](int src, bool last) {
         GemmArgs<T> a;
-        a.mat = c.W; a.ldm = c.ldw; a.mat_stride = (long long)D * c.ldw;
-        a.X = c.V[src]; a.ldx = ldv; a.ko = 0;
-        a.out = c.V[src ^ 1]; a.ldo = ldv; a.mo = 0;
-        a.M = D; a.K = D; a.tile_rho = c.tile_rho;
+        a.mat = c.W; a.ldm = c.ldw; a.mat_stride = (long long)Dit * c.ldw;
+        a.X = reduced ? c.Vh[src] : c.V[src]; a.ldx = ldv; a.ko = 0;
+        a.out = reduced ? c.Vh[src ^ 1] : c.V[src ^ 1]; a.ldo = ldv; a.mo = 0;
+        a.M = Dit; a.K = Dit; a.tile_rho = c.tile_rho;
         a.b_all = c.b_all; a.bias_cols = with_g ? c.Bias[lcur] : nullptr;
-        a.L = c.L; a.U = c.U; a.orig = c.orig[lcur]; a.nx = nx; a.nc = nc; a.D = D;
+        a.L = c.L; a.U = c.U; a.orig = c.orig[lcur]; a.nx = nx; a.nc = nc; a.D = Dit;
         a.kmask = kmask; a.n_rt64 = n_rt64;
+        a.reduced = reduced ? 1 : 0; a.Rv = c.Rv; a.Rinv = c.Rinv; a.lamp = c.lamp;
+        a.plain = (reduced && last) ? c.V[src ^ 1] : nullptr; a.ldp = ldv;
         note_launch();
         if (use_dmma && nact_host[0] >= dmma_min && DmmaLaunch<T, EPI_ITER>::ok(a)) {
-            DmmaLaunch<T, EPI_ITER>::go(a, D, cap, nact_host[0] >= dmma_big, st);
+            DmmaLaunch<T, EPI_ITER>::go(a, Dit, cap, nact_host[0] >= dmma_big, st);
         } else if (nact_host[0] < 2048) {
-            bgemm_simt64<T, EPI_ITER><<<dim3((D + SM64 - 1) / SM64, cap / SM64), 256, 0, st>>>(a);
+            bgemm_simt64<T, EPI_ITER><<<dim3((Dit + SM64 - 1) / SM64, cap / SM64), 256, 0, st>>>(a);
         } else {
-            bgemm_simt<T, EPI_ITER><<<dim3((D + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
+            bgemm_simt<T, EPI_ITER><<<dim3((Dit + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
         }
     };
     auto gemm_res_tc = [&](int src) -> int {
@@ -1063,7 +1176,8 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.Yh = nullptr; a.Yl = nullptr;
         a.Yplain = reinterpret_cast<float*>(c.Tres);
         a.D = D; a.nx = nx; a.nc = nc; a.ldv = nc + 2 * nx;
-        a.raw = 1; a.M = nc + 2 * nx; a.w_row0 = prob->n_rho * D; a.chunk_kb = tc_chunk; a.chunk_rows = 0;
+        a.raw = 1; a.M = nc + 2 * nx; a.w_row0 = prob->n_rho * Dit; a.chunk_kb = tc_chunk; a.chunk_rows = 0;
+        a.reduced = 0; a.Rv = nullptr; a.Rinv = nullptr; a.lamp = nullptr;
         a.steps = 1; a.done = nullptr; a.Yh_alt = nullptr; a.Yl_alt = nullptr;
         a.kmask = nullptr; a.n_rt64 = n_rt64; a.rot = 0; a.ticket = nullptr;
         a.k_blocks = (D + 31) / 32;
@@ -1082,6 +1196,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.tile_rho = c.tile_rho; a.b_all = nullptr; a.bias_cols = nullptr; a.L = nullptr; a.U = nullptr;
         a.orig = c.orig[lcur]; a.nx = nx; a.nc = nc; a.D = D;
         a.kmask = nullptr; a.n_rt64 = n_rt64;
+        a.reduced = 0; a.Rv = nullptr; a.Rinv = nullptr; a.lamp = nullptr; a.plain = nullptr; a.ldp = 0;
         const bool small = nact_host[0] < 2048;
         auto one = [&](int Mrows) {
             note_launch();
@@ -1141,7 +1256,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
             RQP_CUDA_TRY(cudaEventCreate(&ev_w.b));
             RQP_CUDA_TRY(cudaEventRecord(ev_w.a, st));
         }
-        const int n_rt128 = (D + 127) / 128;
+        const int n_rt128 = (Dit + 127) / 128;
         const int tiles_w = use_tc ? nact_host[3 - pick_bn(n_rt128, bt->engine)] * n_rt128 : 0;
         const bool window_pays = use_tc && (tiles_w > sm_count || pick_ksplit(tiles_w, nk_iter) > 1);
         if (use_tc && steps > 1 && (tc_window == 2 || (tc_window == 1 && window_pays))) {
@@ -1157,7 +1272,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
                     rc = gemm_iter_tc(cur, 1, s == steps - 1, s > 0 && pdl_ok);
                     if (rc != RQP_OK) return rc;
                 } else {
-                    gemm_iter(cur);
+                    gemm_iter(cur, s == steps - 1);
                 }
                 cur ^= 1;
             }

@@ -180,18 +180,27 @@ struct EpiRow {
     float* pp;          // a.Yplain + m or null
     float bias_shared;
     bool m_ok, is_z;
+    // reduced iteration: rows >= nx are t+ = A x+ (is_z marks them); red = this thread owns such a row
+    bool red;
+    float R, Rinv;      // rho_vec entry of the row and its reciprocal
+    float* la;          // a.lamp + (m - nx): lambda+ of the row, one per slot (stride nc)
 };
 
+// RED: the reduced iteration (a.reduced != 0); columns then go in groups of 8 instead of 16 (the extra lambda+
+// values would otherwise push the 128-column kernel into spills).
+template <bool RED>
 __device__ __forceinline__ void tc_epilogue_chunk(const TcArgs& a, const EpiRow& e, const uint32_t (&r)[32], int n0,
                                                   int lane) {
+    constexpr int GW = RED ? 8 : 16;
     const int o_lane = __ldg(a.orig + n0 + lane);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        float lo[16], hi[16], bc[16];
-        int oj[16];
+    for (int h = 0; h < 32 / GW; ++h) {
+        float lo[GW], hi[GW], bc[GW], lp[GW];
+        int oj[GW];
+        float* la = e.la + size_t(n0 + h * GW) * a.nc;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            oj[j] = __shfl_sync(0xffffffffu, o_lane, h * 16 + j);
+        for (int j = 0; j < GW; ++j) {
+            oj[j] = __shfl_sync(0xffffffffu, o_lane, h * GW + j);
             const int oc = max(oj[j], 0) * a.nc;
             lo[j] = -CUDART_INF_F;
             hi[j] = CUDART_INF_F;
@@ -200,22 +209,38 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcArgs& a, const EpiRow&
                 hi[j] = __ldg(e.Uz + oc);
             }
             bc[j] = e.bias_shared;
-            if (e.bcol != nullptr && e.m_ok) bc[j] = __ldg(e.bcol + size_t(n0 + h * 16 + j) * a.D);
+            if (e.bcol != nullptr && e.m_ok) bc[j] = __ldg(e.bcol + size_t(n0 + h * GW + j) * a.D);
+            lp[j] = 0.f;
+            // lambda+ was written by whichever CTA ran this tile in the previous iteration: read it from L2
+            if (RED && e.red && oj[j] >= 0) lp[j] = __ldcg(la + size_t(j) * a.nc);
         }
-        const size_t col0 = size_t(n0 + h * 16) * a.ldv;
+        const size_t col0 = size_t(n0 + h * GW) * a.ldv;
         float* ph = e.ph + col0;
         float* pl = e.pl + col0;
         float* pp = e.pp ? e.pp + col0 : nullptr;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            float y = __uint_as_float(r[h * 16 + j]) + bc[j];
-            y = clamp_keep_nan(y, lo[j], hi[j]);
-            const float yh = tf32_rna(y);
-            const float yl = tf32_rna(y - yh);   // round (not truncate) the low plane: no one-sided bias
+        for (int j = 0; j < GW; ++j) {
+            const float t = __uint_as_float(r[h * GW + j]) + bc[j];
+            // dense layer: y = clamp(t) is the new state entry.  Reduced iteration, t rows: z+ = clamp(t+ +
+            // lambda+ / R), lambda++ = lambda+ + R (t+ - z+), and the operand entry is w+ = R z+ - lambda++
+            const float y = clamp_keep_nan((RED && e.red) ? fmaf(lp[j], e.Rinv, t) : t, lo[j], hi[j]);
+            const float lpn = fmaf(e.R, t - y, lp[j]);
+            const float v = (RED && e.red) ? fmaf(e.R, y, -lpn) : y;
+            const float yh = tf32_rna(v);
+            const float yl = tf32_rna(v - yh);   // round (not truncate) the low plane: no one-sided bias
             if (oj[j] >= 0 && e.m_ok) {
                 ph[0] = yh;
                 pl[0] = yl;
                 if (pp) pp[0] = y;
+                if (RED && e.red) {
+                    __stcg(la + size_t(j) * a.nc, lpn);
+                    if (pp) {                     // last iteration of the window: plain lambda and its planes
+                        const float lh = tf32_rna(lp[j]);
+                        pp[a.nc] = lp[j];
+                        ph[a.nc] = lh;
+                        pl[a.nc] = tf32_rna(lp[j] - lh);
+                    }
+                }
             }
             ph += a.ldv;
             pl += a.ldv;
@@ -237,6 +262,10 @@ __device__ __forceinline__ EpiRow make_epi_row(const TcArgs& a, int m, int rho, 
     e.pl = yl + mc;
     e.pp = yp ? yp + mc : nullptr;
     e.bias_shared = (e.m_ok && a.bias_cols == nullptr) ? __ldg(a.b_all + size_t(rho) * a.D + m) : 0.f;
+    e.red = a.reduced != 0 && e.is_z;
+    e.R = e.red ? __ldg(a.Rv + size_t(rho) * a.nc + mz) : 0.f;
+    e.Rinv = e.red ? __ldg(a.Rinv + size_t(rho) * a.nc + mz) : 0.f;
+    e.la = a.lamp + mz;
     return e;
 }
 
@@ -754,7 +783,8 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
             for (int c = 0; c < NCH; ++c) {
                 const int n0 = col0 + half * Cfg::COLS_PER_EPI_WARP + c * 32;
                 if (a.raw) tc_epilogue_raw(a, m, sum[c], n0, lane);
-                else tc_epilogue_chunk(a, e, sum[c], n0, lane);
+                else if (a.reduced) tc_epilogue_chunk<true>(a, e, sum[c], n0, lane);
+                else tc_epilogue_chunk<false>(a, e, sum[c], n0, lane);
             }
             if (a.done != nullptr) {
                 // this warp's share of the tile is written: make it visible GPU-wide (to TMA readers too),

@@ -35,6 +35,12 @@ struct TcArgs {
     unsigned int* ticket;   // window mode with more items than CTAs: global ticket counter (zeroed before the launch), else null
     int rot;                // window mode: rotation of the item -> CTA assignment per iteration (0 = fixed)
     unsigned long long* dbg;  // optional [16] cycle counters written by CTA 0 (diagnostics)
+    // reduced iteration (rqp_batch.reduced): D = nx + nc rows; rows >= nx are t+ = A x+, whose epilogue advances
+    // z, lambda+ (lamp, in place) and writes w+ = R z+ - lambda++ as the operand planes
+    int reduced;
+    const float* Rv;        // [n_rho][nc]
+    const float* Rinv;      // [n_rho][nc]
+    float* lamp;            // [cap][nc]
 };
 
 // 2-D fp32 row-major [rows][ld] tensor, box = 32 columns (128 B) x box_rows rows, SWIZZLE_128B, zero OOB fill

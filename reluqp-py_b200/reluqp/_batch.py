@@ -54,9 +54,10 @@ class BatchEngine(object):
         self.stng = _cabi.rqp_settings()
         self.ws = None
         self.ws_B = 0
-        self.W_hi = self.W_lo = None
-        self.kmask = None
-        self.kmask_min = 0
+        self._planes = {}        # reduced? -> (W_hi, W_lo)
+        self._kmasks = {}        # reduced? -> (mask, fewest blocks of a 128-row tile)
+        # the iteration is the reduced one (rqp_batch.reduced) unless RQP_BATCH_DENSE=1 (read at
+        # every solve) or solve(reduced=False)
         self._stage = {}         # name -> (pinned host tensor, device tensor) for host inputs, largest batch seen
         self._x_host = None
 
@@ -102,38 +103,46 @@ class BatchEngine(object):
         ent[2].record()
         return devbuf[:B]
 
-    def _block_mask(self):
-        """Sparsity map of the layer matrices for the GEMM engines (``rqp_batch.kmask``), computed once per
-        setup by ``layer_block_mask``; None when D has more than 64 column blocks or ``RQP_NO_KMASK`` is set."""
-        if self.kmask is None and os.environ.get("RQP_NO_KMASK") is None:
-            self.kmask, self.kmask_min = layer_block_mask(self.solver.layers.W_all)
-        return self.kmask
+    def _iter_matrices(self, reduced):
+        """The matrices an iteration multiplies by: the dense layer ``W_all [n_rho, D, ldw]`` or the reduced
+        ``Wr [n_rho, nx + nc, ldw]`` (``ReLU_Layer.reduced_matrices``)."""
+        return self.solver.layers.reduced_matrices()["Wr"] if reduced else self.solver.layers.W_all
 
-    def _tf32_planes(self):
+    def _block_mask(self, reduced=False):
+        """Sparsity map of the iteration matrices for the GEMM engines (``rqp_batch.kmask``), computed once per
+        setup by ``layer_block_mask``; None when there are more than 64 column blocks or ``RQP_NO_KMASK`` is set.
+        Returns ``(mask or None, fewest blocks of a 128-row tile)``."""
+        if os.environ.get("RQP_NO_KMASK") is not None:
+            return None, 0
+        if reduced not in self._kmasks:
+            self._kmasks[reduced] = layer_block_mask(self._iter_matrices(reduced))
+        return self._kmasks[reduced]
+
+    def _tf32_planes(self, reduced=False):
         """fp32 only: W ~= W_hi + W_lo with W_hi = rna_tf32(W) (nearest, ties away: add half an ulp of
         the 10-bit mantissa to the bit pattern, clear the low 13 bits) and W_lo = rna_tf32(W - W_hi)
         (W - W_hi is exact in fp32; rounding it keeps the hardware from truncating it one-sidedly).
         Operands of the tcgen05 3xTF32 engine; split once per setup.  After the n_rho * D rows of the
-        layer matrices come nc + 2 nx rows of the residual operator [A 0 0; H 0 0; 0 0 A'] of
-        ``compute_residuals`` (``reluqpth.py:309-311``), so the per-window checks use the same engine."""
-        if self.W_hi is None:
+        layer matrices (reduced: n_rho * (nx + nc) rows of Wr) come nc + 2 nx rows of the residual operator
+        [A 0 0; H 0 0; 0 0 A'] of ``compute_residuals`` (``reluqpth.py:309-311``) over the operand layout
+        [x; z or w; lambda], so the per-window checks use the same engine."""
+        if reduced not in self._planes:
             def rna(t):
                 return ((t.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
             sv = self.solver
             qp = sv.QP
             nx, nc = qp.nx, qp.nc
-            W = sv.layers.W_all                      # [n_rho, D, ldw]
-            n_rho, D, ldw = W.shape
-            full = torch.zeros((n_rho * D + nc + 2 * nx, ldw), dtype=torch.float32, device=W.device)
-            full[:n_rho * D] = W.reshape(n_rho * D, ldw)
-            r0 = n_rho * D
+            W = self._iter_matrices(reduced)         # [n_rho, D or nx + nc, ldw]
+            n_rho, Dit, ldw = W.shape
+            full = torch.zeros((n_rho * Dit + nc + 2 * nx, ldw), dtype=torch.float32, device=W.device)
+            full[:n_rho * Dit] = W.reshape(n_rho * Dit, ldw)
+            r0 = n_rho * Dit
             full[r0:r0 + nc, :nx] = qp.A
             full[r0 + nc:r0 + nc + nx, :nx] = qp.H
             full[r0 + nc + nx:, nx + nc:nx + 2 * nc] = qp.A.t()
             hi = rna(full)
-            self.W_hi = hi.contiguous()
-            self.W_lo = rna((full - hi).contiguous()).contiguous()
-        return self.W_hi, self.W_lo
+            self._planes[reduced] = (hi.contiguous(), rna((full - hi).contiguous()).contiguous())
+        return self._planes[reduced]
 
     def _settings(self):
         st, s = self.solver.settings, self.stng
@@ -160,8 +169,11 @@ class BatchEngine(object):
             self.ws.fill_(int(poison))
         return self.ws
 
-    def solve(self, l, u, g=None, engine=0, x_out=None):
-        """engine: 0 auto (fp32 -> tcgen05 3xTF32 with chunked accumulation, fp64 -> DMMA tensor-core tiles;
+    def solve(self, l, u, g=None, engine=0, x_out=None, reduced=None):
+        """reduced: iterate on the reduced state [x; R z - lambda+] (``ReLU_Layer.reduced_matrices``: an
+        (nx + nc)^2 product per iteration instead of (nx + 2 nc)^2, same iterates up to rounding); None = yes
+        unless RQP_BATCH_DENSE=1.
+        engine: 0 auto (fp32 -> tcgen05 3xTF32 with chunked accumulation, fp64 -> DMMA tensor-core tiles;
         few columns -> the single-QP kernel per column), 1 SIMT tiles, 2 tcgen05 (fp32), 4 / 5 / 6 tcgen05
         with 128 / 64 / 32-column tiles.  ``x_out``: optional pinned host array / tensor ``[B, nx]`` that
         receives the primal solutions (one asynchronous device -> host copy, waited for before returning)."""
@@ -203,13 +215,25 @@ class BatchEngine(object):
                              rho_ind=rho_ind.data_ptr(), iter=it.data_ptr(), status=status.data_ptr(),
                              pri_res=pri.data_ptr(), dua_res=dua.data_ptr(), rho_estimate=rho.data_ptr(),
                              engine=int(engine))
+        reduced = (os.environ.get("RQP_BATCH_DENSE") is None) if reduced is None else bool(reduced)
+        if reduced:
+            red = sv.layers.reduced_matrices()
+            br = red["br"]
+            if getattr(sv, "_g_updated", False):       # update(g=...) since setup: b from the live g, setup dtype
+                bs = red["Bred_setup"]
+                br = torch.matmul(bs, qp.g.to(bs.dtype)).to(dt).contiguous()
+            self._keep_red = br
+            bt.reduced = 1
+            bt.Wr, bt.br, bt.Rv, bt.Rinv = red["Wr"].data_ptr(), br.data_ptr(), red["R"].data_ptr(), red["Rinv"].data_ptr()
+            if G is not None:
+                bt.Bred = red["Bred"].data_ptr()
         if dt == torch.float32 and engine != 1:
-            wh, wl = self._tf32_planes()
+            wh, wl = self._tf32_planes(reduced)
             bt.W_hi, bt.W_lo = wh.data_ptr(), wl.data_ptr()
             bt.res_planes = 1
-        km = self._block_mask()
+        km, km_min = self._block_mask(reduced)
         if km is not None:
-            bt.kmask, bt.kmask_min_blocks = km.data_ptr(), self.kmask_min
+            bt.kmask, bt.kmask_min_blocks = km.data_ptr(), km_min
         win_ms = C.c_float(0.0)
         if getattr(self, "time_first_window", False):     # bench: per-launch time of the dominant kernel
             bt.first_window_ms = C.pointer(win_ms)

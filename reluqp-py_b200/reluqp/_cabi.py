@@ -76,7 +76,9 @@ class rqp_batch(C.Structure):
                 ("pri_res", C.c_void_p), ("dua_res", C.c_void_p), ("rho_estimate", C.c_void_p),
                 ("engine", C.c_int32), ("res_planes", C.c_int32), ("W_hi", C.c_void_p), ("W_lo", C.c_void_p),
                 ("reserved_dbg", C.c_void_p), ("kmask", C.c_void_p), ("kmask_min_blocks", C.c_int32),
-                ("first_window_ms", C.POINTER(C.c_float))]
+                ("first_window_ms", C.POINTER(C.c_float)),
+                ("reduced", C.c_int32), ("Wr", C.c_void_p), ("br", C.c_void_p), ("Bred", C.c_void_p),
+                ("Rv", C.c_void_p), ("Rinv", C.c_void_p)]
 
 
 _lib = None

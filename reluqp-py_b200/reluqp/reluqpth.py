@@ -154,6 +154,8 @@ class ReLU_Layer(object):
         rvec_all = rho64[:, None].repeat(1, nc)
         rvec_all[:, eq] = (rho64 * 1e3)[:, None]
         rvec_all = rvec_all.to(sdt)
+        # kept for the reduced matrices of the batched path (formed on first use, reduced_matrices())
+        self._rvec_all, self._red_src, self._reduced = rvec_all, (H, A, q.g.clone()), None
         per_rho = 8 * (3 * nx * nx + 3 * nx * nc + nc * nc) * H.element_size() // 8
         chunk = max(1, min(n, int((2 << 30) // max(1, per_rho))))
         for c0 in range(0, n, chunk):
@@ -194,6 +196,47 @@ class ReLU_Layer(object):
             self.M_ks = {i: self.M_all[i, :, :nx + nc] for i in range(n)}
             self.R_ks = {i: self.R_all[i] for i in range(n)}
         return W_all, B_all, b_all
+
+    def reduced_matrices(self):
+        """Matrices of the REDUCED iteration the batched engines run (``rqp_batch.reduced``).  The
+        lambda rows of W_rho are ``[R A, -R, I]`` and its x / z rows are products with K (``reluqpth.py:71-77``), so
+        with ``w = R z - lam+`` (``lam+ = lam + R (A x - z)``) one layer application is
+        ``[x+; A x+] = Wr [x; w] + br`` with ``Wr = [M; A M]``, ``M = [sigma K | K A']``, ``br = [-K g; -A K g]``,
+        followed by the elementwise ``z+ = clamp(A x+ + lam+ / R, l, u)``: an ``(nx + nc)^2`` product instead of
+        ``(nx + 2 nc)^2``.  Formed once, on first use, in the setup dtype with the same batched-over-rho recipe as
+        ``setup_matrices`` and rounded to the solver dtype.  Returns a dict: ``Wr [n_rho, nx + nc, ldw]`` (ldw as
+        W_all's, columns >= nx + nc zero), ``Bred [n_rho, nx + nc, nx]`` in the solver dtype and in the setup dtype
+        (``Bred_setup``), ``br [n_rho, nx + nc]``, ``R``, ``Rinv [n_rho, nc]``."""
+        if self._reduced is not None:
+            return self._reduced
+        st = self.settings
+        H, A, g = self._red_src
+        sdt, dev = H.dtype, H.device
+        nc, nx = A.shape
+        D, Dr = nx + 2 * nc, nx + nc
+        ldw = _round_up(D, 4)
+        n = len(self.rho_list)
+        rvec_all = self._rvec_all
+        Wr = torch.zeros((n, Dr, ldw), device=dev, dtype=st.precision)
+        Bred = torch.zeros((n, Dr, nx), device=dev, dtype=sdt)
+        Ix = torch.eye(nx, device=dev, dtype=sdt)
+        At = A.T
+        per_rho = (3 * nx * nx + 4 * nx * nc + nc * nc) * H.element_size()
+        chunk = max(1, min(n, int((2 << 30) // max(1, per_rho))))
+        for c0 in range(0, n, chunk):
+            rvec = rvec_all[c0:c0 + chunk]
+            m = rvec.shape[0]
+            K = torch.linalg.inv(H + st.sigma * Ix + At @ (rvec[:, :, None] * A))
+            M = torch.cat([st.sigma * K, K @ At], dim=2)         # [m, nx, nx + nc]
+            Wr[c0:c0 + m, :nx, :Dr] = M
+            Wr[c0:c0 + m, nx:, :Dr] = A @ M
+            Bred[c0:c0 + m, :nx] = -K
+            Bred[c0:c0 + m, nx:] = -(A @ K)
+        self._reduced = dict(Wr=Wr, Bred_setup=Bred, Bred=Bred.to(st.precision).contiguous(),
+                             br=torch.matmul(Bred, g).to(st.precision).contiguous(),
+                             R=rvec_all.to(st.precision).contiguous(),
+                             Rinv=(1.0 / rvec_all).to(st.precision).contiguous())
+        return self._reduced
 
     def forward(self, input, idx):
         """One ADMM iteration ``v <- clamp(W_idx v + b_idx)`` (``reluqpth.py:80-89``) on the
@@ -460,6 +503,7 @@ class ReLU_QP(object):
         self._tuning = launch_tuning
         self._engine = None
         self._batch = None
+        self._g_updated = False
         self.layers._engine = None
         self._timer = timer
         self.clear_primal_dual()
@@ -544,6 +588,7 @@ class ReLU_QP(object):
                 self._push(lo, hi)
         if g is not None:
             L = self.layers
+            self._g_updated = True          # the batched path re-forms its reduced bias from the live g
             if self._engine is not None:
                 with torch.cuda.device(st.device):
                     rc = self._engine.lib.rqp_update_bias(
@@ -797,14 +842,14 @@ class ReLU_QP(object):
             self._batch = BatchEngine(self)
         return self._batch
 
-    def solve_batch(self, l, u, g=None, engine=0, x_out=None):
+    def solve_batch(self, l, u, g=None, engine=0, x_out=None, reduced=None):
         """Solve B QPs that share this solver's H, A (hence every W_rho) and differ in l, u
         (``[B, nc]``) and optionally g (``[B, nx]``).  Column j is defined as what the reference
         would return for ``update(l=l[j], u=u[j][, g=g[j]])`` followed by a cold ``solve()``.
         Host arrays travel with one asynchronous copy each (directly from the caller's memory when it is
         pinned, see ``pinned_batch_arrays``); ``x_out`` (pinned host ``[B, nx]``) receives x.
         Returns a ``BatchResults``; the single-QP state (``output``, ``rho_ind``, ``QP.l/u``) is not touched."""
-        return self._batch_engine().solve(l, u, g, engine=engine, x_out=x_out)
+        return self._batch_engine().solve(l, u, g, engine=engine, x_out=x_out, reduced=reduced)
 
     def pinned_batch_arrays(self, B, with_g=False):
         """``(l, u[, g], x_out)`` as pinned host numpy arrays of the right shapes and dtype for ``solve_batch``."""

@@ -13,6 +13,18 @@ from reluqp.mpc import RandomLinMPC
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["reduced", "dense"])
+def iteration_form(request, monkeypatch):
+    """Every test of this module runs twice: on the reduced iteration (state [x; R z - lambda+], an
+    (nx + nc)^2 product per iteration: the default) and on the dense layer v <- clamp(W_rho v + b)
+    (RQP_BATCH_DENSE=1).  Both must reproduce the reference column by column."""
+    if request.param == "dense":
+        monkeypatch.setenv("RQP_BATCH_DENSE", "1")
+    else:
+        monkeypatch.delenv("RQP_BATCH_DENSE", raising=False)
+    return request.param
+
+
 def gpu_model(prob, **kw):
     m = reluqpth.ReLU_QP()
     m.setup(*prob, device="cuda", warm_starting=False, **kw)
@@ -108,7 +120,9 @@ def test_small_batch_dispatch_matches_batched_engine():
     assert torch.equal(m.QP.l, l_before)    # the solver's own problem data is restored
     np.testing.assert_array_equal(ra.iter.cpu().numpy(), rb.iter.cpu().numpy())
     assert ra.status == rb.status == ["solved"] * 6
-    assert float((ra.x - rb.x).abs().max()) < 1e-9 and float((ra.lam - rb.lam).abs().max()) < 1e-8
+    # lambda carries the 1e3 * rho of the equality rows: the reduced form's different rounding path shows there
+    assert float((ra.x - rb.x).abs().max()) < 1e-9
+    assert float((ra.lam - rb.lam).abs().max()) < 1e-7 * float(rb.lam.abs().max())
     np.testing.assert_allclose(ra.pri_res.cpu().numpy(), rb.pri_res.cpu().numpy(), rtol=1e-4, atol=1e-10)
 
 
@@ -126,7 +140,14 @@ def test_batched_with_per_column_g():
     for j, r in enumerate(ref):
         assert int(res.iter[j]) == r.iter and res.status[j] == r.status, j
         assert rel_err(res.x[j].cpu().numpy(), r.x.numpy()) < 1e-6
-        assert int(res.rho_ind[j]) == r.rho_ind
+        if int(res.rho_ind[j]) != r.rho_ind:
+            # The index moves once more at the terminating check, on residuals that are rounding noise by then
+            # (dua ~ 1e-8 here): another summation order may land on the other side of a switching threshold.
+            # Accept that only when the oracle's own estimate sits within a factor 1.5 of that threshold.
+            rhos, tol = O.rho_set(O.OracleSettings(eps_abs=1e-6)), 5.0
+            near = min(abs(np.log(r.rho_estimate / (rhos[k] * f))) for k in (r.rho_ind, int(res.rho_ind[j]))
+                       for f in (tol, 1.0 / tol))
+            assert abs(int(res.rho_ind[j]) - r.rho_ind) == 1 and near < np.log(1.5), (j, r.rho_estimate)
 
 
 def test_batched_max_iter_and_adaptive_off():
@@ -218,7 +239,8 @@ def test_sparsity_map_and_ticket_scheduling_are_bit_identical(monkeypatch):
     instead of a static tile -> CTA assignment) and the 64-column tiles of the single-wave regime change WHO
     computes a tile and WHICH zero blocks it visits, never what is summed: results must be bit-identical to
     the dense, statically scheduled kernels in fp32 (tcgen05) and in fp64 (DMMA), fixed-iteration runs and
-    full solves alike."""
+    full solves alike.  (The zero blocks are a property of the dense layer matrices: pinned to that form.)"""
+    monkeypatch.setenv("RQP_BATCH_DENSE", "1")
     monkeypatch.setenv("RQP_NO_KSPLIT", "1")     # split-K changes the summation order by design
     plant = RandomLinMPC(nx=12, nu=4, horizon=20, seed=0, u_max=0.05)
     L, U = plant.bounds(plant.sample_x0(2600))
@@ -244,8 +266,9 @@ def test_sparsity_map_and_ticket_scheduling_are_bit_identical(monkeypatch):
                 out[mode] = (torch.cat([a.x, a.z, a.lam], 1).clone(), b.iter.clone(),
                              torch.cat([b.x, b.z, b.lam], 1).clone(), b.pri_res.clone(), b.dua_res.clone())
                 if mode == "new":       # the map exists and some 128-row tile really has zero blocks to skip
-                    assert mf._batch.kmask is not None
-                    assert 0 < mf._batch.kmask_min < (plant.H.shape[0] + 2 * plant.A.shape[0] + 31) // 32
+                    km, km_min = mf._batch._block_mask(False)
+                    assert km is not None
+                    assert 0 < km_min < (plant.H.shape[0] + 2 * plant.A.shape[0] + 31) // 32
             for mode in ("rotated", "plain"):
                 for i in range(5):
                     assert torch.equal(out["new"][i], out[mode][i]), (prec, B, mode, i)
@@ -257,6 +280,7 @@ def test_sparsity_map_at_64_column_blocks(monkeypatch):
     live (the lambda rows' identity block sits in the last columns).  Fixed-iteration batched runs with and
     without the map must agree bit for bit in fp32 (tcgen05) and fp64 (DMMA), and the map must really skip
     blocks."""
+    monkeypatch.setenv("RQP_BATCH_DENSE", "1")
     monkeypatch.setenv("RQP_NO_KSPLIT", "1")
     nx, ne, ni = 1024, 256, 256                      # nc = 512, D = 2048
     H, g, A, l, u, _ = utils.rand_qp(nx, ne, ni, seed=11, compute_sol=False)
@@ -277,8 +301,9 @@ def test_sparsity_map_at_64_column_blocks(monkeypatch):
             assert r.sweeps >= 0
             out[mode] = torch.cat([r.x, r.z, r.lam], 1).clone()
             if mode == "map":
-                assert m._batch.kmask is not None and 0 < m._batch.kmask_min < 64
-                assert bool((m._batch.kmask < 0).any())          # bit 63 set somewhere (int64 sign bit)
+                km, km_min = m._batch._block_mask(False)
+                assert km is not None and 0 < km_min < 64
+                assert bool((km < 0).any())          # bit 63 set somewhere (int64 sign bit)
         assert torch.isfinite(out["map"]).all()
         assert torch.equal(out["map"], out["dense"]), prec
     monkeypatch.delenv("RQP_NO_KMASK", raising=False)

@@ -179,7 +179,7 @@ def test_cabi_exports_match_header():
     assert ctypes.sizeof(_cabi.rqp_settings) == 80
     assert ctypes.sizeof(_cabi.rqp_problem) == 96
     assert ctypes.sizeof(_cabi.rqp_state) == 32
-    assert ctypes.sizeof(_cabi.rqp_batch) == 152
+    assert ctypes.sizeof(_cabi.rqp_batch) == 200
     # bad arguments are reported, not crashed on (no GPU needed: checks come first)
     assert lib.rqp_update_bias(1, 0, 0, 0, None, None, None, None) == -1
     assert lib.rqp_query(0, None) == -1
@@ -217,3 +217,48 @@ def test_layer_block_mask_matches_brute_force():
                   for r in range(n_rho) for p in range((rt + 1) // 2)]
         assert fewest == min(per128)
     assert layer_block_mask(torch.zeros((1, 2080, 2080))) == (None, 0)
+
+
+def test_reduced_iteration_is_the_dense_layer():
+    """The reduced iteration of the batched engines (ReLU_Layer.reduced_matrices, rqp_batch.reduced):
+    [x+; A x+] = Wr [x; w] + br with w = R z - lam+, lam+ = lam + R (A x - z), then z+ = clamp(A x+ + lam+ / R)
+    must be the same map as the reference's dense layer v+ = clamp(W_rho v + b_rho) (reluqpth.py:71-89), for
+    every rho of the grid, from a random state, over several iterations -- including a restart from the plain
+    state (what a check window boundary does) in between."""
+    from reluqp import reluqpth, utils
+    H, g, A, l, u, _ = utils.rand_qp(12, 3, 4, seed=2, compute_sol=False)
+    m = reluqpth.ReLU_QP()
+    m.setup(H, g, A, l, u, device="cpu")
+    lay, qp = m.layers, m.QP
+    red = lay.reduced_matrices()
+    nx, nc = qp.nx, qp.nc
+    assert red["Wr"].shape[1] == nx + nc and float(red["Wr"][:, :, nx + nc:].abs().max()) == 0.0
+    rng = np.random.RandomState(0)
+    for ri in range(0, len(lay.rho_list), 3):
+        v = torch.tensor(rng.randn(nx + 2 * nc))
+        W, b = lay.W_ks[ri], lay.b_ks[ri]
+        Wr, br, R, Rinv = red["Wr"][ri, :, :nx + nc], red["br"][ri], red["R"][ri], red["Rinv"][ri]
+        x, z, lam = v[:nx].clone(), v[nx:nx + nc].clone(), v[nx + nc:].clone()
+
+        def start(x, z, lam):
+            lamp = lam + R * (qp.A @ x - z)
+            return lamp, R * z - lamp
+        lamp, w = start(x, z, lam)
+        for k in range(9):
+            v = W @ v + b
+            v[nx:nx + nc] = torch.clamp(v[nx:nx + nc], qp.l, qp.u)
+            y = Wr @ torch.cat([x, w]) + br
+            x, t = y[:nx], y[nx:]
+            lam = lamp
+            z = torch.clamp(t + lamp * Rinv, qp.l, qp.u)
+            lamp = lamp + R * (t - z)
+            w = R * z - lamp
+            if k == 4:
+                lamp, w = start(x, z, lam)
+            # K = (H + sigma I + A'RA)^-1 has condition ~ max(R) / sigma: both forms carry rounding noise of that
+            # order relative to 1e-16, so the tolerance scales with the rho of the layer
+            scale = float(v[:nx + nc].abs().max())
+            assert float((torch.cat([x, z]) - v[:nx + nc]).abs().max()) < 1e-6 * scale, (ri, k)
+            # lambda+ = lambda + R (A x - z) multiplies that noise by R once more (1e3 * rho on equality rows)
+            tol = 1e-8 * scale * max(1.0, float(R.max()))
+            assert float((lam - v[nx + nc:]).abs().max()) < tol, (ri, k)

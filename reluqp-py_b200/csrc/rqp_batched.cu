@@ -876,7 +876,7 @@ static BatchLayout batch_layout(const rqp_problem* p, int B, int ldv, bool with_
     l.off_btab = take(64 * 4);
     l.off_done = take(size_t(l.cap / 32 + 2) * 4);      // window kernel: one completion counter per column tile
     // split-K of the tcgen05 kernels (fewer tiles than SMs): one work item per SM at most
-    l.off_kcnt = take(planes ? size_t(kMaxSplitItems) * 8 * 4 : 0);
+    l.off_kcnt = take(planes ? size_t(kMaxSplitItems) * 16 * 4 : 0);     // [tiles][epilogue warps <= 16]
     l.off_scratch = take(planes ? size_t(kMaxSplitItems) * 128 * 128 * 4 : 0);
     l.off_nact = take(4);
     l.off_lamp = take(size_t(l.cap) * p->nc * es);       // reduced iteration: lambda+ per slot
@@ -1102,7 +1102,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.ksplit = pick_ksplit(tiles, a.raw ? nk_raw : nk_iter);
         a.scratch = reinterpret_cast<float*>(w8 + lay.off_scratch);
         a.kcnt = reinterpret_cast<unsigned int*>(w8 + lay.off_kcnt);
-        if (a.ksplit > 1) RQP_CUDA_TRY(cudaMemsetAsync(a.kcnt, 0, size_t(kMaxSplitItems) * 8 * 4, st));
+        if (a.ksplit > 1) RQP_CUDA_TRY(cudaMemsetAsync(a.kcnt, 0, size_t(kMaxSplitItems) * 16 * 4, st));
         return RQP_OK;
     };
     auto gemm_iter_tc = [&](int src, int steps, bool write_plain, bool pdl) -> int {
@@ -1121,6 +1121,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.reduced = reduced ? 1 : 0;
         a.Rv = reinterpret_cast<const float*>(c.Rv); a.Rinv = reinterpret_cast<const float*>(c.Rinv);
         a.lamp = reinterpret_cast<float*>(c.lamp);
+        a.xflags = getenv("RQP_TC_XFLAGS") ? atoi(getenv("RQP_TC_XFLAGS")) : 0;
         a.steps = steps; a.done = nullptr;
         a.kmask = kmask; a.n_rt64 = n_rt64; a.rot = 0; a.ticket = nullptr;
         a.dbg = static_cast<unsigned long long*>(bt->reserved_dbg);
@@ -1177,7 +1178,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         a.Yplain = reinterpret_cast<float*>(c.Tres);
         a.D = D; a.nx = nx; a.nc = nc; a.ldv = nc + 2 * nx;
         a.raw = 1; a.M = nc + 2 * nx; a.w_row0 = prob->n_rho * Dit; a.chunk_kb = tc_chunk; a.chunk_rows = 0;
-        a.reduced = 0; a.Rv = nullptr; a.Rinv = nullptr; a.lamp = nullptr;
+        a.reduced = 0; a.Rv = nullptr; a.Rinv = nullptr; a.lamp = nullptr; a.xflags = 0;
         a.steps = 1; a.done = nullptr; a.Yh_alt = nullptr; a.Yl_alt = nullptr;
         a.kmask = nullptr; a.n_rt64 = n_rt64; a.rot = 0; a.ticket = nullptr;
         a.k_blocks = (D + 31) / 32;

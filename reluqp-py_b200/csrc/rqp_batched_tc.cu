@@ -23,6 +23,12 @@
 #include "rqp_host.h"
 #include "rqp_tc.h"
 
+#ifndef RQP_TC_STAGES128
+#define RQP_TC_STAGES128 0   // experiment switch: smem ring depth of the 128-column kernel (0 = default 3)
+#endif
+#ifndef RQP_TC_EXP
+#define RQP_TC_EXP 0          // timing experiments (WRONG results): 1 = no bound / lambda+ loads, 2 = no stores
+#endif
 #ifndef RQP_TC_KAHAN
 #define RQP_TC_KAHAN 0      // experiment switch (tools/kahan_variant.sh): compensated sum of the chunk partials
 #endif
@@ -34,7 +40,7 @@ constexpr int TC_BN = 128;       // columns per tile (UMMA N) of the full-size 1
 constexpr int TC_BK = 32;        // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                 // 16 KB per operand plane
 constexpr int TC_ACC_STAGES = 2;
-constexpr int TC_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+// threads per CTA = 64 + 32 * EPI_WARPS: warp 0 TMA, warp 1 MMA, warps 2.. epilogue (EPI_WARPS / 4 per TMEM lane quarter)
 
 // 1-CTA kernel, templated on the column-tile width BN.  Narrow tiles (64, 32 columns) are for check
 // windows with few active columns: the per-iteration latency of a tile is the time one SM needs to
@@ -44,9 +50,15 @@ template <int BN>
 struct TcCfg {
     static constexpr int X_TILE_BYTES = BN * TC_BK * 4;
     static constexpr int STAGE_BYTES = 2 * TC_TILE_BYTES + 2 * X_TILE_BYTES;
-    static constexpr int STAGES = BN == 128 ? 3 : (BN == 64 ? 4 : 5);
+    static constexpr int STAGES = RQP_TC_STAGES128 > 0 && BN == 128 ? RQP_TC_STAGES128 : (BN == 128 ? 3 : (BN == 64 ? 4 : 5));
     static constexpr int TMEM_COLS = TC_ACC_STAGES * BN;          // 256 / 128 / 64 (powers of two >= 32)
-    static constexpr int EPI_WARPS = BN >= 64 ? 8 : 4;
+    // Epilogue warps: every warp owns 32 TMEM lanes (state rows) x COLS_PER_EPI_WARP columns.  The epilogue is
+    // issue / latency bound (a few dozen instructions per element, in-kernel counters: 25-50 k cycles per
+    // 128 x 128 tile with 8 warps = two per scheduler, against ~16-20 k cycles of MMAs), so the full-width tile gets
+    // 16 warps of 32 columns each: four warps per scheduler hide each other's latencies.
+    static constexpr int EPI_WARPS = BN == 128 ? 16 : (BN == 64 ? 8 : 4);
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    // (576 threads are allocated as 20 warps: 96 registers per thread)
     static constexpr int COLS_PER_EPI_WARP = BN / (EPI_WARPS / 4);
     static constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 /*align*/ + 640 /*barriers, bucket table, ticket ring*/;
 };
@@ -122,6 +134,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 // start address >> 4 in [0,14), LBO (unused for swizzled K-major) in [16,30), SBO = 8 rows * 128 B in
 // [32,46), version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
@@ -157,10 +188,14 @@ __device__ __forceinline__ void red_release_add_u32(uint32_t* p, uint32_t v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Round to TF32 (10 explicit mantissa bits), nearest, ties away from zero -- cvt.rna.tf32.f32 -- written as the two
+// integer operations it amounts to for every finite input (add half an ulp of the 13 dropped bits to the magnitude,
+// clear them; a carry into the exponent is the correct round-up, an overflow gives inf, NaN stays NaN).  ptxas expands
+// the cvt into ~7 instructions (inf guard, select ...), and the epilogue rounds twice per element: at ~45 (x rows) to
+// ~90 (bounded rows) instructions per element it is ISSUE bound (16 K elements per tile against ~16 K cycles of MMAs).
+// Same formula as the host-side split of the W planes (reluqp/_batch.py: _tf32_planes).
 __device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 
@@ -186,38 +221,71 @@ struct EpiRow {
     float* la;          // a.lamp + (m - nx): lambda+ of the row, one per slot (stride nc)
 };
 
-// RED: the reduced iteration (a.reduced != 0); columns then go in groups of 8 instead of 16 (the extra lambda+
-// values would otherwise push the 128-column kernel into spills).
-template <bool RED>
+// Template switches keep the code of the common case lean (the epilogue is issue bound):
+//   RED    the reduced iteration (a.reduced != 0)
+//   PLAIN  last iteration of a window: also write the plain state (and, reduced, lambda with its planes)
+//   GCOL   per-column bias (rqp_batch.G)
+// Columns go in groups of 8: all global loads of a group are issued before its first store (the compiler cannot
+// hoist loads above stores that may alias).
+// Stores are NOT predicated on the slot being a real column: padding slots of a bucket (orig < 0) receive whatever
+// their (never read) accumulator column holds -- columns are independent, a padding slot's operand row only feeds
+// its own output column, which nobody reads.
+// Fast path (warp-uniform): a warp whose 32 rows are all x rows (dense layer: also lambda rows) has no bounds, no
+// lambda+ and no slot -> column map to fetch: bias, TF32 split, stores.
+template <bool RED, bool PLAIN, bool GCOL>
 __device__ __forceinline__ void tc_epilogue_chunk(const TcArgs& a, const EpiRow& e, const uint32_t (&r)[32], int n0,
                                                   int lane) {
-    constexpr int GW = RED ? 8 : 16;
-    const int o_lane = __ldg(a.orig + n0 + lane);
+    constexpr int GW = 8;
+    const int ldv = a.ldv;
+    if (!__any_sync(0xffffffffu, e.is_z)) {
+        if (!e.m_ok) return;
+        float* ph = e.ph + size_t(n0) * ldv;
+        float* pl = e.pl + size_t(n0) * ldv;
+        float* pp = PLAIN ? e.pp + size_t(n0) * ldv : nullptr;
+        const float* bcol = GCOL ? e.bcol + size_t(n0) * a.D : nullptr;
+#pragma unroll
+        for (int h = 0; h < 32 / GW; ++h) {
+            float bc[GW];
+#pragma unroll
+            for (int j = 0; j < GW; ++j) bc[j] = GCOL ? __ldg(bcol + size_t(h * GW + j) * a.D) : e.bias_shared;
+#pragma unroll
+            for (int j = 0; j < GW; ++j) {
+                const float y = __uint_as_float(r[h * GW + j]) + bc[j];
+                const float yh = tf32_rna(y);
+                ph[0] = yh;
+                pl[0] = tf32_rna(y - yh);   // round (not truncate) the low plane: no one-sided bias
+                if (PLAIN) pp[0] = y;
+                ph += ldv;
+                pl += ldv;
+                if (PLAIN) pp += ldv;
+            }
+        }
+        return;
+    }
+    const int o_lane = max(__ldg(a.orig + n0 + lane), 0);
 #pragma unroll
     for (int h = 0; h < 32 / GW; ++h) {
         float lo[GW], hi[GW], bc[GW], lp[GW];
-        int oj[GW];
         float* la = e.la + size_t(n0 + h * GW) * a.nc;
 #pragma unroll
         for (int j = 0; j < GW; ++j) {
-            oj[j] = __shfl_sync(0xffffffffu, o_lane, h * GW + j);
-            const int oc = max(oj[j], 0) * a.nc;
+            const int oc = __shfl_sync(0xffffffffu, o_lane, h * GW + j) * a.nc;
             lo[j] = -CUDART_INF_F;
             hi[j] = CUDART_INF_F;
-            if (e.is_z) {
+            if (e.is_z && RQP_TC_EXP != 1) {
                 lo[j] = __ldg(e.Lz + oc);
                 hi[j] = __ldg(e.Uz + oc);
             }
             bc[j] = e.bias_shared;
-            if (e.bcol != nullptr && e.m_ok) bc[j] = __ldg(e.bcol + size_t(n0 + h * GW + j) * a.D);
+            if (GCOL && e.m_ok) bc[j] = __ldg(e.bcol + size_t(n0 + h * GW + j) * a.D);
             lp[j] = 0.f;
             // lambda+ was written by whichever CTA ran this tile in the previous iteration: read it from L2
-            if (RED && e.red && oj[j] >= 0) lp[j] = __ldcg(la + size_t(j) * a.nc);
+            if (RED && e.red && RQP_TC_EXP != 1) lp[j] = __ldcg(la + j * a.nc);
         }
-        const size_t col0 = size_t(n0 + h * GW) * a.ldv;
+        const size_t col0 = size_t(n0 + h * GW) * ldv;
         float* ph = e.ph + col0;
         float* pl = e.pl + col0;
-        float* pp = e.pp ? e.pp + col0 : nullptr;
+        float* pp = PLAIN ? e.pp + col0 : nullptr;
 #pragma unroll
         for (int j = 0; j < GW; ++j) {
             const float t = __uint_as_float(r[h * GW + j]) + bc[j];
@@ -227,14 +295,13 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcArgs& a, const EpiRow&
             const float lpn = fmaf(e.R, t - y, lp[j]);
             const float v = (RED && e.red) ? fmaf(e.R, y, -lpn) : y;
             const float yh = tf32_rna(v);
-            const float yl = tf32_rna(v - yh);   // round (not truncate) the low plane: no one-sided bias
-            if (oj[j] >= 0 && e.m_ok) {
+            if (e.m_ok && (RQP_TC_EXP != 2 || yh == 1.2345f)) {
                 ph[0] = yh;
-                pl[0] = yl;
-                if (pp) pp[0] = y;
+                pl[0] = tf32_rna(v - yh);
+                if (PLAIN) pp[0] = y;
                 if (RED && e.red) {
-                    __stcg(la + size_t(j) * a.nc, lpn);
-                    if (pp) {                     // last iteration of the window: plain lambda and its planes
+                    __stcg(la + j * a.nc, lpn);
+                    if (PLAIN) {                  // last iteration of the window: plain lambda and its planes
                         const float lh = tf32_rna(lp[j]);
                         pp[a.nc] = lp[j];
                         ph[a.nc] = lh;
@@ -242,11 +309,20 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcArgs& a, const EpiRow&
                     }
                 }
             }
-            ph += a.ldv;
-            pl += a.ldv;
-            if (pp) pp += a.ldv;
+            ph += ldv;
+            pl += ldv;
+            if (PLAIN) pp += ldv;
         }
     }
+}
+template <bool RED>
+__device__ __forceinline__ void tc_epilogue_dispatch(const TcArgs& a, const EpiRow& e, const uint32_t (&r)[32], int n0,
+                                                     int lane) {
+    const bool plain = e.pp != nullptr, gcol = a.bias_cols != nullptr;      // uniform over the launch / the tile
+    if (!plain && !gcol) tc_epilogue_chunk<RED, false, false>(a, e, r, n0, lane);
+    else if (plain && !gcol) tc_epilogue_chunk<RED, true, false>(a, e, r, n0, lane);
+    else if (!plain) tc_epilogue_chunk<RED, false, true>(a, e, r, n0, lane);
+    else tc_epilogue_chunk<RED, true, true>(a, e, r, n0, lane);
 }
 
 __device__ __forceinline__ EpiRow make_epi_row(const TcArgs& a, int m, int rho, float* yh, float* yl, float* yp) {
@@ -460,7 +536,7 @@ struct TcWalk {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1)
 rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
                       const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                       const __grid_constant__ CUtensorMap map_xh1, const __grid_constant__ CUtensorMap map_xl1,
@@ -556,9 +632,9 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                             mbar_wait(empty + st2, ph2 ^ 1u);
                             w_empty += clock64() - tw;
                             unsigned char* sp = base + size_t(st2) * STAGE_BYTES;
-                            mbar_expect_tx(full + st2, STAGE_BYTES);
+                            mbar_expect_tx(full + st2, STAGE_BYTES - (RQP_TC_EXP >= 3 ? XT : 0) - (RQP_TC_EXP >= 4 ? TC_TILE_BYTES : 0));
                             tma_load_2d(sp, &map_wh, kb * TC_BK, wrow, full + st2);
-                            tma_load_2d(sp + TC_TILE_BYTES, &map_wl, kb * TC_BK, wrow, full + st2);
+                            if (RQP_TC_EXP < 4) tma_load_2d(sp + TC_TILE_BYTES, &map_wl, kb * TC_BK, wrow, full + st2);
                             if (++st2 == STAGES) { st2 = 0; ph2 ^= 1u; }
                         }
                         if (first) { grid_dep_wait(); first = false; }
@@ -576,7 +652,7 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                         const int kb = ki.next();
                         unsigned char* sp = base + size_t(stage) * STAGE_BYTES;
                         tma_load_2d(sp + 2 * TC_TILE_BYTES, mxh, kb * TC_BK, xrow, full + stage);
-                        tma_load_2d(sp + 2 * TC_TILE_BYTES + XT, mxl, kb * TC_BK, xrow, full + stage);
+                        if (RQP_TC_EXP < 3) tma_load_2d(sp + 2 * TC_TILE_BYTES + XT, mxl, kb * TC_BK, xrow, full + stage);
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
                     for (int i = P; i < nk; ++i) {
@@ -585,11 +661,11 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                         mbar_wait(empty + stage, phase ^ 1u);
                         w_empty += clock64() - tw;
                         unsigned char* sp = base + size_t(stage) * STAGE_BYTES;
-                        mbar_expect_tx(full + stage, STAGE_BYTES);
+                        mbar_expect_tx(full + stage, STAGE_BYTES - (RQP_TC_EXP >= 3 ? XT : 0) - (RQP_TC_EXP >= 4 ? TC_TILE_BYTES : 0));
                         tma_load_2d(sp, &map_wh, kb * TC_BK, wrow, full + stage);
-                        tma_load_2d(sp + TC_TILE_BYTES, &map_wl, kb * TC_BK, wrow, full + stage);
+                        if (RQP_TC_EXP < 4) tma_load_2d(sp + TC_TILE_BYTES, &map_wl, kb * TC_BK, wrow, full + stage);
                         tma_load_2d(sp + 2 * TC_TILE_BYTES, mxh, kb * TC_BK, xrow, full + stage);
-                        tma_load_2d(sp + 2 * TC_TILE_BYTES + XT, mxl, kb * TC_BK, xrow, full + stage);
+                        if (RQP_TC_EXP < 3) tma_load_2d(sp + 2 * TC_TILE_BYTES + XT, mxl, kb * TC_BK, xrow, full + stage);
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -664,7 +740,7 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
         const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter + 32)
         const int half = (warp - 2) >> 2;             // which share of the tile's columns
         uint32_t acc = 0, acc_phase = 0;
-        long long w_accf = 0, t_store = 0;
+        long long w_accf = 0, t_store = 0, t_fence = 0, t_store_z = 0, n_z = 0;
         grid_dep_wait();
         long long t_all = clock64();
         TcWalk walk;
@@ -713,9 +789,20 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                     if (ch == 0) {
                         tmem_ld32(taddr + c * 32, sum[c]);
                     } else {
+#if !RQP_TC_KAHAN
+                        // two 16-column reads: 16 fewer live registers than one 32-column read
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            uint32_t r[16];
+                            tmem_ld16(taddr + c * 32 + hh * 16, r);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                sum[c][hh * 16 + j] =
+                                    __float_as_uint(__uint_as_float(sum[c][hh * 16 + j]) + __uint_as_float(r[j]));
+                        }
+#else
                         uint32_t r[32];
                         tmem_ld32(taddr + c * 32, r);
-#if RQP_TC_KAHAN
                         // experiment: error-free (two-sum) accumulation of the chunk partials
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -725,10 +812,6 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                             comp[c][j] += (aa - (ss - bv)) + (bb - bv);
                             sum[c][j] = __float_as_uint(ss);
                         }
-#else
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            sum[c][j] = __float_as_uint(__uint_as_float(sum[c][j]) + __uint_as_float(r[j]));
 #endif
                     }
                 }
@@ -783,21 +866,26 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
             for (int c = 0; c < NCH; ++c) {
                 const int n0 = col0 + half * Cfg::COLS_PER_EPI_WARP + c * 32;
                 if (a.raw) tc_epilogue_raw(a, m, sum[c], n0, lane);
-                else if (a.reduced) tc_epilogue_chunk<true>(a, e, sum[c], n0, lane);
-                else tc_epilogue_chunk<false>(a, e, sum[c], n0, lane);
+                else if (a.reduced) tc_epilogue_dispatch<true>(a, e, sum[c], n0, lane);
+                else tc_epilogue_dispatch<false>(a, e, sum[c], n0, lane);
             }
+            const long long tf0 = clock64();
             if (a.done != nullptr) {
                 // this warp's share of the tile is written: make it visible GPU-wide (to TMA readers too),
                 // then count the warp into the column tile's completion counter
-                __threadfence();
+                if (!(a.xflags & 1)) __threadfence();
                 fence_proxy_async_all();
                 __syncwarp();
                 if (lane == 0) red_release_add_u32(a.done + t / a.n_row_tiles, 1u);
             }
-            t_store += clock64() - ts0;
+            const long long te = clock64();
+            t_store += te - ts0;
+            t_fence += te - tf0;
+            if (__any_sync(0xffffffffu, e.is_z)) { t_store_z += te - ts0; n_z += 1; }
         }
         if (a.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) {
             a.dbg[6] = w_accf; a.dbg[7] = clock64() - t_all; a.dbg[8] = t_store;
+            a.dbg[10] = t_fence; a.dbg[11] = t_store_z; a.dbg[12] = n_z;
         }
     }
     tc_fence_before();
@@ -852,7 +940,7 @@ static int tc_launch_bn(const CUtensorMap& wh, const CUtensorMap& wl, const CUte
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(grid));
-    cfg.blockDim = dim3(TC_THREADS);
+    cfg.blockDim = dim3(TcCfg<BN>::THREADS);
     cfg.dynamicSmemBytes = TcCfg<BN>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];

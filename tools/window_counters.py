@@ -24,6 +24,6 @@ for rep in range(3):
     r = m.solve_batch(Ld, Ud)
     d = m._batch.dbg.cpu().tolist()
     names = ["prod wait-empty", "prod total", "mma wait-full", "mma wait-acc", "mma total", "tiles", "epi wait-acc-full",
-             "epi total", "epi store", "prod wait-dep"]
+             "epi total", "epi store", "prod wait-dep", "epi fence", "epi store (tiles with clamped rows)", "such tiles"]
     print("B %d window: %.3f ms total solve; " % (B, r.run_time * 1e3) +
           ", ".join("%s %d" % (n, v) for n, v in zip(names, d)), flush=True)

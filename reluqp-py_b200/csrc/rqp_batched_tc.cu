@@ -194,6 +194,11 @@ __device__ __forceinline__ void red_release_add_u32(uint32_t* p, uint32_t v) {
 // the cvt into ~7 instructions (inf guard, select ...), and the epilogue rounds twice per element: at ~45 (x rows) to
 // ~90 (bounded rows) instructions per element it is ISSUE bound (16 K elements per tile against ~16 K cycles of MMAs).
 // Same formula as the host-side split of the W planes (reluqp/_batch.py: _tf32_planes).
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void red_relaxed_add_u32(uint32_t* p, uint32_t v) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ float tf32_rna(float x) {
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
@@ -235,41 +240,39 @@ struct EpiRow {
 template <bool RED, bool PLAIN, bool GCOL>
 __device__ __forceinline__ void tc_epilogue_chunk(const TcArgs& a, const EpiRow& e, const uint32_t (&r)[32], int n0,
                                                   int lane) {
+    // Addressing: every per-column address is (64-bit base of this thread's row) + (32-bit element offset): one
+    // IMAD.WIDE.U32 per access instead of the four-instruction 64-bit pointer increments ptxas generates otherwise.
+    // All offsets fit 32 bits (slots x ldv, columns x nc, slots x D < 2^31).
     constexpr int GW = 8;
-    const int ldv = a.ldv;
+    const unsigned ldv = unsigned(a.ldv), nc = unsigned(a.nc), Dg = unsigned(a.D);
     if (!__any_sync(0xffffffffu, e.is_z)) {
         if (!e.m_ok) return;
-        float* ph = e.ph + size_t(n0) * ldv;
-        float* pl = e.pl + size_t(n0) * ldv;
-        float* pp = PLAIN ? e.pp + size_t(n0) * ldv : nullptr;
-        const float* bcol = GCOL ? e.bcol + size_t(n0) * a.D : nullptr;
+        unsigned off = unsigned(n0) * ldv;
 #pragma unroll
         for (int h = 0; h < 32 / GW; ++h) {
             float bc[GW];
 #pragma unroll
-            for (int j = 0; j < GW; ++j) bc[j] = GCOL ? __ldg(bcol + size_t(h * GW + j) * a.D) : e.bias_shared;
+            for (int j = 0; j < GW; ++j) bc[j] = GCOL ? __ldg(e.bcol + unsigned(n0 + h * GW + j) * Dg) : e.bias_shared;
 #pragma unroll
             for (int j = 0; j < GW; ++j) {
                 const float y = __uint_as_float(r[h * GW + j]) + bc[j];
                 const float yh = tf32_rna(y);
-                ph[0] = yh;
-                pl[0] = tf32_rna(y - yh);   // round (not truncate) the low plane: no one-sided bias
-                if (PLAIN) pp[0] = y;
-                ph += ldv;
-                pl += ldv;
-                if (PLAIN) pp += ldv;
+                e.ph[off] = yh;
+                e.pl[off] = tf32_rna(y - yh);   // round (not truncate) the low plane: no one-sided bias
+                if (PLAIN) e.pp[off] = y;
+                off += ldv;
             }
         }
         return;
     }
     const int o_lane = max(__ldg(a.orig + n0 + lane), 0);
+    unsigned off = unsigned(n0) * ldv, loff = unsigned(n0) * nc;
 #pragma unroll
     for (int h = 0; h < 32 / GW; ++h) {
         float lo[GW], hi[GW], bc[GW], lp[GW];
-        float* la = e.la + size_t(n0 + h * GW) * a.nc;
 #pragma unroll
         for (int j = 0; j < GW; ++j) {
-            const int oc = __shfl_sync(0xffffffffu, o_lane, h * GW + j) * a.nc;
+            const unsigned oc = unsigned(__shfl_sync(0xffffffffu, o_lane, h * GW + j)) * nc;
             lo[j] = -CUDART_INF_F;
             hi[j] = CUDART_INF_F;
             if (e.is_z && RQP_TC_EXP != 1) {
@@ -277,15 +280,11 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcArgs& a, const EpiRow&
                 hi[j] = __ldg(e.Uz + oc);
             }
             bc[j] = e.bias_shared;
-            if (GCOL && e.m_ok) bc[j] = __ldg(e.bcol + size_t(n0 + h * GW + j) * a.D);
+            if (GCOL && e.m_ok) bc[j] = __ldg(e.bcol + unsigned(n0 + h * GW + j) * Dg);
             lp[j] = 0.f;
             // lambda+ was written by whichever CTA ran this tile in the previous iteration: read it from L2
-            if (RED && e.red && RQP_TC_EXP != 1) lp[j] = __ldcg(la + j * a.nc);
+            if (RED && e.red && RQP_TC_EXP != 1) lp[j] = __ldcg(e.la + (loff + unsigned(j) * nc));
         }
-        const size_t col0 = size_t(n0 + h * GW) * ldv;
-        float* ph = e.ph + col0;
-        float* pl = e.pl + col0;
-        float* pp = PLAIN ? e.pp + col0 : nullptr;
 #pragma unroll
         for (int j = 0; j < GW; ++j) {
             const float t = __uint_as_float(r[h * GW + j]) + bc[j];
@@ -296,22 +295,21 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcArgs& a, const EpiRow&
             const float v = (RED && e.red) ? fmaf(e.R, y, -lpn) : y;
             const float yh = tf32_rna(v);
             if (e.m_ok && (RQP_TC_EXP != 2 || yh == 1.2345f)) {
-                ph[0] = yh;
-                pl[0] = tf32_rna(v - yh);
-                if (PLAIN) pp[0] = y;
+                e.ph[off] = yh;
+                e.pl[off] = tf32_rna(v - yh);
+                if (PLAIN) e.pp[off] = y;
                 if (RED && e.red) {
-                    __stcg(la + j * a.nc, lpn);
+                    __stcg(e.la + loff, lpn);
                     if (PLAIN) {                  // last iteration of the window: plain lambda and its planes
                         const float lh = tf32_rna(lp[j]);
-                        pp[a.nc] = lp[j];
-                        ph[a.nc] = lh;
-                        pl[a.nc] = tf32_rna(lp[j] - lh);
+                        e.pp[off + nc] = lp[j];
+                        e.ph[off + nc] = lh;
+                        e.pl[off + nc] = tf32_rna(lp[j] - lh);
                     }
                 }
             }
-            ph += ldv;
-            pl += ldv;
-            if (PLAIN) pp += ldv;
+            off += ldv;
+            loff += nc;
         }
     }
 }
@@ -430,14 +428,14 @@ __device__ __forceinline__ void tc_tile_rows(const TcArgs& a, int rho, int rt, i
 
 // Residual epilogue: the accumulator goes out as plain fp32, Out[slot][m] (ld = a.ldv).
 __device__ __forceinline__ void tc_epilogue_raw(const TcArgs& a, int m, const uint32_t (&r)[32], int n0, int lane) {
-    const int o_lane = __ldg(a.orig + n0 + lane);
-    const bool m_ok = m < a.M;
-    float* pp = a.Yplain + size_t(n0) * a.ldv + (m_ok ? m : 0);
+    (void)lane;
+    if (m >= a.M) return;
+    float* pp = a.Yplain + m;
+    unsigned off = unsigned(n0) * unsigned(a.ldv);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        const int oj = __shfl_sync(0xffffffffu, o_lane, j);
-        if (oj >= 0 && m_ok) pp[0] = __uint_as_float(r[j]);
-        pp += a.ldv;
+        pp[off] = __uint_as_float(r[j]);      // padding slots included: their rows of the result buffer are never read
+        off += unsigned(a.ldv);
     }
 }
 
@@ -873,10 +871,17 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
             if (a.done != nullptr) {
                 // this warp's share of the tile is written: make it visible GPU-wide (to TMA readers too),
                 // then count the warp into the column tile's completion counter
-                if (!(a.xflags & 1)) __threadfence();
+                // Every lane orders its own stores (fence.acq_rel.gpu, SASS MEMBAR.ALL.GPU -- not the sequentially
+                // consistent MEMBAR.SC.GPU of __threadfence(), which cost ~4 k cycles per tile here), the warp
+                // barrier orders the lanes, lane 0's relaxed add then completes the release pattern.
+                if (a.xflags & 1) __threadfence();
+                else fence_acq_rel_gpu();
                 fence_proxy_async_all();
                 __syncwarp();
-                if (lane == 0) red_release_add_u32(a.done + t / a.n_row_tiles, 1u);
+                if (lane == 0) {
+                    if (a.xflags & 1) red_release_add_u32(a.done + t / a.n_row_tiles, 1u);
+                    else red_relaxed_add_u32(a.done + t / a.n_row_tiles, 1u);
+                }
             }
             const long long te = clock64();
             t_store += te - ts0;

@@ -147,6 +147,7 @@ def _measure(m, args, rank, world, dev, B_local, B_total, steps, warmup, flush, 
 # (B, element bytes, engine, reduced iteration?) -> (bytes, file under profiles/)
 TRAFFIC = {
     (4096, 4, 0, False): (500.15e6 + 687.35e6, "profiles/r02_batched_window_ncu_full.csv"),
+    (4096, 4, 0, True): (223.39e6 + 411.90e6, "profiles/r02e_batched_window_ncu_full.csv"),
 }
 
 
@@ -227,7 +228,7 @@ def run_batched(args, rank, world, dev):
         n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * weak["dev_s"] / args.steps,
         higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32" if elem == 4 else "f64",
         data="synthetic", config=batched_config(args, world),
-        engine={0: "auto (tcgen05 cta_group::1, 128x{128,64,32} tiles picked per check window, chunked accumulation of the x rows, PDL)", 1: "simt", 2: "tcgen05 cta_group::1"}.get(args.batch_engine, str(args.batch_engine)) if dt == torch.float32 else {0: "fp64 DMMA (mma.sync.m8n8k4.f64)", 1: "fp64 simt"}.get(args.batch_engine, "?"),
+        engine={0: "auto (tcgen05 cta_group::1, 128x{128,64,32} tiles picked per check window, chunked accumulation of the x rows, 16 epilogue warps, PDL)", 1: "simt", 2: "tcgen05 cta_group::1"}.get(args.batch_engine, str(args.batch_engine)) if dt == torch.float32 else {0: "fp64 DMMA (mma.sync.m8n8k4.f64)", 1: "fp64 simt"}.get(args.batch_engine, "?"),
         iteration_form=("reduced: [x+; A x+] = Wr [x; R z - lambda+] + br, (nx+nc)^2 = {}^2 product per column-iteration, "
                         "z / lambda update in the GEMM epilogue".format(Dit)) if reduced else
                        "dense layer v+ = clamp(W_rho v + b), D^2 = {}^2 product per column-iteration".format(D),

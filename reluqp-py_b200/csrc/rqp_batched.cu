@@ -1000,7 +1000,9 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     const bool pdl_ok = getenv("RQP_NO_PDL") == nullptr;
     const bool tc_narrow = getenv("RQP_NO_NARROW") == nullptr;
     const bool tc_ksplit_ok = getenv("RQP_NO_KSPLIT") == nullptr;
-    const int tc_ksplit_max = getenv("RQP_KSPLIT_MAX") ? atoi(getenv("RQP_KSPLIT_MAX")) : 8;
+    // at most 4 ranks per tile: with the reduced iteration's 20 k-blocks an 8-way split costs more in the partial-sum
+    // exchange than its shorter mainloops save (B = 64 / 256 / 512: 18.7 / 71.1 / 130 k solves/s with 4, 17.6 / 69.2 / 128 with 8)
+    const int tc_ksplit_max = getenv("RQP_KSPLIT_MAX") ? atoi(getenv("RQP_KSPLIT_MAX")) : 4;
     // one launch per check window (1-CTA tcgen05 kernels): 0 never, 1 when CTAs own several tiles, 2 always
     const int tc_window = getenv("RQP_NO_WINDOW") ? 0 : (getenv("RQP_WINDOW") ? atoi(getenv("RQP_WINDOW")) : 1);
     // fp64: DMMA tensor-core GEMM (engine 1 forces the SIMT kernels)

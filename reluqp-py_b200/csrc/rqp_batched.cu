@@ -874,7 +874,8 @@ static BatchLayout batch_layout(const rqp_problem* p, int B, int ldv, bool with_
     l.off_cursor = take(size_t(p->n_rho) * 4);
     l.off_tile = take(size_t(l.n_tiles) * 4);
     l.off_btab = take(64 * 4);
-    l.off_done = take(size_t(l.cap / 32 + 2) * 4);      // window kernel: one completion counter per column tile
+    // window kernel: one completion counter per (column tile, row tile of the iteration matrix) + the ticket counter
+    l.off_done = take((size_t(l.cap / 32 + 1) * size_t((D + 127) / 128) + 1) * 4);
     // split-K of the tcgen05 kernels (fewer tiles than SMs): one work item per SM at most
     l.off_kcnt = take(planes ? size_t(kMaxSplitItems) * 16 * 4 : 0);     // [tiles][epilogue warps <= 16]
     l.off_scratch = take(planes ? size_t(kMaxSplitItems) * 128 * 128 * 4 : 0);
@@ -1000,9 +1001,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     const bool pdl_ok = getenv("RQP_NO_PDL") == nullptr;
     const bool tc_narrow = getenv("RQP_NO_NARROW") == nullptr;
     const bool tc_ksplit_ok = getenv("RQP_NO_KSPLIT") == nullptr;
-    // at most 4 ranks per tile: with the reduced iteration's 20 k-blocks an 8-way split costs more in the partial-sum
-    // exchange than its shorter mainloops save (B = 64 / 256 / 512: 18.7 / 71.1 / 130 k solves/s with 4, 17.6 / 69.2 / 128 with 8)
-    const int tc_ksplit_max = getenv("RQP_KSPLIT_MAX") ? atoi(getenv("RQP_KSPLIT_MAX")) : 4;
+    const int tc_ksplit_max = getenv("RQP_KSPLIT_MAX") ? atoi(getenv("RQP_KSPLIT_MAX")) : 8;
     // one launch per check window (1-CTA tcgen05 kernels): 0 never, 1 when CTAs own several tiles, 2 always
     const int tc_window = getenv("RQP_NO_WINDOW") ? 0 : (getenv("RQP_WINDOW") ? atoi(getenv("RQP_WINDOW")) : 1);
     // fp64: DMMA tensor-core GEMM (engine 1 forces the SIMT kernels)
@@ -1079,6 +1078,8 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     auto pick_ksplit = [&](int tiles, int nk_min) -> int {
         if (!tc_ksplit_ok || tiles < 1) return 1;
         const int lim = sm_count < kMaxSplitItems ? sm_count : kMaxSplitItems;
+        // (measured with the reduced iteration, ranks per tile capped at 4 vs 8: B = 64 / 256 / 512 +4 / +1 / +2 % with 4,
+        // B = 1024 / 2048 +7 / +8 % with 8, B = 4096 equal: 8 stays)
         for (int ks = tc_ksplit_max; ks >= 2; ks >>= 1)
             if (tiles * ks <= lim && ks <= nk_min) return ks;
         return 1;
@@ -1138,12 +1139,13 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
             const int bound = nact_host[3 - b] * a.n_row_tiles * a.ksplit;
             if (steps > 1) {
                 a.done = reinterpret_cast<unsigned int*>(w8 + lay.off_done);
-                RQP_CUDA_TRY(cudaMemsetAsync(a.done, 0, size_t(cap / 32 + 1) * 4, st));
+                const size_t n_done = size_t(cap / 32 + 1) * size_t((D + 127) / 128);
+                RQP_CUDA_TRY(cudaMemsetAsync(a.done, 0, (n_done + 1) * 4, st));
                 const int grid = bound < sm_count ? bound : sm_count;
                 if (bound > grid) {
                     // more items than CTAs: hand items out through a ticket counter (the spare last entry of
                     // the `done` array, zeroed above); RQP_NO_TICKET=1: static assignment rotated per iteration
-                    if (tc_ticket) a.ticket = a.done + cap / 32;
+                    if (tc_ticket) a.ticket = a.done + n_done;
                     else a.rot = pick_rot(grid);
                 }
             }

@@ -611,57 +611,87 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                     int t, rank, rho, xrow, rt, wrow;
                     KIter ki;
                     if (!tc_item<BN>(sb, a, u, t, rank, rho, xrow, rt, wrow, ki)) break;
-                    int nk = ki.count();
-                    // Is there something to wait for before this tile's state planes may be read: the previous
-                    // kernel (first tile of a PDL launch) or the previous iteration of this column tile (window
-                    // mode)?  Then W, which depends on neither, goes first: up to a ring-full of W planes is
-                    // issued before the wait, the state planes follow.  Otherwise k-blocks stream normally.
-                    const uint32_t need = uint32_t(it) * uint32_t(a.n_row_tiles) * Cfg::EPI_WARPS;
-                    const uint32_t* cnt = a.done != nullptr ? a.done + t / a.n_row_tiles : nullptr;
-                    const bool dep = cnt != nullptr && it > 0 && ld_acquire_u32(cnt) < need;
-                    int P = 0;
-                    if (first || dep) {
-                        P = nk < STAGES ? nk : STAGES;
-                        uint32_t st2 = stage, ph2 = phase;
-                        KIter kw = ki;
-                        for (int s = 0; s < P; ++s) {
-                            const int kb = kw.next();
+                    const int nk = ki.count();
+                    // W planes depend on nothing and run up to a ring-full ahead of the state planes.  The state
+                    // planes of k-block kb are rows [32 kb, 32 kb + 32) of what the PREVIOUS iteration wrote for this
+                    // column tile, i.e. the output of its row tile kb / 4: in window mode the producer waits for
+                    // exactly that row tile (one completion counter per (column tile, row tile)), so the MMAs of
+                    // iteration i + 1 start on the rows that are ready -- the x rows, whose epilogue is the short
+                    // one -- while the epilogues of the bounded rows of iteration i are still running.  (Writes are
+                    // safe: a tile's epilogue overwrites what iteration i read only after its own mainloop, which
+                    // needs EVERY row tile of iteration i complete.)  First tile of a PDL launch: the previous
+                    // kernel is waited for before the first state-plane load.
+                    const uint32_t need = uint32_t(it) * Cfg::EPI_WARPS;
+                    const uint32_t* cnt = (a.done != nullptr && it > 0) ? a.done + size_t(t / a.n_row_tiles) * a.n_row_tiles
+                                                                        : nullptr;
+                    int ready_rt = 0;                       // row tiles of the previous iteration known complete
+                    const int nrt = a.n_row_tiles <= 16 ? a.n_row_tiles : 1;   // (more than 16 row tiles: poll one at a time)
+                    // one round trip polls ALL outstanding counters of the column tile (independent relaxed loads; the
+                    // acquire fence follows once, before the state planes are read)
+                    auto poll = [&]() {
+                        uint32_t c16[16];
+#pragma unroll
+                        for (int r2 = 0; r2 < 16; ++r2)
+                            c16[r2] = (r2 >= ready_rt && r2 < ready_rt + nrt && r2 < a.n_row_tiles) ? ld_relaxed_u32(cnt + r2) : 0u;
+#pragma unroll
+                        for (int r2 = 0; r2 < 16; ++r2)
+                            if (r2 == ready_rt && r2 < a.n_row_tiles && c16[r2] >= need) ++ready_rt;
+                    };
+                    if (cnt != nullptr) {
+                        if (a.n_row_tiles <= 16) poll();
+                        fence_acq_rel_gpu();
+                        fence_proxy_async_all();
+                    }
+                    int w_issued = 0;
+                    uint32_t wst = stage, wph = phase;
+                    KIter kw = ki;
+                    auto issue_w = [&]() {
+                        const int kbw = kw.next();
+                        unsigned char* spw = base + size_t(wst) * STAGE_BYTES;
+                        mbar_expect_tx(full + wst, STAGE_BYTES - (RQP_TC_EXP >= 3 ? XT : 0) - (RQP_TC_EXP >= 4 ? TC_TILE_BYTES : 0));
+                        tma_load_2d(spw, &map_wh, kbw * TC_BK, wrow, full + wst);
+                        if (RQP_TC_EXP < 4) tma_load_2d(spw + TC_TILE_BYTES, &map_wl, kbw * TC_BK, wrow, full + wst);
+                        if (++wst == STAGES) { wst = 0; wph ^= 1u; }
+                        ++w_issued;
+                    };
+                    for (int x_issued = 0; x_issued < nk; ++x_issued) {
+                        if (w_issued == x_issued) {           // this k-block's W planes: wait for the ring slot
                             const long long tw = clock64();
-                            mbar_wait(empty + st2, ph2 ^ 1u);
+                            mbar_wait(empty + wst, wph ^ 1u);
                             w_empty += clock64() - tw;
-                            unsigned char* sp = base + size_t(st2) * STAGE_BYTES;
-                            mbar_expect_tx(full + st2, STAGE_BYTES - (RQP_TC_EXP >= 3 ? XT : 0) - (RQP_TC_EXP >= 4 ? TC_TILE_BYTES : 0));
-                            tma_load_2d(sp, &map_wh, kb * TC_BK, wrow, full + st2);
-                            if (RQP_TC_EXP < 4) tma_load_2d(sp + TC_TILE_BYTES, &map_wl, kb * TC_BK, wrow, full + st2);
-                            if (++st2 == STAGES) { st2 = 0; ph2 ^= 1u; }
+                            issue_w();
                         }
-                        if (first) { grid_dep_wait(); first = false; }
-                        if (dep) {
-                            const long long tw = clock64();
-                            uint32_t spins = 0;
-                            while (ld_acquire_u32(cnt) < need) {
-                                if (++spins > (1u << 24)) __trap();
+                        const int kb = ki.next();
+                        if (first) {
+                            // first tile of a launch: a ring-full of W planes goes out before the previous kernel
+                            // (programmatic dependent launch) is waited for
+                            while (w_issued < nk && w_issued < x_issued + STAGES && mbar_try_wait(empty + wst, wph ^ 1u))
+                                issue_w();
+                            grid_dep_wait();
+                            first = false;
+                        }
+                        if (cnt != nullptr) {
+                            const int rtk = min((kb * TC_BK) / TC_BM, a.n_row_tiles - 1);
+                            bool waited = false;
+                            if (ready_rt <= rtk) {
+                                const long long tw = clock64();
+                                uint32_t spins = 0;
+                                while (ready_rt <= rtk) {
+                                    if (a.n_row_tiles <= 16) poll();
+                                    else if (ld_relaxed_u32(cnt + ready_rt) >= need) ++ready_rt;
+                                    if (ready_rt > rtk) break;
+                                    if (++spins > (1u << 24)) __trap();
+                                    // while waiting: W planes of later k-blocks into slots that are free right now
+                                    if (w_issued < nk && w_issued < x_issued + STAGES && mbar_try_wait(empty + wst, wph ^ 1u))
+                                        issue_w();
+                                }
+                                w_dep += clock64() - tw;
+                                waited = true;
+                                fence_acq_rel_gpu();
                             }
-                            w_dep += clock64() - tw;
+                            if (waited) fence_proxy_async_all();   // acquire above -> TMA reads below
                         }
-                    }
-                    if (cnt != nullptr && it > 0) fence_proxy_async_all();   // acquire above -> TMA reads below
-                    for (int s = 0; s < P; ++s) {
-                        const int kb = ki.next();
                         unsigned char* sp = base + size_t(stage) * STAGE_BYTES;
-                        tma_load_2d(sp + 2 * TC_TILE_BYTES, mxh, kb * TC_BK, xrow, full + stage);
-                        if (RQP_TC_EXP < 3) tma_load_2d(sp + 2 * TC_TILE_BYTES + XT, mxl, kb * TC_BK, xrow, full + stage);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-                    }
-                    for (int i = P; i < nk; ++i) {
-                        const int kb = ki.next();
-                        const long long tw = clock64();
-                        mbar_wait(empty + stage, phase ^ 1u);
-                        w_empty += clock64() - tw;
-                        unsigned char* sp = base + size_t(stage) * STAGE_BYTES;
-                        mbar_expect_tx(full + stage, STAGE_BYTES - (RQP_TC_EXP >= 3 ? XT : 0) - (RQP_TC_EXP >= 4 ? TC_TILE_BYTES : 0));
-                        tma_load_2d(sp, &map_wh, kb * TC_BK, wrow, full + stage);
-                        if (RQP_TC_EXP < 4) tma_load_2d(sp + TC_TILE_BYTES, &map_wl, kb * TC_BK, wrow, full + stage);
                         tma_load_2d(sp + 2 * TC_TILE_BYTES, mxh, kb * TC_BK, xrow, full + stage);
                         if (RQP_TC_EXP < 3) tma_load_2d(sp + 2 * TC_TILE_BYTES + XT, mxl, kb * TC_BK, xrow, full + stage);
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -764,10 +794,13 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                 // empty K slice (the host avoids it; kept correct): contributes zeros, but must not run ahead
                 // of the iteration order the other ranks get from their operand dependency
                 if (a.done != nullptr && it > 0) {
-                    const uint32_t need = uint32_t(it) * uint32_t(a.n_row_tiles) * Cfg::EPI_WARPS;
-                    uint32_t spins = 0;
-                    while (ld_acquire_u32(a.done + t / a.n_row_tiles) < need) {
-                        if (++spins > (1u << 24)) __trap();
+                    const uint32_t need = uint32_t(it) * Cfg::EPI_WARPS;
+                    const uint32_t* cnt = a.done + size_t(t / a.n_row_tiles) * a.n_row_tiles;
+                    for (int r2 = 0; r2 < a.n_row_tiles; ++r2) {
+                        uint32_t spins = 0;
+                        while (ld_acquire_u32(cnt + r2) < need) {
+                            if (++spins > (1u << 24)) __trap();
+                        }
                     }
                 }
 #pragma unroll
@@ -879,8 +912,9 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                 fence_proxy_async_all();
                 __syncwarp();
                 if (lane == 0) {
-                    if (a.xflags & 1) red_release_add_u32(a.done + t / a.n_row_tiles, 1u);
-                    else red_relaxed_add_u32(a.done + t / a.n_row_tiles, 1u);
+                    // t = column tile * n_row_tiles + row tile: one counter per tile
+                    if (a.xflags & 1) red_release_add_u32(a.done + t, 1u);
+                    else red_relaxed_add_u32(a.done + t, 1u);
                 }
             }
             const long long te = clock64();

@@ -41,7 +41,7 @@ struct TcArgs {
     const float* Rv;        // [n_rho][nc]
     const float* Rinv;      // [n_rho][nc]
     float* lamp;            // [cap][nc]
-    int xflags;             // experiment switches (RQP_TC_XFLAGS): 1 = __threadfence() + red.release instead of fence.acq_rel + red.relaxed, 2 = bounds via ld.cg
+    int xflags;             // experiment switches (RQP_TC_XFLAGS): 1 = __threadfence() + red.release instead of fence.acq_rel + red.relaxed, 2 = bounds via ld.cg, 4 = row tiles of a column tile handed out in descending order
 };
 
 // 2-D fp32 row-major [rows][ld] tensor, box = 32 columns (128 B) x box_rows rows, SWIZZLE_128B, zero OOB fill

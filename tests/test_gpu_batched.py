@@ -639,3 +639,24 @@ def test_host_array_paths_and_small_batch_isolation(golden):
     ms = gpu_model((plant.H, plant.g, plant.A, L[0], U[0]), structured=True)
     with pytest.raises(RuntimeError, match="dense layer matrices"):
         ms.solve_batch(L4, U4)
+
+
+def test_shared_g_follows_update():
+    """solve_batch without per-column g uses the solver's CURRENT g: after update(g=...) the dense form reads the
+    refreshed b_rho = B_rho g (rqp_update_bias), the reduced form re-forms br = [-K g; -A K g] from the live g.
+    Column j must equal the oracle's cold solve of (H, g_new, A, l_j, u_j)."""
+    H, g, A, l, u, _ = utils.rand_qp(30, 7, 7, seed=4, compute_sol=False)
+    Ls, Us = [], []
+    for sd in range(48):
+        _, _, _, l2, u2, _ = utils.update_qp(H, A, 7, 7, seed=20 + sd, compute_sol=False)
+        Ls.append(l2); Us.append(u2)
+    L, U = np.stack(Ls), np.stack(Us)
+    _, g_new, _, _, _, _ = utils.update_qp(H, A, 7, 7, seed=77, compute_sol=False)
+    m = gpu_model((H, g, A, l, u), eps_abs=1e-6)
+    m.update(g=g_new)
+    res = m.solve_batch(L, U, engine=1)
+    assert res.sweeps > 0
+    ref = O.solve_batch(H, g_new, A, L[:6], U[:6], eps_abs=1e-6)
+    for j, r in enumerate(ref):
+        assert int(res.iter[j]) == r.iter and res.status[j] == r.status, j
+        assert rel_err(res.x[j].cpu().numpy(), r.x.numpy()) < 1e-6, j

@@ -874,13 +874,19 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                 for (int c = 0; c < NCH; ++c)
 #pragma unroll
                     for (int j = 0; j < 32; ++j) __stcg(mine + (c * 32 + j) * 32, __uint_as_float(sum[c][j]));
-                __threadfence();
+                // release: every lane orders its own partials (fence.acq_rel.gpu, not the sequentially consistent
+                // fence of __threadfence(): this exchange sits on the per-iteration latency chain of small active
+                // sets), the warp barrier orders the lanes, lane 0's atomic follows
+                if (a.xflags & 1) __threadfence();
+                else fence_acq_rel_gpu();
                 __syncwarp();
                 uint32_t old = 0;
                 if (lane == 0) old = atomicAdd(a.kcnt + size_t(t) * Cfg::EPI_WARPS + w, 1u);
                 old = __shfl_sync(0xffffffffu, old, 0);
                 if ((old % uint32_t(a.ksplit)) != uint32_t(a.ksplit - 1)) continue;   // a later rank finishes it
-                __threadfence();
+                if (a.xflags & 1) __threadfence();
+                else fence_acq_rel_gpu();                  // acquire: the other ranks' partials
+                __syncwarp();
                 for (int r = 0; r < a.ksplit; ++r) {
                     const float* part = a.scratch + ((size_t(t) * a.ksplit + r) * Cfg::EPI_WARPS + w) * SUB + lane;
 #pragma unroll

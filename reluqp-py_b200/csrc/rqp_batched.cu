@@ -1003,7 +1003,9 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     const bool tc_ksplit_ok = getenv("RQP_NO_KSPLIT") == nullptr;
     const int tc_ksplit_max = getenv("RQP_KSPLIT_MAX") ? atoi(getenv("RQP_KSPLIT_MAX")) : 8;
     // one launch per check window (1-CTA tcgen05 kernels): 0 never, 1 when CTAs own several tiles, 2 always
-    const int tc_window = getenv("RQP_NO_WINDOW") ? 0 : (getenv("RQP_WINDOW") ? atoi(getenv("RQP_WINDOW")) : 1);
+    // (default since the per-row-tile dependencies: always -- with one unsplit tile per CTA the window kernel now beats
+    // 25 programmatic dependent launches too: B = 512 / 1024 / 2048 +6 / +6 / +4 %; RQP_WINDOW=1 restores "when it pays")
+    const int tc_window = getenv("RQP_NO_WINDOW") ? 0 : (getenv("RQP_WINDOW") ? atoi(getenv("RQP_WINDOW")) : 2);
     // fp64: DMMA tensor-core GEMM (engine 1 forces the SIMT kernels)
     const bool use_dmma = std::is_same<T, double>::value && bt->engine != 1 && getenv("RQP_NO_DMMA") == nullptr;
     const int dmma_min = getenv("RQP_DMMA_MIN") ? atoi(getenv("RQP_DMMA_MIN")) : 1;

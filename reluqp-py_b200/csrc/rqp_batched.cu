@@ -1065,7 +1065,9 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         // mainloop -> epilogue -> next iteration's mainloop is serial (33 us per iteration), with two narrower
         // tiles per CTA in window mode the epilogue of one overlaps the mainloop of the other (a 64-column
         // MMA costs ~0.65 of a 128-column one): 2106 active columns 855 -> 712 us per window, 1753: 832 -> 648
-        return tc_narrow ? 1 : 0;
+        // ... as long as the 128-column tiles would leave a quarter of the SMs idle (reduced iteration, C4: 2048 columns
+        // = 80 tiles: window 0.57 -> 0.47 ms with 64-column tiles; 3072 = 120 tiles: equal; 3569 = 140 tiles: 3 % slower)
+        return (tc_narrow && nact_host[3] * n_row_tiles * 4 <= sm_count * 3) ? 1 : 0;
     };
     // pdl: this launch directly follows another 1-CTA tcgen05 iteration kernel of the same window
     // One launch = `steps` iterations starting from buffer `src`.  steps > 1 is the window mode of the 1-CTA

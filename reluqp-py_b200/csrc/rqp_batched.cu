@@ -875,7 +875,7 @@ static BatchLayout batch_layout(const rqp_problem* p, int B, int ldv, bool with_
     l.off_tile = take(size_t(l.n_tiles) * 4);
     l.off_btab = take(64 * 4);
     // window kernel: one completion counter per (column tile, row tile of the iteration matrix) + the ticket counter
-    l.off_done = take((size_t(l.cap / 32 + 1) * size_t((D + 127) / 128) + 1) * 4);
+    l.off_done = take((size_t(l.cap / 32 + 1) * size_t((D + 127) / 128 + 1) + 1) * 4);
     // split-K of the tcgen05 kernels (fewer tiles than SMs): one work item per SM at most
     l.off_kcnt = take(planes ? size_t(kMaxSplitItems) * 16 * 4 : 0);     // [tiles][epilogue warps <= 16]
     l.off_scratch = take(planes ? size_t(kMaxSplitItems) * 128 * 128 * 4 : 0);
@@ -1143,7 +1143,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
             const int bound = nact_host[3 - b] * a.n_row_tiles * a.ksplit;
             if (steps > 1) {
                 a.done = reinterpret_cast<unsigned int*>(w8 + lay.off_done);
-                const size_t n_done = size_t(cap / 32 + 1) * size_t((D + 127) / 128);
+                const size_t n_done = size_t(cap / 32 + 1) * size_t((D + 127) / 128 + 1);
                 RQP_CUDA_TRY(cudaMemsetAsync(a.done, 0, (n_done + 1) * 4, st));
                 const int grid = bound < sm_count ? bound : sm_count;
                 if (bound > grid) {

@@ -626,8 +626,9 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                     // needs EVERY row tile of iteration i complete.)  First tile of a PDL launch: the previous
                     // kernel is waited for before the first state-plane load.
                     const uint32_t need = uint32_t(it) * Cfg::EPI_WARPS;
-                    const uint32_t* cnt = (a.done != nullptr && it > 0) ? a.done + size_t(t / a.n_row_tiles) * a.n_row_tiles
-                                                                        : nullptr;
+                    // counters of a column tile: one per row tile, then the total over all its row tiles
+                    const uint32_t* cnt = (a.done != nullptr && it > 0)
+                                              ? a.done + size_t(t / a.n_row_tiles) * (a.n_row_tiles + 1) : nullptr;
                     int ready_rt = 0;                       // row tiles of the previous iteration known complete
                     const int nrt = a.n_row_tiles <= 16 ? a.n_row_tiles : 1;   // (more than 16 row tiles: poll one at a time)
                     // one round trip polls ALL outstanding counters of the column tile (independent relaxed loads; the
@@ -642,8 +643,17 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                             if (r2 == ready_rt && r2 < a.n_row_tiles && c16[r2] >= need) ++ready_rt;
                     };
                     if (cnt != nullptr) {
-                        if (a.n_row_tiles <= 16) poll();
-                        fence_acq_rel_gpu();
+                        // fast path (plenty of columns: the previous iteration of this column tile is long complete):
+                        // one acquire load of the total, exactly what a per-column-tile dependency costs; only a tile
+                        // that really has to wait polls the row tiles (the fence that turns those relaxed polls into
+                        // an acquire stalls behind the SM's outstanding epilogue stores: -9 % at 65536 columns when it
+                        // sat on every tile's path)
+                        if (ld_acquire_u32(cnt + a.n_row_tiles) >= need * uint32_t(a.n_row_tiles)) {
+                            ready_rt = a.n_row_tiles;
+                        } else {
+                            if (a.n_row_tiles <= 16) poll();
+                            fence_acq_rel_gpu();
+                        }
                         fence_proxy_async_all();
                     }
                     int w_issued = 0;
@@ -799,12 +809,10 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                 // of the iteration order the other ranks get from their operand dependency
                 if (a.done != nullptr && it > 0) {
                     const uint32_t need = uint32_t(it) * Cfg::EPI_WARPS;
-                    const uint32_t* cnt = a.done + size_t(t / a.n_row_tiles) * a.n_row_tiles;
-                    for (int r2 = 0; r2 < a.n_row_tiles; ++r2) {
-                        uint32_t spins = 0;
-                        while (ld_acquire_u32(cnt + r2) < need) {
-                            if (++spins > (1u << 24)) __trap();
-                        }
+                    const uint32_t* cnt = a.done + size_t(t / a.n_row_tiles) * (a.n_row_tiles + 1) + a.n_row_tiles;
+                    uint32_t spins = 0;
+                    while (ld_acquire_u32(cnt) < need * uint32_t(a.n_row_tiles)) {
+                        if (++spins > (1u << 24)) __trap();
                     }
                 }
 #pragma unroll
@@ -923,9 +931,14 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                 __syncwarp();
                 if (lane == 0) {
                     // one counter per (column tile, row tile)
-                    uint32_t* dcnt = a.done + size_t(t / a.n_row_tiles) * a.n_row_tiles + rt;
-                    if (a.xflags & 1) red_release_add_u32(dcnt, 1u);
-                    else red_relaxed_add_u32(dcnt, 1u);
+                    uint32_t* dcnt = a.done + size_t(t / a.n_row_tiles) * (a.n_row_tiles + 1);
+                    if (a.xflags & 1) {
+                        red_release_add_u32(dcnt + rt, 1u);
+                        red_release_add_u32(dcnt + a.n_row_tiles, 1u);
+                    } else {
+                        red_relaxed_add_u32(dcnt + rt, 1u);
+                        red_relaxed_add_u32(dcnt + a.n_row_tiles, 1u);
+                    }
                 }
             }
             const long long te = clock64();

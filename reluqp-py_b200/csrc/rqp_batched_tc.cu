@@ -178,7 +178,14 @@ __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol
 
 // Cross-CTA dataflow of the window kernel: a consumer's TMA (async proxy) reads what another CTA's
 // epilogue wrote with ordinary stores (generic proxy).
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Generic-proxy stores (an epilogue's state planes) <-> async-proxy reads (another CTA's TMA) of GLOBAL memory.  The
+// unqualified `fence.proxy.async` compiles to MEMBAR.ALL.GPU + FENCE.VIEW.ASYNC.S -- a second full memory barrier per
+// lane next to the release / acquire fence that is there anyway; the .global form is the one view fence
+// (FENCE.VIEW.ASYNC.G).  RQP_TC_XFLAGS=8 restores the unqualified form.
+__device__ __forceinline__ void fence_proxy_async_all(int heavy = 0) {
+    if (heavy) asm volatile("fence.proxy.async;" ::: "memory");
+    else asm volatile("fence.proxy.async.global;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -654,7 +661,7 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                             if (a.n_row_tiles <= 16) poll();
                             fence_acq_rel_gpu();
                         }
-                        fence_proxy_async_all();
+                        fence_proxy_async_all(a.xflags & 8);
                     }
                     int w_issued = 0;
                     uint32_t wst = stage, wph = phase;
@@ -703,7 +710,7 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                                 waited = true;
                                 fence_acq_rel_gpu();
                             }
-                            if (waited) fence_proxy_async_all();   // acquire above -> TMA reads below
+                            if (waited) fence_proxy_async_all(a.xflags & 8);   // acquire above -> TMA reads below
                         }
                         unsigned char* sp = base + size_t(stage) * STAGE_BYTES;
                         tma_load_2d(sp + 2 * TC_TILE_BYTES, mxh, kb * TC_BK, xrow, full + stage);
@@ -927,7 +934,7 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                 // barrier orders the lanes, lane 0's relaxed add then completes the release pattern.
                 if (a.xflags & 1) __threadfence();
                 else fence_acq_rel_gpu();
-                fence_proxy_async_all();
+                fence_proxy_async_all(a.xflags & 8);
                 __syncwarp();
                 if (lane == 0) {
                     // one counter per (column tile, row tile)

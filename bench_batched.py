@@ -147,7 +147,7 @@ def _measure(m, args, rank, world, dev, B_local, B_total, steps, warmup, flush, 
 # (B, element bytes, engine, reduced iteration?) -> (bytes, file under profiles/)
 TRAFFIC = {
     (4096, 4, 0, False): (500.15e6 + 687.35e6, "profiles/r02_batched_window_ncu_full.csv"),
-    (4096, 4, 0, True): (223.39e6 + 411.90e6, "profiles/r02e_batched_window_ncu_full.csv"),
+    (4096, 4, 0, True): (143.63e6 + 368.77e6, "profiles/r02f_batched_window_ncu_full.csv"),
 }
 
 

@@ -244,19 +244,23 @@ struct EpiRow {
 // its own output column, which nobody reads.
 // Fast path (warp-uniform): a warp whose 32 rows are all x rows (dense layer: also lambda rows) has no bounds, no
 // lambda+ and no slot -> column map to fetch: bias, TF32 split, stores.
-template <bool RED, bool PLAIN, bool GCOL>
+// GW: columns per load group (8 on the 576-thread kernel with its 96 registers, 16 on the narrow-tile kernels: half
+// the dependent round trips for the bounds / lambda+ where a tile's latency is the whole iteration).
+// ncol: how many of the warp's 32 columns are real columns of the bucket (the last tile of a bucket is partial; in
+// the straggler windows a tile holds a handful): groups past them are skipped.
+template <bool RED, bool PLAIN, bool GCOL, int GW>
 __device__ __forceinline__ void tc_epilogue_chunk(const TcArgs& a, const EpiRow& e, const uint32_t (&r)[32], int n0,
-                                                  int lane) {
+                                                  int ncol) {
     // Addressing: every per-column address is (64-bit base of this thread's row) + (32-bit element offset): one
     // IMAD.WIDE.U32 per access instead of the four-instruction 64-bit pointer increments ptxas generates otherwise.
     // All offsets fit 32 bits (slots x ldv, columns x nc, slots x D < 2^31).
-    constexpr int GW = 8;
     const unsigned ldv = unsigned(a.ldv), nc = unsigned(a.nc), Dg = unsigned(a.D);
     if (!__any_sync(0xffffffffu, e.is_z)) {
         if (!e.m_ok) return;
         unsigned off = unsigned(n0) * ldv;
 #pragma unroll
         for (int h = 0; h < 32 / GW; ++h) {
+            if (h * GW >= ncol) break;
             float bc[GW];
 #pragma unroll
             for (int j = 0; j < GW; ++j) bc[j] = GCOL ? __ldg(e.bcol + unsigned(n0 + h * GW + j) * Dg) : e.bias_shared;
@@ -272,10 +276,11 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcArgs& a, const EpiRow&
         }
         return;
     }
-    const int o_lane = max(__ldg(a.orig + n0 + lane), 0);
+    const int o_lane = max(__ldg(a.orig + n0 + (threadIdx.x & 31)), 0);
     unsigned off = unsigned(n0) * ldv, loff = unsigned(n0) * nc;
 #pragma unroll
     for (int h = 0; h < 32 / GW; ++h) {
+        if (h * GW >= ncol) break;
         float lo[GW], hi[GW], bc[GW], lp[GW];
 #pragma unroll
         for (int j = 0; j < GW; ++j) {
@@ -320,14 +325,14 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcArgs& a, const EpiRow&
         }
     }
 }
-template <bool RED>
+template <bool RED, int GW>
 __device__ __forceinline__ void tc_epilogue_dispatch(const TcArgs& a, const EpiRow& e, const uint32_t (&r)[32], int n0,
-                                                     int lane) {
+                                                     int ncol) {
     const bool plain = e.pp != nullptr, gcol = a.bias_cols != nullptr;      // uniform over the launch / the tile
-    if (!plain && !gcol) tc_epilogue_chunk<RED, false, false>(a, e, r, n0, lane);
-    else if (plain && !gcol) tc_epilogue_chunk<RED, true, false>(a, e, r, n0, lane);
-    else if (!plain) tc_epilogue_chunk<RED, false, true>(a, e, r, n0, lane);
-    else tc_epilogue_chunk<RED, true, true>(a, e, r, n0, lane);
+    if (!plain && !gcol) tc_epilogue_chunk<RED, false, false, GW>(a, e, r, n0, ncol);
+    else if (plain && !gcol) tc_epilogue_chunk<RED, true, false, GW>(a, e, r, n0, ncol);
+    else if (!plain) tc_epilogue_chunk<RED, false, true, GW>(a, e, r, n0, ncol);
+    else tc_epilogue_chunk<RED, true, true, GW>(a, e, r, n0, ncol);
 }
 
 __device__ __forceinline__ EpiRow make_epi_row(const TcArgs& a, int m, int rho, float* yh, float* yl, float* yp) {
@@ -369,6 +374,19 @@ __device__ __forceinline__ bool tc_tile_lookup(const int* sb, int t, int n_row_t
         ct -= nct;
     }
     return false;
+}
+// Real columns of the bucket in column tile t / n_row_tiles (the last tile of a bucket is partial).
+template <int BN>
+__device__ __forceinline__ int tc_tile_cols(const int* sb, int t, int n_row_tiles) {
+    int ct = t / n_row_tiles;
+    const int nb = sb[0];
+    for (int i = 0; i < nb; ++i) {
+        const int cnt = sb[3 + 3 * i];
+        const int nct = (cnt + BN - 1) / BN;
+        if (ct < nct) return min(BN, cnt - ct * BN);
+        ct -= nct;
+    }
+    return 0;
 }
 // The k-blocks (32 state columns each) a work item runs over, in ascending order: either a plain range
 // [kb, kb_hi) or, when the caller supplied block masks (TcArgs::kmask, at most 64 k-blocks), the set bits of
@@ -434,14 +452,14 @@ __device__ __forceinline__ void tc_tile_rows(const TcArgs& a, int rho, int rt, i
 }
 
 // Residual epilogue: the accumulator goes out as plain fp32, Out[slot][m] (ld = a.ldv).
-__device__ __forceinline__ void tc_epilogue_raw(const TcArgs& a, int m, const uint32_t (&r)[32], int n0, int lane) {
-    (void)lane;
+__device__ __forceinline__ void tc_epilogue_raw(const TcArgs& a, int m, const uint32_t (&r)[32], int n0, int ncol) {
     if (m >= a.M) return;
     float* pp = a.Yplain + m;
     unsigned off = unsigned(n0) * unsigned(a.ldv);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        pp[off] = __uint_as_float(r[j]);      // padding slots included: their rows of the result buffer are never read
+        if (j >= ncol) break;
+        pp[off] = __uint_as_float(r[j]);
         off += unsigned(a.ldv);
     }
 }
@@ -918,12 +936,16 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
             if (!a.raw)
                 e = make_epi_row(a, m, rho, (it & 1) ? a.Yh_alt : a.Yh, (it & 1) ? a.Yl_alt : a.Yl,
                                  it == a.steps - 1 ? a.Yplain : nullptr);
+            const int tile_cols = tc_tile_cols<BN>(sb, t, a.n_row_tiles);
+            constexpr int GWB = BN == 128 ? 8 : 16;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                const int n0 = col0 + half * Cfg::COLS_PER_EPI_WARP + c * 32;
-                if (a.raw) tc_epilogue_raw(a, m, sum[c], n0, lane);
-                else if (a.reduced) tc_epilogue_dispatch<true>(a, e, sum[c], n0, lane);
-                else tc_epilogue_dispatch<false>(a, e, sum[c], n0, lane);
+                const int cw = half * Cfg::COLS_PER_EPI_WARP + c * 32;      // this warp's first column within the tile
+                const int n0 = col0 + cw;
+                const int ncol = max(0, min(32, tile_cols - cw));
+                if (a.raw) tc_epilogue_raw(a, m, sum[c], n0, ncol);
+                else if (a.reduced) tc_epilogue_dispatch<true, GWB>(a, e, sum[c], n0, ncol);
+                else tc_epilogue_dispatch<false, GWB>(a, e, sum[c], n0, ncol);
             }
             const long long tf0 = clock64();
             if (a.done != nullptr) {

@@ -1178,6 +1178,9 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
             bgemm_simt<T, EPI_ITER><<<dim3((Dit + GM - 1) / GM, cap / GN), 256, 0, st>>>(a);
         }
     };
+    // the residual launch follows the window kernel directly: as a programmatic dependent its prologue (TMEM
+    // allocation, barrier init, the first ring of residual-operator planes) overlaps the window kernel's tail
+    const bool raw_pdl = pdl_ok && getenv("RQP_NO_RAW_PDL") == nullptr;
     auto gemm_res_tc = [&](int src) -> int {
         TcArgs a;
         a.tile_rho = c.tile_rho; a.btab = c.btab; a.orig = c.orig[lcur];
@@ -1197,7 +1200,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         if (rc1 != RQP_OK) return rc1;
         const int bound = nact_host[3 - b] * a.n_row_tiles * a.ksplit;
         return tc_launch(map_wh, map_wl, map_xh[b][src], map_xl[b][src], map_xh[b][src], map_xl[b][src], a, kBoxRows[b],
-                         bound, false, sm_count, st);
+                         bound, raw_pdl, sm_count, st);
     };
     auto gemm_res = [&](int src) {
         GemmArgs<T> a;

@@ -26,6 +26,9 @@
 #ifndef RQP_TC_STAGES128
 #define RQP_TC_STAGES128 0   // experiment switch: smem ring depth of the 128-column kernel (0 = default 3)
 #endif
+#ifndef RQP_TC_GW128
+#define RQP_TC_GW128 8        // columns per load group in the epilogue of the 576-thread kernel (96 registers)
+#endif
 #ifndef RQP_TC_EXP
 #define RQP_TC_EXP 0          // timing experiments (WRONG results): 1 = no bound / lambda+ loads, 2 = no stores
 #endif
@@ -937,7 +940,7 @@ rqp_batched_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_c
                 e = make_epi_row(a, m, rho, (it & 1) ? a.Yh_alt : a.Yh, (it & 1) ? a.Yl_alt : a.Yl,
                                  it == a.steps - 1 ? a.Yplain : nullptr);
             const int tile_cols = tc_tile_cols<BN>(sb, t, a.n_row_tiles);
-            constexpr int GWB = BN == 128 ? 8 : 16;
+            constexpr int GWB = BN == 128 ? RQP_TC_GW128 : 16;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 const int cw = half * Cfg::COLS_PER_EPI_WARP + c * 32;      // this warp's first column within the tile

@@ -108,6 +108,24 @@ __device__ __forceinline__ void put_operand(T* dh, T* dl, int i, T v, int tc) {
 // ------------------------------------------------------------------------------------------------
 // init: all columns start from v = 0 at their given rho index, one bucket per distinct index
 // ------------------------------------------------------------------------------------------------
+// The small kernels of a check pass (check, scan, scatter) are launched as programmatic dependents of whatever precedes
+// them in the stream: their launch latency overlaps the predecessor's tail; nothing is touched before this wait.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... Params, typename... Args>
+static void launch_pdl(void (*kern)(Params...), dim3 grid, dim3 block, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, Params(args)...);
+}
+
 template <typename T>
 __global__ void batch_init_keys(BatchCtx<T> c) {
     // slots of buffer 1 hold the columns in original order; keys = their rho index
@@ -136,6 +154,7 @@ __global__ void batch_hist(const int* __restrict__ key, int cap, int* counts) {
 // one thread: aligned bucket starts, tile table, number of active columns
 __global__ void batch_scan(int* counts, int* starts, int* cursor, int* tile_rho, int* btab, int n_rho,
                            int n_tiles, int* n_active, int* n_active_host) {
+    pdl_wait();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int pos = 0, total = 0, t = 0, nb = 0, t32 = 0, t64 = 0, t128 = 0;
     for (int r = 0; r < n_rho; ++r) {
@@ -171,6 +190,7 @@ __global__ void batch_scan(int* counts, int* starts, int* cursor, int* tile_rho,
 template <typename T>
 __global__ void batch_scatter(BatchCtx<T> c, int vsrc, int src, int iter_now, int status_if_out, int copy_state) {
     // vsrc: V buffer holding the current state; src: current layout.  Destination = the other ones.
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (j >= c.cap) return;
@@ -736,6 +756,7 @@ __device__ __forceinline__ double t_sqrt_b<double>(double x) { return sqrt(x); }
 
 template <typename T>
 __global__ void batch_check(BatchCtx<T> c, int vbuf, int buf, int final_pass) {
+    pdl_wait();
     // vbuf: V buffer with the iterate to check; buf: current layout.  Also the first two steps of the
     // regroup that follows: the histogram of the new keys (counts[] is zero on entry: batch_scan clears it
     // after reading) and the reset of the OTHER layout's slot map, which the scatter fills next.
@@ -982,6 +1003,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     // regroup: key[] filled for the current layout -> histogram, aligned starts, scatter into the
     // other V buffer / other layout; both indices flip
     // after_check: batch_check already built the histogram and reset the other layout's slot map
+    const bool small_pdl = getenv("RQP_NO_PDL") == nullptr && getenv("RQP_NO_SMALL_PDL") == nullptr;
     auto regroup = [&](int iter_now, int status_out, int copy_state, bool after_check) -> int {
         if (!after_check) {
             RQP_CUDA_TRY(cudaMemsetAsync(c.counts, 0, size_t(c.n_rho) * 4, st));
@@ -989,9 +1011,10 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
             batch_hist<<<(cap + thr - 1) / thr, thr, 0, st>>>(c.key, cap, c.counts);
             note_launch();
         }
-        batch_scan<<<1, 32, 0, st>>>(c.counts, c.starts, c.cursor, c.tile_rho, c.btab, c.n_rho, lay.n_tiles,
-                                     c.n_active, c.n_active_host);
-        batch_scatter<T><<<warp_blocks, thr, 0, st>>>(c, cur, lcur, iter_now, status_out, copy_state);
+        launch_pdl(batch_scan, dim3(1), dim3(32), st, small_pdl, c.counts, c.starts, c.cursor, c.tile_rho, c.btab, c.n_rho,
+                   lay.n_tiles, c.n_active, c.n_active_host);
+        launch_pdl(batch_scatter<T>, dim3(warp_blocks), dim3(thr), st, small_pdl, c, cur, lcur, iter_now, status_out,
+                   copy_state);
         note_launch(2);
         RQP_CUDA_TRY(cudaGetLastError());
         cur ^= 1;
@@ -1312,7 +1335,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
             } else {
                 gemm_res(cur);
             }
-            batch_check<T><<<warp_blocks, thr, 0, st>>>(c, cur, lcur, 0);
+            launch_pdl(batch_check<T>, dim3(warp_blocks), dim3(thr), st, small_pdl, c, cur, lcur, 0);
             note_launch();
             rc = regroup(k, RQP_STATUS_SOLVED, 1, true);
             if (rc != RQP_OK) return rc;
@@ -1330,7 +1353,7 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
         } else {
             gemm_res(cur);
         }
-        batch_check<T><<<warp_blocks, thr, 0, st>>>(c, cur, lcur, 1);
+        launch_pdl(batch_check<T>, dim3(warp_blocks), dim3(thr), st, small_pdl, c, cur, lcur, 1);
         note_launch();
         rc = regroup(stng->max_iter, RQP_STATUS_MAX_ITER, 1, true);
         if (rc != RQP_OK) return rc;

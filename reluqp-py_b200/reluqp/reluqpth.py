@@ -40,6 +40,25 @@ def _round_up(n, m):
     return (n + m - 1) // m * m
 
 
+class _NoGuard(object):
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _on_device(device):
+    """``torch.cuda.device(device)`` only when another device is current: torch's guard costs several microseconds
+    per use (8 us of an 87 us MPC control step went to it), the check a fraction of one."""
+    if device.type != "cuda" or torch.cuda.current_device() == device.index:
+        return _NO_GUARD
+    return torch.cuda.device(device)
+
+
 class _Timer(object):
     """CUDA events on a CUDA device (what the reference uses, ``reluqpth.py:99-100``); host
     clock otherwise.  Seconds."""
@@ -55,14 +74,14 @@ class _Timer(object):
     def tic(self):
         self.t0 = time.perf_counter()
         if self.cuda:
-            with torch.cuda.device(self.device):      # events belong to the solver's device, whatever is current
+            with _on_device(self.device):      # events belong to the solver's device, whatever is current
                 self.start.record()
 
     def toc(self, sync=True):
         """Seconds since tic().  sync=False (update): do not block the host; the time is the host
         time spent enqueueing, the device part is absorbed by the following solve's run_time."""
         if self.cuda and sync:
-            with torch.cuda.device(self.device):
+            with _on_device(self.device):
                 self.end.record()
             self.end.synchronize()
             return self.start.elapsed_time(self.end) / 1000.0
@@ -590,7 +609,7 @@ class ReLU_QP(object):
             L = self.layers
             self._g_updated = True          # the batched path re-forms its reduced bias from the live g
             if self._engine is not None:
-                with torch.cuda.device(st.device):
+                with _on_device(st.device):
                     rc = self._engine.lib.rqp_update_bias(
                         _cabi.dtype_code(st.precision), len(L.rho_list), L.B_all.shape[1], self.QP.nx,
                         L.B_all.data_ptr(), self.QP.g.data_ptr(), L.b_all.data_ptr(),
@@ -695,7 +714,7 @@ class ReLU_QP(object):
         if not eng.mapped:
             raise RuntimeError("resolve() needs the mapped result record (RQP_RESULT_MAPPED=1)")
         self._glu_pending = hi > lo     # if the call fails after enqueueing the copy, the next _stage() must wait
-        with torch.cuda.device(st.device):
+        with _on_device(st.device):
             rc = eng.lib.rqp_resolve(C.byref(eng.prob), C.byref(eng.stng), C.byref(eng.state),
                                      eng.res_host.data_ptr(), None, 0, eng.ws.data_ptr(), eng.ws.numel(),
                                      self._glu_ptr + lo * es, self._glu_host_ptr + lo * es, (hi - lo) * es,
@@ -751,8 +770,13 @@ class ReLU_QP(object):
         state.epoch = eng.epoch
         eng._arm_post(xh)
         lib = eng.lib
-        with torch.cuda.device(st.device):
-            stream = _cabi.raw_stream(st.device.index)
+        dev_index = st.device.index
+        # (the device guard of torch costs microseconds: only when another device is current)
+        guard = torch.cuda.device(st.device) if torch.cuda.current_device() != dev_index else None
+        if guard is not None:
+            guard.__enter__()
+        try:
+            stream = _cabi.raw_stream(dev_index)
             if lo is not None:
                 rc = lib.rqp_copy_h2d(self._glu_ptr + lo * es, self._glu_host_ptr + lo * es, (hi - lo) * es, stream)
                 if rc != 0:
@@ -765,13 +789,19 @@ class ReLU_QP(object):
                                    eng.ws_ptr, eng.ws_bytes, stream)
             if rc != 0:
                 _cabi.check(rc, "rqp_solve")
+        finally:
+            if guard is not None:
+                guard.__exit__(None, None, None)
         eng.epoch = int(state.epoch)
         r = eng.finish()
         info = self.results.info
         info.update_time = 0.0
         self.rho_ind = int(r.rho_ind)
         out = self.output
-        self.x, self.z, self.lam = out[:nx], out[nx:nx + nc], out[nx + nc:nx + 2 * nc]
+        if getattr(self, "_views_of", None) is not out:          # x, z, lambda stay views of the same state vector
+            self._views = (out[:nx], out[nx:nx + nc], out[nx + nc:nx + 2 * nc])
+            self._views_of = out
+        self.x, self.z, self.lam = self._views
         self.results.x_host = self._x_host_np
         self.update_results(iter=int(r.iter), status=STATUS_NAMES[int(r.status)], pri_res=r.pri_res,
                             dua_res=r.dua_res, rho_estimate=r.rho_estimate, obj_val=r.obj_val)

@@ -1053,7 +1053,16 @@ static int run_batched(const rqp_problem* prob, const rqp_settings* stng, rqp_ba
     const int tc_chunk_env = getenv("RQP_TC_CHUNK") ? atoi(getenv("RQP_TC_CHUNK")) : -1;
     const bool tc_chunk_all_env = getenv("RQP_TC_CHUNK_ALL") != nullptr;
     const int tc_escalate_k = getenv("RQP_TC_ESCALATE") ? atoi(getenv("RQP_TC_ESCALATE")) : 8 * stng->check_interval;
-    int tc_chunk = tc_chunk_env >= 0 ? tc_chunk_env : 2;
+    // Base chunk (RQP_TC_CHUNK0 overrides it and keeps the escalation, RQP_TC_CHUNK fixes it for the whole solve):
+    // 2 k-blocks for the dense layer (K = 960 at C4: chunks of 5 or more lose the effect).  The reduced iteration has
+    // shorter rows and its 1e3 rho sits in the elementwise step, not in the products: measured at C4 (K = 640 = 20
+    // k-blocks), chunks of 2 / 4 / 5 / 6 / 8 k-blocks all need 108.5-108.9 iterations on average (10 and 20: 121.9) while
+    // a full window takes 0.643 / 0.614 / 0.607 / 0.611 / 0.608 ms -- so a quarter of the row's k-blocks per chunk (each
+    // chunk of a tile then has its own TMEM stage), at least 2, at most 6.
+    const int tc_chunk0_env = getenv("RQP_TC_CHUNK0") ? atoi(getenv("RQP_TC_CHUNK0")) : -1;
+    const int nkb_it = (Dit + 31) / 32;
+    const int tc_chunk0 = reduced ? (nkb_it + 3) / 4 < 2 ? 2 : ((nkb_it + 3) / 4 > 6 ? 6 : (nkb_it + 3) / 4) : 2;
+    int tc_chunk = tc_chunk_env >= 0 ? tc_chunk_env : (tc_chunk0_env >= 0 ? tc_chunk0_env : tc_chunk0);
     bool tc_chunk_x = !tc_chunk_all_env;
     // tensor maps: W planes (128-row boxes) and the state planes with 128 / 64 / 32-row boxes
     // (reduced iteration: the iteration launches read the operand planes through maps that END at nx + nc -- the

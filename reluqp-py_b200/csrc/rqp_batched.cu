@@ -659,9 +659,12 @@ struct DmmaLaunch<double, EPI> {
         constexpr size_t smem = ring > red ? ring : red;
         static bool attr_set[kMaxDevices] = {};
         const int dev = current_device_slot();
-        if (!attr_set[dev]) {
-            cudaFuncSetAttribute(bgemm_dmma<EPI, WM, WN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-            attr_set[dev] = true;
+        {
+            std::lock_guard<std::mutex> lk(attr_mutex());
+            if (!attr_set[dev]) {
+                cudaFuncSetAttribute(bgemm_dmma<EPI, WM, WN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+                attr_set[dev] = true;
+            }
         }
         bgemm_dmma<EPI, WM, WN, KS>
             <<<dim3((Mrows + 32 * WM - 1) / (32 * WM), cap / (64 * WN)), 32 * WM * WN * KS, smem, st>>>(a);

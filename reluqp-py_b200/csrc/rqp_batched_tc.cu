@@ -1028,10 +1028,13 @@ static int tc_launch_bn(const CUtensorMap& wh, const CUtensorMap& wl, const CUte
     static bool attr_set[kMaxDevices] = {};
     const int dev = current_device_slot();
     auto kern = rqp_batched_tc_kernel<BN>;
-    if (!attr_set[dev]) {
-        RQP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          int(TcCfg<BN>::SMEM_BYTES)));
-        attr_set[dev] = true;
+    {
+        std::lock_guard<std::mutex> lk(attr_mutex());
+        if (!attr_set[dev]) {
+            RQP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              int(TcCfg<BN>::SMEM_BYTES)));
+            attr_set[dev] = true;
+        }
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(grid));

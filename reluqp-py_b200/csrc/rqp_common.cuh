@@ -1,5 +1,6 @@
 // Device-side helpers shared by the ReLU-QP kernels (sm_100a only).
 #pragma once
+#include <mutex>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -27,6 +28,12 @@ void note_launch(int n = 1);
 // Function attributes (dynamic shared memory opt-in) are per device: a process that drives several
 // GPUs must set them once on each, so the "already done" caches are indexed by the current device.
 constexpr int kMaxDevices = 64;
+// The per-device "attribute already set" caches of the launch wrappers are plain statics shared by all host threads:
+// their check-and-set sections take this lock (uncontended: tens of nanoseconds).
+inline std::mutex& attr_mutex() {
+    static std::mutex m;
+    return m;
+}
 inline int current_device_slot() {
     int d = 0;
     cudaGetDevice(&d);

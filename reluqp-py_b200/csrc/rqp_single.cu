@@ -1181,6 +1181,7 @@ static bool tiny_ok(const rqp_problem* prob, const rqp_settings* stng) {
 template <typename T, int TR>
 static int launch_tiny_tr(const SingleParams& prm, size_t smem, cudaStream_t stream) {
     static size_t ok_dev[kMaxDevices] = {};
+    std::lock_guard<std::mutex> attr_lock(attr_mutex());   // the cache below is shared by all host threads
     size_t& okb = ok_dev[current_device_slot()];
     if (smem > okb) {       // more than 48 KB of dynamic shared memory needs the opt-in, once per device
         RQP_CUDA_TRY(cudaFuncSetAttribute(rqp_tiny_kernel<T, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -1343,6 +1344,7 @@ template <typename T, int CPT>
 static int launch_cluster(const SingleParams& prm, const SinglePlan& plan, cudaStream_t stream) {
     auto kern = rqp_single_kernel<T, CPT, 256, true, 8>;
     static size_t smem_ok_dev[kMaxDevices] = {};
+    std::lock_guard<std::mutex> attr_lock(attr_mutex());   // the cache below is shared by all host threads
     size_t& smem_ok = smem_ok_dev[current_device_slot()];
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(plan.grid));
@@ -1376,6 +1378,7 @@ static int launch_one(const SingleParams& prm, const SinglePlan& plan, cudaStrea
     // per-instantiation cache of the largest dynamic shared memory size already opted into (and
     // checked to be launchable); saves two runtime calls per solve
     static size_t smem_ok_dev[kMaxDevices] = {};
+    std::lock_guard<std::mutex> attr_lock(attr_mutex());   // the cache below is shared by all host threads
     size_t& smem_ok = smem_ok_dev[current_device_slot()];
     if (plan.smem_bytes > smem_ok || smem_ok == 0) {
         RQP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes)));

@@ -542,6 +542,7 @@ template <typename T>
 static int launch_struct_t(const StructParams& prm, const StructPlan& plan, cudaStream_t stream) {
     auto kern = rqp_struct_kernel<T>;
     static size_t smem_ok_dev[kMaxDevices] = {};
+    std::lock_guard<std::mutex> attr_lock(attr_mutex());   // the cache below is shared by all host threads
     size_t& smem_ok = smem_ok_dev[current_device_slot()];
     if (plan.smem_bytes > smem_ok) {
         RQP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes)));
